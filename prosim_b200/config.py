@@ -1,0 +1,125 @@
+"""The slice of the reference's yacs config the rollout path reads.
+
+Key names and values follow prosim_demo/cfg/waymo_demo.yaml (the only released
+model shape) layered over prosim/config/default.py; ``get_config`` mirrors the
+reference's entry point of the same name (config/default.py:690-733) including the
+derived ``TARGET.ELEMENTS += ',xd,yd'`` patch for PRED_VEL (:725-730).  A real yacs
+node from the reference can be passed to ``ProSimB200`` instead: only attribute
+access is used.
+"""
+import copy
+
+
+class Config(dict):
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError:
+            raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        self[name] = value
+
+    def clone(self):
+        return copy.deepcopy(self)
+
+    def merge_from_list(self, opts):
+        assert len(opts) % 2 == 0
+        for key, val in zip(opts[0::2], opts[1::2]):
+            node = self
+            parts = key.split('.')
+            for p in parts[:-1]:
+                node = node[p]
+            node[parts[-1]] = val
+
+
+def _wrap(d):
+    return Config({k: _wrap(v) if isinstance(v, dict) else v for k, v in d.items()})
+
+
+_ATTN = dict(LEARNABLE_PE=False, NUM_LAYER=6, NUM_HEAD=8, FF_DIM=16, DROPOUT=0.1, PE_NUM_FREQ=64)
+
+_DEFAULTS = {
+    'TASK': {'TYPES': ['motion_pred'], 'MOTION_PRED': {'PROMPT': 'agent_status'}},
+    'PROMPT': {
+        'AGENT_STATUS': {'USE_VEL': True, 'USE_EXTEND': True, 'USE_AGENT_TYPE': True},
+        'CONDITION': {'TYPES': [], 'EVAL_COND_SETS': []},
+    },
+    'ROLLOUT': {
+        'PARALLEL_NUM': 1,
+        'POLICY': {'REPLAN_FREQ': 10, 'TOP_K': 1, 'TOP_K_TRAIN': 1, 'MAX_STEPS': 80},
+    },
+    'LOSS': {'ROLLOUT_TRAJ': {'USE_GOAL_PRED_LOSS': True}},
+    'DATASET': {
+        'USE_PED_CYCLIST': True,
+        'MOTION': {'DT': 0.1},
+        'FORMAT': {
+            'MAP': {'MAX_POINTS': 2048, 'WITH_TYPE_EMB': True, 'WITH_DIR': True},
+            'TARGET': {'SAMPLE_RATE': 10, 'STEPS': 10, 'ELEMENTS': 'x,y,h', 'TAIL_PADDING': True},
+            'HISTORY': {'ELEMENTS': 'x,y,s,c,xd,yd,xdd,ydd', 'STEPS': 11, 'WITH_EXTEND': True,
+                        'WITH_AGENT_TYPE': True, 'WITH_TIME_EMB': True},
+        },
+    },
+    'MODEL': {
+        'TYPE': 'prosim_b200',
+        'BPTT': False,
+        'HIDDEN_DIM': 128,
+        'REL_POS_EDGE_FUNC': 'radius',
+        'OBS_UPDATE': {'ATTN_UPDATE': False, 'FUSION': 'replace'},
+        'MAP_ENCODER': {'POINTNET': {'NUM_MLP_LAYERS': 5, 'NUM_PRE_LAYERS': 3}},
+        'OBS_ENCODER': {'POINTNET': {'NUM_MLP_LAYERS': 3, 'NUM_PRE_LAYERS': 1}},
+        'SCENE_ENCODER': {'TYPE': 'attn_fusion_relpe', 'MAP_TYPE': 'pointnet', 'OBS_TYPE': 'pointnet',
+                          'ATTN': dict(_ATTN, MAX_NUM_NEIGH=32, AGENT_RADIUS=100, SCENE_RADIUS=50)},
+        'DECODER': {'TYPE': 'attn_fusion_relpe', 'GOAL_PRED': {'ENABLE': False, 'K': 1},
+                    'ATTN': dict(_ATTN, SCENE_RADIUS=300, PROMPT_RADIUS=300, MAX_NUM_NEIGH=512)},
+        'POLICY': {'TYPE': 'rel_pe_temporal',
+                   'ACT_DECODER': {
+                       'TYPE': 'policy_no_rnn', 'RANDOM_NOISE_STD': 0.0,
+                       'MCG': {'LAYER': 3},
+                       'TRAJ': {'K': 1, 'PRED_GMM': False, 'PRED_VEL': True, 'PRED_MODE': 'anchor'},
+                       'CONTEXT': {'GOAL': False, 'EMD': True, 'GT_GOAL': False, 'USE_POSE_EMB': False},
+                       'ATTN': dict(_ATTN, AGENT_RADIUS=100, MAP_RADIUS=50, MAX_NUM_NEIGH=768, NOT_USE_MAP=False)}},
+        'CONDITION_TRANSFORMER': {'USE_TEMPORAL_ENCODING': True, 'ATTN_TYPE': 'gnn', 'NLAYER': 3, 'NHEAD': 8,
+                                  'FF_DIM': 16, 'DROPOUT': 0.1, 'COND_POOL_FUNC': 'mean',
+                                  'CONDITION_LOCATIONS': ['policy_decoder'], 'USE_PLACEHOLDER': True,
+                                  'PE': {'ENABLE': True}},
+    },
+}
+
+
+def get_config(config_paths=None, opts=None, cluster='local'):
+    """Defaults of the released demo model; ``opts`` is the reference's flat [key, value, ...] list."""
+    cfg = _wrap(copy.deepcopy(_DEFAULTS))
+    if config_paths:
+        raise NotImplementedError('yaml overlays are out of scope: pass opts or a reference yacs node')
+    if opts:
+        cfg.merge_from_list(list(opts))
+    if cfg.MODEL.POLICY.ACT_DECODER.TRAJ.PRED_VEL:
+        if 'xd,yd' not in cfg.DATASET.FORMAT.TARGET.ELEMENTS:
+            cfg.DATASET.FORMAT.TARGET.ELEMENTS = cfg.DATASET.FORMAT.TARGET.ELEMENTS + ',xd,yd'
+    return cfg
+
+
+def check_supported(cfg):
+    """Raise if a config selects a model variant outside the built path."""
+    m = cfg.MODEL
+    problems = []
+    if m.HIDDEN_DIM != 128:
+        problems.append('MODEL.HIDDEN_DIM must be 128')
+    if m.REL_POS_EDGE_FUNC != 'radius':
+        problems.append("MODEL.REL_POS_EDGE_FUNC must be 'radius'")
+    if m.OBS_UPDATE.FUSION != 'replace' or m.OBS_UPDATE.ATTN_UPDATE:
+        problems.append("MODEL.OBS_UPDATE must be FUSION='replace', ATTN_UPDATE=False")
+    for name, a in (('SCENE_ENCODER', m.SCENE_ENCODER.ATTN), ('DECODER', m.DECODER.ATTN),
+                    ('POLICY.ACT_DECODER', m.POLICY.ACT_DECODER.ATTN)):
+        if a.LEARNABLE_PE or a.NUM_HEAD != 8 or a.FF_DIM != 16:
+            problems.append(f'MODEL.{name}.ATTN must be fixed PE, 8 heads x 16')
+    t = m.POLICY.ACT_DECODER.TRAJ
+    if t.K != 1 or t.PRED_GMM or not t.PRED_VEL or t.PRED_MODE != 'anchor':
+        problems.append('MODEL.POLICY.ACT_DECODER.TRAJ must be K=1, anchor, PRED_VEL, no GMM')
+    if m.DECODER.GOAL_PRED.ENABLE:
+        problems.append('MODEL.DECODER.GOAL_PRED must be disabled')
+    if set(cfg.PROMPT.CONDITION.TYPES) - {'goal'}:
+        problems.append("PROMPT.CONDITION.TYPES may only contain 'goal'")
+    if problems:
+        raise NotImplementedError('; '.join(problems))
