@@ -1,0 +1,202 @@
+"""Seeded synthetic Waymo-shaped scenes in the exact layouts the rollout path consumes.
+
+Follows SURVEY.md section 8d: the layouts are those produced by the reference's data
+pipeline (prosim/dataset/format_utils.py:184-263 map sym-coord, :357-447 centred history,
+:667-687 future obs; dataset/prompt_utils.py:111-150 agent-status prompt;
+dataset/condition_utils.py:126-175 goal condition), the values are synthetic:
+
+  agents   position U[-75,75]^2 m, heading U[-pi,pi), speed U(0,15) m/s (20 % parked),
+           type {1:80 %, 2:10 %, 3:10 %}, constant-velocity 11-step history @0.1 s
+           expressed in each agent's own last-step frame
+  map      polyline centre U[-150,150]^2, random heading, 20 points / 0.5 m (slightly
+           curved) -> 19 vectors x 11 features in the polyline's own frame
+  fut_obs  one entry per later tick: static columns copied, motion columns empty, mask False
+           (the rollout's step_env fills them, traj_sam.py:266-270)
+
+Padding slots (ragged batches) hold NaN under a False mask, as the reference's
+``get_center_obs`` leaves them.
+"""
+import math
+
+import torch
+
+from .containers import InputMaskData, BatchDataDict, BatchPrompt, BatchCondition, SceneBatch
+
+HIST = 11
+OBS_DIM = 24
+MAP_VEC = 19
+MAP_DIM = 11
+
+
+def _rot(x, y, theta):
+    c, s = torch.cos(theta), torch.sin(theta)
+    return x * c - y * s, x * s + y * c
+
+
+def _one_scene(g, n_agents, n_map):
+    f32 = torch.float32
+    U = lambda *shape: torch.rand(*shape, generator=g, dtype=f32)
+    # ---- agents
+    pos = U(n_agents, 2) * 150.0 - 75.0
+    heading = U(n_agents) * (2 * math.pi) - math.pi
+    speed = U(n_agents) * 15.0
+    speed = torch.where(U(n_agents) < 0.2, torch.zeros_like(speed), speed)
+    tsel = U(n_agents)
+    atype = torch.where(tsel < 0.8, 1, torch.where(tsel < 0.9, 2, 3)).to(torch.int64)
+    e1, e2 = U(n_agents), U(n_agents)
+    length = torch.where(atype == 1, 4.0 + 1.2 * e1, torch.where(atype == 2, 0.6 + 0.4 * e1, 1.6 + 0.4 * e1))
+    width = torch.where(atype == 1, 1.8 + 0.4 * e2, torch.where(atype == 2, 0.6 + 0.4 * e2, 0.6 + 0.2 * e2))
+
+    obs = torch.zeros(n_agents, HIST, OBS_DIM, dtype=f32)
+    k = torch.arange(HIST, dtype=f32)
+    obs[:, :, 0] = -speed[:, None] * (HIST - 1 - k)[None, :] * 0.1
+    obs[:, :, 3] = 1.0
+    obs[:, :, 4] = speed[:, None]
+    obs[:, :, 8] = length[:, None]
+    obs[:, :, 9] = width[:, None]
+    for t in (1, 2, 3):
+        obs[:, :, 9 + t] = (atype == t).to(f32)[:, None]
+    obs[:, torch.arange(HIST), 13 + torch.arange(HIST)] = 1.0
+
+    prompt = torch.zeros(n_agents, 7, dtype=f32)
+    prompt[:, 0] = speed
+    prompt[:, 2] = length
+    prompt[:, 3] = width
+    for t in (1, 2, 3):
+        prompt[:, 3 + t] = (atype == t).to(f32)
+
+    # ---- map: arcs sampled in the world frame, then moved to the polyline's own frame
+    centre = U(n_map, 2) * 300.0 - 150.0
+    mhead = U(n_map) * (2 * math.pi) - math.pi
+    kappa = (U(n_map) - 0.5) * 0.08
+    s = (torch.arange(MAP_VEC + 1, dtype=f32) - MAP_VEC / 2.0) * 0.5
+    ang = mhead[:, None] + kappa[:, None] * s[None, :]
+    step = 0.5
+    dx = torch.cos(ang) * step
+    dy = torch.sin(ang) * step
+    px = centre[:, 0:1] + torch.cumsum(dx, dim=1) - dx
+    py = centre[:, 1:2] + torch.cumsum(dy, dim=1) - dy
+    start = torch.stack([px[:, :-1], py[:, :-1]], dim=-1)
+    end = torch.stack([px[:, 1:], py[:, 1:]], dim=-1)
+    p0, p1 = start[:, 0], end[:, -1]
+    m_heading = torch.atan2(p1[:, 1] - p0[:, 1], p1[:, 0] - p0[:, 0])
+    m_pos = (p0 + p1) / 2
+    sx, sy = _rot(start[..., 0] - m_pos[:, None, 0], start[..., 1] - m_pos[:, None, 1], -m_heading[:, None])
+    ex, ey = _rot(end[..., 0] - m_pos[:, None, 0], end[..., 1] - m_pos[:, None, 1], -m_heading[:, None])
+    msel, lsel = U(n_map), U(n_map)
+    mtype = torch.where(msel < 0.5, 1.0, torch.where(msel < 0.75, 2.0, 3.0))
+    tls = torch.where(lsel < 0.7, -1.0, torch.where(lsel < 0.8, 0.0, torch.where(lsel < 0.9, 1.0, 2.0)))
+    mp = torch.zeros(n_map, MAP_VEC, MAP_DIM, dtype=f32)
+    mp[..., 0], mp[..., 1], mp[..., 2], mp[..., 3] = sx, sy, ex, ey
+    mp[..., 4] = mtype[:, None]
+    mp[..., 5] = tls[:, None]
+    for t in (1, 2, 3):
+        mp[..., 5 + t] = (mtype == t).to(f32)[:, None]
+    diff = torch.stack([ex - sx, ey - sy], dim=-1)
+    mp[..., 9:11] = diff / torch.clip(torch.norm(diff, dim=-1, keepdim=True), min=1e-6)
+    return dict(pos=pos, heading=heading, speed=speed, atype=atype, obs=obs, prompt=prompt,
+                map=mp, map_pos=m_pos, map_heading=m_heading)
+
+
+def make_batch(n_scenes=1, n_agents=128, n_map=512, steps=80, goal=False, first_scene=0,
+               agents_per_scene=None, map_per_scene=None, permute_obs=False, pin_memory=False):
+    """Build a SceneBatch-like object on the host.
+
+    agents_per_scene / map_per_scene: optional per-scene counts (ragged batch, padded to the max).
+    permute_obs: store observation slots in a different order than the prompt slots, so the
+                 agent-id -> slot bookkeeping (traj_sam.py:245-249, 616-621) is exercised.
+    """
+    agents_per_scene = list(agents_per_scene or [n_agents] * n_scenes)
+    map_per_scene = list(map_per_scene or [n_map] * n_scenes)
+    B = len(agents_per_scene)
+    A, M = max(agents_per_scene), max(map_per_scene)
+    f32 = torch.float32
+    nan = float('nan')
+
+    obs_in = torch.full((B, A, HIST, OBS_DIM), nan, dtype=f32)
+    obs_mask = torch.zeros(B, A, HIST, OBS_DIM, dtype=torch.bool)
+    obs_pos = torch.zeros(B, A, 2, dtype=f32)
+    obs_head = torch.zeros(B, A, dtype=f32)
+    map_in = torch.zeros(B, M, MAP_VEC, MAP_DIM, dtype=f32)
+    map_mask = torch.zeros(B, M, MAP_VEC, dtype=torch.bool)
+    map_pos = torch.zeros(B, M, 1, 2, dtype=f32)
+    map_head = torch.zeros(B, M, 1, dtype=f32)
+    prompt = torch.zeros(B, A, 7, dtype=f32)
+    prompt_mask = torch.zeros(B, A, dtype=torch.bool)
+    p_pos = torch.zeros(B, A, 2, dtype=f32)
+    p_head = torch.zeros(B, A, 1, dtype=f32)
+    p_type = torch.zeros(B, A, dtype=torch.int64)
+    goal_in = torch.zeros(B, A, 3, dtype=f32)
+    goal_mask = torch.zeros(B, A, dtype=torch.bool)
+    goal_pidx = -torch.ones(B, A, 1, dtype=torch.int64)
+    prompt_ids, obs_ids = [], []
+
+    for b in range(B):
+        g = torch.Generator().manual_seed(1000 + first_scene + b)
+        na, nm = agents_per_scene[b], map_per_scene[b]
+        sc = _one_scene(g, na, nm)
+        ids = [str(100 + 7 * i) for i in range(na)]
+        perm = torch.randperm(na, generator=g) if permute_obs else torch.arange(na)
+        obs_in[b, :na] = sc['obs'][perm]
+        obs_mask[b, :na] = True
+        obs_pos[b, :na] = sc['pos'][perm]
+        obs_head[b, :na] = sc['heading'][perm]
+        obs_ids.append([ids[int(i)] for i in perm])
+        map_in[b, :nm] = sc['map']
+        map_mask[b, :nm] = True
+        map_pos[b, :nm, 0] = sc['map_pos']
+        map_head[b, :nm, 0] = sc['map_heading']
+        prompt[b, :na] = sc['prompt']
+        prompt_mask[b, :na] = True
+        p_pos[b, :na] = sc['pos']
+        p_head[b, :na, 0] = sc['heading']
+        p_type[b, :na] = sc['atype']
+        prompt_ids.append(ids)
+        if goal:
+            noise = torch.randn(na, 2, generator=g, dtype=f32)
+            goal_in[b, :na, 0] = sc['speed'] * 8.0 + noise[:, 0]
+            goal_in[b, :na, 1] = noise[:, 1]
+            goal_in[b, :na, 2] = float(steps)
+            goal_mask[b, :na] = True
+            goal_pidx[b, :na, 0] = torch.arange(na)
+
+    all_t = torch.arange(steps)[::10]
+    fut = {}
+    for t in all_t.tolist():
+        if t == 0:
+            continue
+        f_in = obs_in.clone()
+        f_in[..., :8] = 0.0
+        fut[int(t)] = InputMaskData(f_in, torch.zeros_like(obs_mask), torch.zeros_like(obs_pos),
+                                    torch.zeros_like(obs_head), [list(x) for x in obs_ids])
+
+    extras = {
+        'init_obs': InputMaskData(obs_in, obs_mask, obs_pos, obs_head, obs_ids),
+        'init_map': InputMaskData(map_in, map_mask, map_pos, map_head),
+        'prompt': BatchPrompt({'motion_pred': {
+            'prompt': prompt, 'prompt_mask': prompt_mask, 'position': p_pos, 'heading': p_head,
+            'agent_type': p_type, 'agent_ids': prompt_ids}}),
+        'condition': BatchCondition({'goal': {'input': goal_in, 'mask': goal_mask, 'prompt_idx': goal_pidx,
+                                              'prompt_mask': prompt_mask.clone()}} if goal else {}),
+        'all_t_indices': all_t,
+        'fut_obs': BatchDataDict(fut),
+    }
+    batch = SceneBatch([f'synthetic_{first_scene + b}' for b in range(B)], extras)
+    if pin_memory:
+        _pin(batch)
+    return batch
+
+
+def _pin(batch):
+    def pin(x):
+        return x.pin_memory() if isinstance(x, torch.Tensor) else x
+    ex = batch.extras
+    for key in ('init_obs', 'init_map'):
+        for k in ('input', 'mask', 'position', 'heading'):
+            ex[key][k] = pin(ex[key][k])
+    for t in ex['fut_obs'].keys():
+        for k in ('input', 'mask', 'position', 'heading'):
+            ex['fut_obs'][t][k] = pin(ex['fut_obs'][t][k])
+    for sub in list(ex['prompt'].all_prompts.values()) + list(ex['condition'].all_cond.values()):
+        for k, v in sub.items():
+            sub[k] = pin(v)

@@ -1,0 +1,141 @@
+"""Parameter table of the rollout path, under the reference's own ``state_dict`` names.
+
+The names/shapes below are what ``ProSim(cfg).state_dict()`` holds for the released model
+shape (verified against the live reference in tests/test_oracle_vs_reference.py and pinned
+in tests/golden/state_dict_keys.json), so a reference checkpoint loads by key:
+  scene_encoder.*            prosim/models/scene_encoder/{pointnet_encoder,attn_fusion}.py
+  prompt_encoder.motion_pred prosim/models/prompt_encoder/base.py:30
+  decoder.*                  prosim/models/decoder/sym_coord.py:28-35
+  policy.act_decoder.*       prosim/models/policy/act_decoder.py:50-76,177-196
+  condition_transformers.policy_decoder.*   condition_transformer/{condition_encoders,condition_attns}.py
+No checkpoint ships with the reference (README.md:56-58), so parity work uses
+``random_state_dict``: every tensor is filled from its own generator keyed by
+(seed, crc32(name)), independent of module construction order.
+"""
+import zlib
+from collections import OrderedDict
+
+import torch
+
+D = 128
+HEADS = 8
+HEAD_DIM = 16
+
+
+def _mlp(prefix, dims, ret_before_act=False, without_norm=False):
+    """layers/mlp.py:475-494 -- Linear [+LN] + ReLU stack; index math of nn.Sequential."""
+    out = []
+    idx = 0
+    n = len(dims) - 1
+    for i in range(n):
+        out.append((f'{prefix}.mlp.{idx}.weight', (dims[i + 1], dims[i]), 'linear_w'))
+        out.append((f'{prefix}.mlp.{idx}.bias', (dims[i + 1],), 'linear_b'))
+        idx += 1
+        if i < n - 1:
+            if not without_norm:
+                out.append((f'{prefix}.mlp.{idx}.weight', (dims[i + 1],), 'ln_w'))
+                out.append((f'{prefix}.mlp.{idx}.bias', (dims[i + 1],), 'ln_b'))
+                idx += 1
+            idx += 1  # ReLU
+    return out
+
+
+def _attn_layer(prefix):
+    """layers/attention_layer.py:28-54 (has_pos_emb=True; both prenorm names exist even when shared)."""
+    p = prefix
+    out = [
+        (f'{p}.to_q.weight', (D, D), 'linear_w'), (f'{p}.to_q.bias', (D,), 'linear_b'),
+        (f'{p}.to_k.weight', (D, D), 'linear_w'),
+        (f'{p}.to_v.weight', (D, D), 'linear_w'), (f'{p}.to_v.bias', (D,), 'linear_b'),
+        (f'{p}.to_k_r.weight', (D, D), 'linear_w'),
+        (f'{p}.to_v_r.weight', (D, D), 'linear_w'), (f'{p}.to_v_r.bias', (D,), 'linear_b'),
+        (f'{p}.to_s.weight', (D, D), 'linear_w'), (f'{p}.to_s.bias', (D,), 'linear_b'),
+        (f'{p}.to_g.weight', (D, 2 * D), 'linear_w'), (f'{p}.to_g.bias', (D,), 'linear_b'),
+        (f'{p}.to_out.weight', (D, D), 'linear_w'), (f'{p}.to_out.bias', (D,), 'linear_b'),
+        (f'{p}.ff_mlp.0.weight', (4 * D, D), 'linear_w'), (f'{p}.ff_mlp.0.bias', (4 * D,), 'linear_b'),
+        (f'{p}.ff_mlp.3.weight', (D, 4 * D), 'linear_w'), (f'{p}.ff_mlp.3.bias', (D,), 'linear_b'),
+    ]
+    for ln in ('attn_prenorm_x_src', 'attn_prenorm_x_dst', 'attn_prenorm_r', 'attn_postnorm',
+               'ff_prenorm', 'ff_postnorm'):
+        out += [(f'{p}.{ln}.weight', (D,), 'ln_w'), (f'{p}.{ln}.bias', (D,), 'ln_b')]
+    return out
+
+
+def _pointnet(prefix, in_dim, num_layers, num_pre):
+    """scene_encoder/pointnet_encoder.py:13-22."""
+    return (_mlp(f'{prefix}.pre_mlps', [in_dim] + [D] * num_pre)
+            + _mlp(f'{prefix}.mlps', [2 * D] + [D] * (num_layers - num_pre))
+            + _mlp(f'{prefix}.out_mlps', [D] * 3, ret_before_act=True, without_norm=True))
+
+
+SHARED_LN_STACKS = ('scene_encoder.a2a_attn_layers', 'scene_encoder.s2s_attn_layers',
+                    'decoder.p2p_attn_layers',
+                    'condition_transformers.policy_decoder.condition_attn.attn_layers')
+
+
+def param_specs(goal_condition=False, num_layers=6, cond_layers=3):
+    specs = []
+    specs += _pointnet('scene_encoder.map_encoder', 11, 5, 3)
+    specs += _pointnet('scene_encoder.obs_encoder', 24, 3, 1)
+    for stack in ('a2a', 's2s'):
+        for i in range(num_layers):
+            specs += _attn_layer(f'scene_encoder.{stack}_attn_layers.{i}')
+    specs += _mlp('prompt_encoder.motion_pred.state_encoder', [7, D, D], ret_before_act=True)
+    for stack in ('p2p', 's2p'):
+        for i in range(num_layers):
+            specs += _attn_layer(f'decoder.{stack}_attn_layers.{i}')
+    if goal_condition:
+        ct = 'condition_transformers.policy_decoder'
+        specs += _mlp(f'{ct}.condition_encoders.goal.goal_encoder', [2, D, D], ret_before_act=True,
+                      without_norm=True)
+        for i in range(cond_layers):
+            specs += _attn_layer(f'{ct}.condition_attn.attn_layers.{i}')
+    pa = 'policy.act_decoder'
+    for stack in ('a2p', 'm2p'):
+        for i in range(num_layers):
+            specs += _attn_layer(f'{pa}.{stack}_attn_layers.{i}')
+    specs += _mlp(f'{pa}.motion_head', [D, D, D // 2, 50], ret_before_act=True)
+    for i in range(3):
+        specs += [(f'{pa}.CG_decode.CGs.{i}.MLP.0.weight', (D, D), 'linear_w'),
+                  (f'{pa}.CG_decode.CGs.{i}.MLP.0.bias', (D,), 'linear_b'),
+                  (f'{pa}.CG_decode.CGs.{i}.MLP.1.weight', (D,), 'ln_w'),
+                  (f'{pa}.CG_decode.CGs.{i}.MLP.1.bias', (D,), 'ln_b')]
+    specs += [(f'{pa}.motion_anchors.weight', (3, D), 'emb')]
+    specs += _mlp(f'{pa}.pred_mlp', [D, D, D // 2, 2], ret_before_act=True)
+    return specs
+
+
+def random_state_dict(seed=0, goal_condition=False, dtype=torch.float32):
+    """Seeded random weights, torch-default-like scales; LayerNorm affine is NOT identity on purpose
+    (so the gamma/beta folding in the kernels is exercised).  Non-bipartite layers share one LayerNorm
+    under two names (attention_layer.py:48-49): the dst copy is tied to the src one."""
+    sd = OrderedDict()
+    for name, shape, kind in param_specs(goal_condition):
+        g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(name.encode())) % (2 ** 63))
+        if kind == 'linear_w':
+            bound = 1.0 / (shape[1] ** 0.5)
+            t = (torch.rand(shape, generator=g, dtype=torch.float64) * 2 - 1) * bound
+        elif kind == 'linear_b':
+            fan_in = dict(param_shapes_cache(goal_condition))[name[:-len('bias')] + 'weight'][1]
+            bound = 1.0 / (fan_in ** 0.5)
+            t = (torch.rand(shape, generator=g, dtype=torch.float64) * 2 - 1) * bound
+        elif kind == 'ln_w':
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g, dtype=torch.float64)
+        elif kind == 'ln_b':
+            t = 0.05 * torch.randn(shape, generator=g, dtype=torch.float64)
+        else:  # emb
+            t = torch.randn(shape, generator=g, dtype=torch.float64)
+        sd[name] = t.to(torch.float32).to(dtype)
+    for name in list(sd.keys()):
+        if '.attn_prenorm_x_dst.' in name and name.startswith(SHARED_LN_STACKS):
+            sd[name] = sd[name.replace('attn_prenorm_x_dst', 'attn_prenorm_x_src')].clone()
+    return sd
+
+
+_SHAPES = {}
+
+
+def param_shapes_cache(goal_condition):
+    if goal_condition not in _SHAPES:
+        _SHAPES[goal_condition] = [(n, s) for n, s, _ in param_specs(goal_condition)]
+    return _SHAPES[goal_condition]

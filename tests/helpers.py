@@ -1,0 +1,60 @@
+"""Shared helpers for the parity tests."""
+import os
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+CASES = {
+    'cfg1_a16_m256_s20': (dict(n_scenes=1, n_agents=16, n_map=256, steps=20), False),
+    'cfg2_a64_m256_s40': (dict(n_scenes=1, n_agents=64, n_map=256, steps=40), False),
+    'cfg3_a128_m512_s80': (dict(n_scenes=1, n_agents=128, n_map=512, steps=80), False),
+    'cfg4_goal_a128_m512_s80': (dict(n_scenes=1, n_agents=128, n_map=512, steps=80, goal=True), True),
+    'ragged_b3_s30': (dict(agents_per_scene=[24, 9, 17], map_per_scene=[40, 64, 33], steps=30,
+                           permute_obs=True), False),
+    'ragged_goal_b2_s20': (dict(agents_per_scene=[12, 20], map_per_scene=[48, 30], steps=20, goal=True,
+                                permute_obs=True), True),
+}
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name + '.npz')))
+
+
+def stack_rollout(out):
+    """rollout_trajs dict -> (names, traj [P,steps,4], vel [P,steps,2]) as float64 numpy on the host."""
+    rt = out['rollout_trajs']
+    names = list(rt.keys())
+    traj = torch.stack([rt[n]['traj'] for n in names]).detach().cpu().double().numpy()
+    vel = torch.stack([rt[n]['vel'] for n in names]).detach().cpu().double().numpy()
+    return names, traj, vel
+
+
+def per_tick_max(a, b, step=10):
+    """max |a-b| per 10-step tick over agents and coordinates."""
+    d = np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64))
+    P, S = d.shape[:2]
+    return d.reshape(P, S // step, step, -1).max(axis=(0, 2, 3))
+
+
+def edge_set(edge_index):
+    e = edge_index.detach().cpu().long()
+    return set(zip(e[1].tolist(), e[0].tolist()))
+
+
+def to_double(batch):
+    """Cast every float tensor of a synthetic batch to float64 (fp64 arbiter runs)."""
+    ex = batch.extras
+    for key in ('init_obs', 'init_map'):
+        for k in ('input', 'position', 'heading'):
+            ex[key][k] = ex[key][k].double()
+    for t in ex['fut_obs'].keys():
+        for k in ('input', 'position', 'heading'):
+            ex['fut_obs'][t][k] = ex['fut_obs'][t][k].double()
+    p = ex['prompt']['motion_pred']
+    for k in ('prompt', 'position', 'heading'):
+        p[k] = p[k].double()
+    for c in ex['condition'].keys():
+        ex['condition'][c]['input'] = ex['condition'][c]['input'].double()
+    return batch

@@ -1,0 +1,41 @@
+"""CPU, only where /root/reference is mounted: the oracle restatement equals the reference's own
+code (run behind oracle/ref_shim.py) bit for bit, on ragged / permuted / goal-conditioned batches."""
+import pytest
+import torch
+
+from oracle import ref_shim
+from oracle.prosim_oracle import ProSimOracle
+from prosim_b200 import synthetic, weights
+
+pytestmark = pytest.mark.ref_tree
+
+
+@pytest.mark.parametrize('goal', [False, True])
+def test_param_table_equals_live_reference(goal):
+    m, _ = ref_shim.build_reference_model(('goal',) if goal else ())
+    ref = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    assert ref == [(n, tuple(s)) for n, s, _ in weights.param_specs(goal)]
+    assert sum(p.numel() for p in m.parameters()) == (11314740 if goal else 10454196)
+
+
+@pytest.mark.parametrize('goal', [False, True])
+def test_oracle_bit_equal_to_reference(goal):
+    m, _ = ref_shim.build_reference_model(('goal',) if goal else ())
+    sd = weights.random_state_dict(0, goal)
+    m.load_state_dict(sd)
+    kw = dict(agents_per_scene=[20, 13], map_per_scene=[48, 37], steps=30, goal=goal, permute_obs=True)
+    b_ref, b_orc = synthetic.make_batch(**kw), synthetic.make_batch(**kw)
+    with torch.no_grad():
+        ref = m.forward(b_ref, 'val')['motion_pred']
+    orc = ProSimOracle(sd, goal).forward(b_orc)['motion_pred']
+    for k in ('motion_pred', 'motion_prob', 'reconst_pred'):
+        assert torch.equal(ref[k], orc[k]), k
+    assert ref['pair_names'] == orc['pair_names']
+    assert list(ref['rollout_trajs']) == list(orc['rollout_trajs'])
+    for name, r in ref['rollout_trajs'].items():
+        for key, val in r.items():
+            assert torch.equal(val, orc['rollout_trajs'][name][key]), (name, key)
+    for t in b_ref.extras['fut_obs'].keys():
+        for key in ('input', 'mask', 'position', 'heading'):
+            a, b = b_ref.extras['fut_obs'][t][key], b_orc.extras['fut_obs'][t][key]
+            assert torch.equal(torch.nan_to_num(a.float()), torch.nan_to_num(b.float())), (t, key)
