@@ -1,0 +1,118 @@
+/* prosim_b200 -- C ABI of the B200-native closed-loop rollout path of ProSim.
+ *
+ * The reference (Ariostgx/ProSim @ 78a398c) is pure Python/PyTorch and has NO FFI of its own: its
+ * "plugin" boundary is the class registry (prosim/core/registry.py:25-136) behind which
+ * ProSim.forward (prosim/models/traj_sam.py:59-175) runs.  This header is therefore the boundary a
+ * maintainer would bind from Python (ctypes) to replace, one for one, the native
+ * work the reference delegates to ATen / torch_cluster / torch_geometric on this path.  Each entry
+ * point cites the reference code it replaces.
+ *
+ * Conventions: every pointer is a DEVICE pointer owned by the caller (PyTorch's allocator on the Python
+ * side); nothing is allocated, freed or retained; calls only ENQUEUE work on `stream` and return
+ * 0 on success, a positive cudaError_t on a launch failure, or a negative value for a bad argument.
+ * All functions are re-entrant; there is no global state besides one-time kernel attribute setup.
+ * Index arrays are int32, masks are uint8 (torch.bool), floats are IEEE fp32.
+ */
+#ifndef PROSIM_B200_H
+#define PROSIM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* prosim_stream_t; /* cudaStream_t */
+
+/* Fixed-stride neighbour lists + the per-edge normalised relative PE that go with them. */
+typedef struct {
+  const float* z;      /* [n_dst*stride][128] LayerNorm(rel PE) without affine, row = dst*stride + j */
+  const int32_t* nbr;  /* [n_dst*stride] source row of edge j of destination dst (ascending)          */
+  const int32_t* deg;  /* [n_dst] number of valid edges per destination                               */
+  int32_t stride;      /* row stride of nbr / z                                                        */
+  int32_t max_deg;     /* upper bound of deg (sizes the softmax scratch in shared memory)             */
+} prosim_graph_t;
+
+/* One side of an alternating attention stack (prosim_attn_stack_fwd). */
+typedef struct {
+  const float* w;          /* n_layers packed AttentionLayers, consecutive (prosim_attn_layer_floats() each) */
+  const float* kv;         /* fixed sources: precomputed [n_layers][n_src][256] K'|V' ; NULL => sources are the
+                              destination rows themselves (non-bipartite layer), K'|V' recomputed every layer   */
+  size_t kv_layer_stride;  /* floats between layers in kv                                                       */
+  prosim_graph_t graph;
+} prosim_stack_side_t;
+
+int prosim_abi_version(void);
+/* sizes (in floats) of the packed weight blocks -- cross-checked by the Python packer */
+int prosim_attn_layer_floats(void);
+int prosim_pointnet_floats(void);
+int prosim_head_floats(void);
+int prosim_mlp2_floats(void);
+/* scratch floats needed by prosim_attn_layer_fwd / prosim_attn_stack_fwd for n_dst destination and n_src self-source rows */
+size_t prosim_attn_workspace_floats(int n_dst, int n_src);
+
+/* PointNet polyline encoder: prosim/models/scene_encoder/pointnet_encoder.py:24-62.
+ * kind 0 = agent history (11 points x 24 features, mask uint8 [.,11,24]; obs_encoder.py:75-86)
+ * kind 1 = map polyline  (19 vectors x 11 features, mask uint8 [.,19];   map_encoder.py:67-88)
+ * rows[n_poly] selects the polylines to encode out of x; out is compact [n_poly][128]. */
+int prosim_pointnet_fwd(int kind, const float* x, const uint8_t* mask, const int32_t* rows, int n_poly,
+                        const float* w, float* out, prosim_stream_t stream);
+
+/* torch_cluster.radius / radius_graph (call sites decoder/sym_coord.py:86,94; policy/act_decoder.py:250,259).
+ * seg[B][4] = {start0,len0,start1,len1}: source ranges of each scene.  drop_self=1 gives radius_graph(loop=False)
+ * semantics (cap+1 candidates, then the query itself removed; query index == source index). */
+int prosim_build_radius_edges(const float* qpos, const int32_t* qscene, int n_q, const float* spos,
+                              const int32_t* seg, float r, int cap, int drop_self, int32_t* nbr, int32_t* deg,
+                              int stride, prosim_stream_t stream);
+/* torch_cluster.knn_graph(loop=True) (call sites scene_encoder/attn_fusion.py:107,109). nmax >= largest scene. */
+int prosim_build_knn_edges(const float* qpos, const int32_t* qscene, int n_q, const float* spos, const int32_t* seg,
+                           int k, int nmax, int32_t* nbr, int32_t* deg, int stride, prosim_stream_t stream);
+/* _get_rel_pe + FourierEmbeddingFix + attn_prenorm_r statistics (act_decoder.py:203-221,
+ * layers/fourier_embedding.py:56-79, attention_layer.py:68). extra (nullable): per-edge vector added before
+ * the normalisation (condition edges, condition_transformer/condition_attns.py:211-216). */
+int prosim_edge_pe(const float* dpos, const float* dori, int n_dst, const float* spos, const float* sori,
+                   const int32_t* nbr, const int32_t* deg, int stride, const float* dim_t16, const float* extra,
+                   float* z, prosim_stream_t stream);
+
+/* AttentionLayer pieces (prosim/models/layers/attention_layer.py:56-118) */
+int prosim_attn_kv(const float* x_src, int n_src, const float* w, size_t w_layer_stride, int n_layers, float* kv,
+                   size_t kv_layer_stride, prosim_stream_t stream);
+/* one full layer: x_src == x_dst (same pointer) selects the non-bipartite form */
+int prosim_attn_layer_fwd(const float* x_src, int n_src, const float* x_dst, int n_dst, const prosim_graph_t* g,
+                          const float* w, float* workspace, size_t workspace_floats, float* out,
+                          prosim_stream_t stream);
+/* n_layers x (layer A [, layer B]) on the same destination rows, each post kernel fused with the next layer's
+ * destination-side projections: the policy's a2p/m2p loop (act_decoder.py:270-277), the generator's p2p/s2p loop
+ * (sym_coord.py:100-103) and the goal-condition GNN (condition_attns.py:222-224; side_b == NULL). */
+int prosim_attn_stack_fwd(const float* x, int n_dst, int n_layers, const prosim_stack_side_t* side_a,
+                          const prosim_stack_side_t* side_b, float* workspace, size_t workspace_floats, float* out,
+                          prosim_stream_t stream);
+
+/* ActDecoder._compute_traj (policy/act_decoder.py:78-135): motion_pred [P][10][5] */
+int prosim_policy_head_fwd(const float* feat, const int32_t* agent_type, int P, const float* w, float* motion_pred,
+                           prosim_stream_t stream);
+/* pred_mlp(policy emd) (act_decoder.py:129-131): out [P][2] */
+int prosim_reconst_fwd(const float* emd, int P, const float* w, float* out, prosim_stream_t stream);
+/* PromptEncoder (prompt_encoder/base.py:30,37-50) / GoalConditionEncoder (condition_encoders.py:21-51) */
+int prosim_mlp2_fwd(const float* in, int ld_in, int k0, int n, int use_ln, const float* w, const float* tpe_t,
+                    int tpe_ld, const float* dim_t128, float* out, prosim_stream_t stream);
+
+/* ProSim.init_agent_trajs (traj_sam.py:597-633) */
+int prosim_init_traj(const float* obs_in, const float* obs_pos, const float* obs_head, const int32_t* p_slot,
+                     const int32_t* p_row, int P, int T, float* traj, float* vel, float* init_pos,
+                     float* init_heading, prosim_stream_t stream);
+/* ProSim.step_env (traj_sam.py:205-274); fut_* may be NULL on the first tick */
+int prosim_step_env(const float* traj, const float* vel, const float* init_pos, const float* init_heading,
+                    const int32_t* p_row, const int32_t* p_slot, int P, int T, int tidx, float* p_pos, float* p_ori,
+                    float* fut_in, uint8_t* fut_mask, float* fut_pos, float* fut_head, prosim_stream_t stream);
+int prosim_gather_pose(const float* pos, const float* head, const int32_t* rows, int n, float* out_pos,
+                       float* out_ori, prosim_stream_t stream);
+/* ProSim.step_agent_traj (traj_sam.py:276-349), TOP_K = 1 */
+int prosim_step_agent_traj(const float* motion_pred, const int32_t* p_row, int P, int T, int tidx, float* traj,
+                           float* vel, prosim_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

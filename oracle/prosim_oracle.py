@@ -83,6 +83,7 @@ class ProSimOracle:
         self.goal_condition = goal_condition
         self.faithful_bookkeeping = faithful_bookkeeping
         self.trace = None  # set to [] to record per-tick state for teacher-forced tests
+        self.trace_states = []
 
     # ------------------------------------------------------------------------- building blocks
     def lin(self, name, x, bias=True):
@@ -423,6 +424,8 @@ class ProSimOracle:
         st = self.init_agent_trajs(policy_ids, batch)
         outs = []
         for t in all_t:
+            if self.trace is not None:
+                self.trace_states.append(dict(t=t, traj=st['traj'].clone(), vel=st['vel'].clone(), last_step=st['last_step']))
             scene, a_pos = self.step_env(scene, st, batch, policy_ids, t, all_t)
             out = self.policy_tick(policy, scene, policy_ids, a_pos, t)
             if self.faithful_bookkeeping:

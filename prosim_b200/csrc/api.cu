@@ -1,0 +1,346 @@
+// C-ABI entry points (include/prosim_b200.h): argument checks + kernel launches, nothing else.
+#include "../../include/prosim_b200.h"
+
+#include "attn.cuh"
+#include "common.cuh"
+#include "graph.cuh"
+#include "pointnet.cuh"
+#include "rollout.cuh"
+#include "weights_layout.h"
+
+using namespace prosim;
+
+namespace {
+
+constexpr int ERR_ARG = -1;
+constexpr int ERR_WORKSPACE = -2;
+
+inline cudaStream_t S(prosim_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Row-tile height (2*RPT rows per CTA): the largest tile that still yields >= one CTA per SM.
+inline int pick_rpt(int n_rows) {
+  const int sms = 148;
+  for (int rpt = 8; rpt > 1; rpt >>= 1)
+    if ((n_rows + 2 * rpt - 1) / (2 * rpt) >= sms) return rpt;
+  return 1;
+}
+
+#define DISPATCH_RPT(rpt, ...)                     \
+  switch (rpt) {                                   \
+    case 8: { constexpr int RPT = 8; __VA_ARGS__; } break; \
+    case 4: { constexpr int RPT = 4; __VA_ARGS__; } break; \
+    case 2: { constexpr int RPT = 2; __VA_ARGS__; } break; \
+    default: { constexpr int RPT = 1; __VA_ARGS__; } break; \
+  }
+
+template <typename K>
+inline cudaError_t allow_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+int setup_attributes() {
+  static int state = 0;  // 0 = not done, 1 = ok, <0/>1 = error
+  if (state != 0) return state == 1 ? 0 : state;
+  cudaError_t e = cudaSuccess;
+  auto acc = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+  acc(allow_smem(attn_edge_kernel, 200 * 1024));
+  acc(allow_smem(attn_post_kernel<8>, PostSmem<8>::bytes));
+  acc(allow_smem(attn_post_kernel<4>, PostSmem<4>::bytes));
+  acc(allow_smem(attn_post_kernel<2>, PostSmem<2>::bytes));
+  acc(allow_smem(attn_post_kernel<1>, PostSmem<1>::bytes));
+  acc(allow_smem(pointnet_kernel<24, 24, 1, 11>, PointNetCfg<11>::smem_bytes));
+  acc(allow_smem(pointnet_kernel<11, 12, 3, 19>, PointNetCfg<19>::smem_bytes));
+  acc(allow_smem(knn_kernel, 64 * 1024));
+  state = e == cudaSuccess ? 1 : (int)e + 1000;
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+struct DstScratch {
+  float *q, *qhat, *s, *gx;
+};
+
+struct StackWs {
+  DstScratch set[2];
+  float *rbar, *aggv, *x0, *x1, *kv;
+};
+
+constexpr size_t WS_PER_DST = 2 * (size_t)(D + H * D + D + D) + H * D + D + 2 * D;
+
+StackWs carve(float* ws, int n_dst) {
+  StackWs w;
+  float* p = ws;
+  for (int i = 0; i < 2; ++i) {
+    w.set[i].q = p;    p += (size_t)n_dst * D;
+    w.set[i].qhat = p; p += (size_t)n_dst * H * D;
+    w.set[i].s = p;    p += (size_t)n_dst * D;
+    w.set[i].gx = p;   p += (size_t)n_dst * D;
+  }
+  w.rbar = p; p += (size_t)n_dst * H * D;
+  w.aggv = p; p += (size_t)n_dst * D;
+  w.x0 = p;   p += (size_t)n_dst * D;
+  w.x1 = p;   p += (size_t)n_dst * D;
+  w.kv = p;
+  return w;
+}
+
+int launch_kv(const float* x, int n, const float* w, size_t wstride, int layers, float* kv, size_t kvstride,
+              cudaStream_t st) {
+  if (n <= 0) return 0;
+  const int rpt = pick_rpt(n * layers);
+  DISPATCH_RPT(rpt, attn_kv_kernel<RPT><<<dim3((n + 2 * RPT - 1) / (2 * RPT), layers), 256, 0, st>>>(x, n, w, wstride, kv, kvstride));
+  PROSIM_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_dstpre(const float* x, int n, const float* w, const DstScratch& d, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const int rpt = pick_rpt(n);
+  DISPATCH_RPT(rpt, attn_dstpre_kernel<RPT><<<(n + 2 * RPT - 1) / (2 * RPT), 256, 0, st>>>(x, n, w, d.q, d.qhat, d.s, d.gx));
+  PROSIM_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_edge(const DstScratch& d, const float* kv, const prosim_graph_t& g, int n_dst, float* rbar, float* aggv,
+                cudaStream_t st) {
+  if (n_dst <= 0) return 0;
+  const int sstride = ((g.max_deg < 4 ? 4 : g.max_deg) + 3) & ~3;
+  const size_t smem = attn_edge_smem_bytes(sstride);
+  if (smem > 200 * 1024) return ERR_ARG;
+  attn_edge_kernel<<<n_dst, 256, smem, st>>>(d.q, d.qhat, kv, g.z, g.nbr, g.deg, g.stride, sstride, rbar, aggv);
+  PROSIM_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_post(const float* x, int n, const float* rbar, const float* aggv, const DstScratch& cur, const float* w,
+                float* out, const float* w_next, const DstScratch& nxt, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const int rpt = pick_rpt(n);
+  DISPATCH_RPT(rpt, attn_post_kernel<RPT><<<(n + 2 * RPT - 1) / (2 * RPT), 256, PostSmem<RPT>::bytes, st>>>(
+                        x, n, rbar, aggv, cur.s, cur.gx, w, out, w_next, nxt.q, nxt.qhat, nxt.s, nxt.gx));
+  PROSIM_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int prosim_abi_version(void) { return 1; }
+int prosim_attn_layer_floats(void) { return aw::SIZE; }
+int prosim_pointnet_floats(void) { return pw::SIZE; }
+int prosim_head_floats(void) { return hw::SIZE; }
+int prosim_mlp2_floats(void) { return mw::SIZE; }
+size_t prosim_attn_workspace_floats(int n_dst, int n_src) {
+  return WS_PER_DST * (size_t)(n_dst < 0 ? 0 : n_dst) + 256 * (size_t)(n_src < 0 ? 0 : n_src) + 64;
+}
+
+int prosim_pointnet_fwd(int kind, const float* x, const uint8_t* mask, const int32_t* rows, int n_poly, const float* w,
+                        float* out, prosim_stream_t stream) {
+  if (n_poly < 0 || (kind != 0 && kind != 1)) return ERR_ARG;
+  if (n_poly == 0) return 0;
+  if (!x || !mask || !rows || !w || !out) return ERR_ARG;
+  if (int e = setup_attributes()) return e;
+  if (kind == 0) {
+    constexpr int G = PointNetCfg<11>::G;
+    pointnet_kernel<24, 24, 1, 11><<<(n_poly + G - 1) / G, 256, PointNetCfg<11>::smem_bytes, S(stream)>>>(
+        x, mask, 24, rows, n_poly, w, out);
+  } else {
+    constexpr int G = PointNetCfg<19>::G;
+    pointnet_kernel<11, 12, 3, 19><<<(n_poly + G - 1) / G, 256, PointNetCfg<19>::smem_bytes, S(stream)>>>(
+        x, mask, 1, rows, n_poly, w, out);
+  }
+  PROSIM_CHECK_LAUNCH();
+  return 0;
+}
+
+int prosim_build_radius_edges(const float* qpos, const int32_t* qscene, int n_q, const float* spos, const int32_t* seg,
+                              float r, int cap, int drop_self, int32_t* nbr, int32_t* deg, int stride,
+                              prosim_stream_t stream) {
+  if (n_q < 0 || cap < 0 || stride <= 0) return ERR_ARG;
+  if (n_q == 0) return 0;
+  if (!qpos || !qscene || !spos || !seg || !nbr || !deg) return ERR_ARG;
+  const float r2 = r * r;
+  radius_kernel<<<(n_q + 7) / 8, 256, 0, S(stream)>>>(reinterpret_cast<const float2*>(qpos), qscene, n_q,
+                                                      reinterpret_cast<const float2*>(spos),
+                                                      reinterpret_cast<const int4*>(seg), r2, cap, drop_self, nbr, deg,
+                                                      stride);
+  PROSIM_CHECK_LAUNCH();
+  return 0;
+}
+
+int prosim_build_knn_edges(const float* qpos, const int32_t* qscene, int n_q, const float* spos, const int32_t* seg,
+                           int k, int nmax, int32_t* nbr, int32_t* deg, int stride, prosim_stream_t stream) {
+  if (n_q < 0 || k <= 0 || nmax <= 0 || stride <= 0) return ERR_ARG;
+  if (n_q == 0) return 0;
+  if (!qpos || !qscene || !spos || !seg || !nbr || !deg) return ERR_ARG;
+  if (int e = setup_attributes()) return e;
+  const size_t smem = (size_t)nmax * 8;
+  if (smem > 64 * 1024) return ERR_ARG;
+  knn_kernel<<<n_q, 128, smem, S(stream)>>>(reinterpret_cast<const float2*>(qpos), qscene, n_q,
+                                            reinterpret_cast<const float2*>(spos), reinterpret_cast<const int4*>(seg), k,
+                                            nmax, nbr, deg, stride);
+  PROSIM_CHECK_LAUNCH();
+  return 0;
+}
+
+int prosim_edge_pe(const float* dpos, const float* dori, int n_dst, const float* spos, const float* sori,
+                   const int32_t* nbr, const int32_t* deg, int stride, const float* dim_t16, const float* extra, float* z,
+                   prosim_stream_t stream) {
+  if (n_dst < 0 || stride <= 0) return ERR_ARG;
+  if (n_dst == 0) return 0;
+  if (!dpos || !dori || !spos || !sori || !nbr || !deg || !dim_t16 || !z) return ERR_ARG;
+  edge_pe_kernel<<<n_dst, 128, 0, S(stream)>>>(reinterpret_cast<const float2*>(dpos), dori,
+                                               reinterpret_cast<const float2*>(spos), sori, nbr, deg, stride, dim_t16,
+                                               extra, z);
+  PROSIM_CHECK_LAUNCH();
+  return 0;
+}
+
+int prosim_attn_kv(const float* x_src, int n_src, const float* w, size_t w_layer_stride, int n_layers, float* kv,
+                   size_t kv_layer_stride, prosim_stream_t stream) {
+  if (n_src < 0 || n_layers <= 0) return ERR_ARG;
+  if (n_src == 0) return 0;
+  if (!x_src || !w || !kv) return ERR_ARG;
+  return launch_kv(x_src, n_src, w, w_layer_stride, n_layers, kv, kv_layer_stride, S(stream));
+}
+
+int prosim_attn_layer_fwd(const float* x_src, int n_src, const float* x_dst, int n_dst, const prosim_graph_t* g,
+                          const float* w, float* workspace, size_t workspace_floats, float* out,
+                          prosim_stream_t stream) {
+  if (n_src < 0 || n_dst < 0 || !g) return ERR_ARG;
+  if (n_dst == 0) return 0;
+  if (!x_src || !x_dst || !w || !workspace || !out || !g->z || !g->nbr || !g->deg) return ERR_ARG;
+  if (workspace_floats < prosim_attn_workspace_floats(n_dst, n_src)) return ERR_WORKSPACE;
+  if (int e = setup_attributes()) return e;
+  cudaStream_t st = S(stream);
+  StackWs ws = carve(workspace, n_dst);
+  if (int e = launch_kv(x_src, n_src, w, 0, 1, ws.kv, 0, st)) return e;
+  if (int e = launch_dstpre(x_dst, n_dst, w, ws.set[0], st)) return e;
+  if (int e = launch_edge(ws.set[0], ws.kv, *g, n_dst, ws.rbar, ws.aggv, st)) return e;
+  return launch_post(x_dst, n_dst, ws.rbar, ws.aggv, ws.set[0], w, out, nullptr, ws.set[1], st);
+}
+
+int prosim_attn_stack_fwd(const float* x, int n_dst, int n_layers, const prosim_stack_side_t* side_a,
+                          const prosim_stack_side_t* side_b, float* workspace, size_t workspace_floats, float* out,
+                          prosim_stream_t stream) {
+  if (n_dst < 0 || n_layers <= 0 || !side_a) return ERR_ARG;
+  if (n_dst == 0) return 0;
+  if (!x || !workspace || !out || !side_a->w) return ERR_ARG;
+  const bool self_src = side_a->kv == nullptr || (side_b && side_b->kv == nullptr);
+  if (workspace_floats < prosim_attn_workspace_floats(n_dst, self_src ? n_dst : 0)) return ERR_WORKSPACE;
+  if (int e = setup_attributes()) return e;
+  cudaStream_t st = S(stream);
+  StackWs ws = carve(workspace, n_dst);
+  const prosim_stack_side_t* sides[2] = {side_a, side_b};
+  const int n_sides = side_b ? 2 : 1;
+  const int total = n_layers * n_sides;
+  // x buffers: input -> x0 -> x1 -> x0 ... ; the last layer writes `out`
+  const float* cur_x = x;
+  int cur_set = 0;
+  if (int e = launch_dstpre(cur_x, n_dst, side_a->w, ws.set[cur_set], st)) return e;
+  for (int i = 0; i < total; ++i) {
+    const int l = i / n_sides;
+    const prosim_stack_side_t* sd = sides[i % n_sides];
+    const float* w = sd->w + (size_t)l * aw::SIZE;
+    const float* kv;
+    if (sd->kv) {
+      kv = sd->kv + (size_t)l * sd->kv_layer_stride;
+    } else {
+      if (int e = launch_kv(cur_x, n_dst, w, 0, 1, ws.kv, 0, st)) return e;
+      kv = ws.kv;
+    }
+    if (int e = launch_edge(ws.set[cur_set], kv, sd->graph, n_dst, ws.rbar, ws.aggv, st)) return e;
+    const bool last = i == total - 1;
+    const float* w_next = nullptr;
+    if (!last) {
+      const int ni = i + 1;
+      w_next = sides[ni % n_sides]->w + (size_t)(ni / n_sides) * aw::SIZE;
+    }
+    float* dst_x = last ? out : (cur_x == ws.x0 ? ws.x1 : ws.x0);
+    if (int e = launch_post(cur_x, n_dst, ws.rbar, ws.aggv, ws.set[cur_set], w, dst_x, w_next, ws.set[cur_set ^ 1], st))
+      return e;
+    cur_x = dst_x;
+    cur_set ^= 1;
+  }
+  return 0;
+}
+
+int prosim_policy_head_fwd(const float* feat, const int32_t* agent_type, int P, const float* w, float* motion_pred,
+                           prosim_stream_t stream) {
+  if (P < 0) return ERR_ARG;
+  if (P == 0) return 0;
+  if (!feat || !agent_type || !w || !motion_pred) return ERR_ARG;
+  const int rpt = pick_rpt(P);
+  DISPATCH_RPT(rpt, policy_head_kernel<RPT><<<(P + 2 * RPT - 1) / (2 * RPT), 256, 0, S(stream)>>>(feat, agent_type, P, w, motion_pred));
+  PROSIM_CHECK_LAUNCH();
+  return 0;
+}
+
+int prosim_reconst_fwd(const float* emd, int P, const float* w, float* out, prosim_stream_t stream) {
+  if (P < 0) return ERR_ARG;
+  if (P == 0) return 0;
+  if (!emd || !w || !out) return ERR_ARG;
+  const int rpt = pick_rpt(P);
+  DISPATCH_RPT(rpt, reconst_kernel<RPT><<<(P + 2 * RPT - 1) / (2 * RPT), 256, 0, S(stream)>>>(emd, P, w, out));
+  PROSIM_CHECK_LAUNCH();
+  return 0;
+}
+
+int prosim_mlp2_fwd(const float* in, int ld_in, int k0, int n, int use_ln, const float* w, const float* tpe_t, int tpe_ld,
+                    const float* dim_t128, float* out, prosim_stream_t stream) {
+  if (n < 0 || k0 <= 0 || k0 > 8 || ld_in < k0) return ERR_ARG;
+  if (n == 0) return 0;
+  if (!in || !w || !out || (tpe_t && !dim_t128)) return ERR_ARG;
+  const int rpt = pick_rpt(n);
+  DISPATCH_RPT(rpt, mlp2_kernel<RPT><<<(n + 2 * RPT - 1) / (2 * RPT), 256, 0, S(stream)>>>(in, ld_in, k0, n, use_ln, w, tpe_t, tpe_ld, dim_t128, out));
+  PROSIM_CHECK_LAUNCH();
+  return 0;
+}
+
+int prosim_init_traj(const float* obs_in, const float* obs_pos, const float* obs_head, const int32_t* p_slot,
+                     const int32_t* p_row, int P, int T, float* traj, float* vel, float* init_pos, float* init_heading,
+                     prosim_stream_t stream) {
+  if (P < 0 || T < HIST) return ERR_ARG;
+  if (P == 0) return 0;
+  if (!obs_in || !obs_pos || !obs_head || !p_slot || !p_row || !traj || !vel || !init_pos || !init_heading) return ERR_ARG;
+  init_traj_kernel<<<(P + 127) / 128, 128, 0, S(stream)>>>(obs_in, obs_pos, obs_head, p_slot, p_row, P, T, traj, vel,
+                                                           init_pos, init_heading);
+  PROSIM_CHECK_LAUNCH();
+  return 0;
+}
+
+int prosim_step_env(const float* traj, const float* vel, const float* init_pos, const float* init_heading,
+                    const int32_t* p_row, const int32_t* p_slot, int P, int T, int tidx, float* p_pos, float* p_ori,
+                    float* fut_in, uint8_t* fut_mask, float* fut_pos, float* fut_head, prosim_stream_t stream) {
+  if (P < 0 || tidx < HIST || tidx > T) return ERR_ARG;
+  if (fut_in && tidx < HIST + 2) return ERR_ARG;
+  if (P == 0) return 0;
+  if (!traj || !vel || !init_pos || !init_heading || !p_row || !p_pos || !p_ori) return ERR_ARG;
+  if (fut_in && (!fut_mask || !fut_pos || !fut_head || !p_slot)) return ERR_ARG;
+  step_env_kernel<<<(P + 127) / 128, 128, 0, S(stream)>>>(traj, vel, init_pos, init_heading, p_row, p_slot, P, T, tidx,
+                                                          p_pos, p_ori, fut_in, fut_mask, fut_pos, fut_head);
+  PROSIM_CHECK_LAUNCH();
+  return 0;
+}
+
+int prosim_gather_pose(const float* pos, const float* head, const int32_t* rows, int n, float* out_pos, float* out_ori,
+                       prosim_stream_t stream) {
+  if (n < 0) return ERR_ARG;
+  if (n == 0) return 0;
+  if (!pos || !head || !rows || !out_pos || !out_ori) return ERR_ARG;
+  gather_pose_kernel<<<(n + 127) / 128, 128, 0, S(stream)>>>(pos, head, rows, n, out_pos, out_ori);
+  PROSIM_CHECK_LAUNCH();
+  return 0;
+}
+
+int prosim_step_agent_traj(const float* motion_pred, const int32_t* p_row, int P, int T, int tidx, float* traj, float* vel,
+                           prosim_stream_t stream) {
+  if (P < 0 || tidx < 1 || tidx + STEP > T) return ERR_ARG;
+  if (P == 0) return 0;
+  if (!motion_pred || !p_row || !traj || !vel) return ERR_ARG;
+  step_agent_traj_kernel<<<(P + 127) / 128, 128, 0, S(stream)>>>(motion_pred, p_row, P, T, tidx, traj, vel);
+  PROSIM_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

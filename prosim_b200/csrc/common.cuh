@@ -1,0 +1,148 @@
+// Shared device helpers for the prosim_b200 kernels (sm_100a).
+//
+// Numerics policy (DESIGN.md "Numerics"): everything is IEEE fp32 -- no fast-math, no TF32/BF16 on
+// the value path -- because the closed loop amplifies rounding by x1.5-3 per tick and parity with
+// the reference's fp32 PyTorch path is gated at 1e-5 per tick.  Reductions run in a fixed order
+// (no float atomics), so results are bit-reproducible run to run and independent of batch size.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace prosim {
+
+constexpr int D = 128;        // hidden dim (waymo_demo.yaml:217)
+constexpr int H = 8;          // heads
+constexpr int DH = 16;        // head dim
+constexpr int LDS_PAD = 132;  // smem row stride for [rows][128] tiles: 16B aligned, conflict-free float4 rows
+constexpr float LN_EPS = 1e-5f;
+
+#define PROSIM_CHECK_LAUNCH()                       \
+  do {                                              \
+    cudaError_t e__ = cudaGetLastError();           \
+    if (e__ != cudaSuccess) return (int)e__;        \
+  } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// torch.remainder semantics for a positive divisor: result in [0, b)
+__device__ __forceinline__ float py_mod(float a, float b) {
+  float m = fmodf(a, b);
+  if (m != 0.0f && m < 0.0f) m += b;
+  return m;
+}
+// models/utils/geometry.py:13-17 in fp32: -pi + (a + pi) % (2 pi); constants rounded to fp32 like torch does
+__device__ __forceinline__ float wrap_angle(float a) {
+  const float PI_F = 3.14159265358979323846f;
+  const float TWO_PI_F = 6.28318530717958647692f;
+  return __fadd_rn(-PI_F, py_mod(__fadd_rn(a, PI_F), TWO_PI_F));
+}
+
+// LayerNorm of one 128-wide row held 4 values per lane (lane l owns columns 4l..4l+3), two-pass.
+// Returns the normalised values WITHOUT affine; mean/rstd out for callers that need them.
+__device__ __forceinline__ float4 ln_row_noaffine(float4 v) {
+  float mean = warp_sum((v.x + v.y) + (v.z + v.w)) * (1.0f / D);
+  float4 c = make_float4(v.x - mean, v.y - mean, v.z - mean, v.w - mean);
+  float var = warp_sum((c.x * c.x + c.y * c.y) + (c.z * c.z + c.w * c.w)) * (1.0f / D);
+  float rstd = 1.0f / sqrtf(var + LN_EPS);
+  return make_float4(c.x * rstd, c.y * rstd, c.z * rstd, c.w * rstd);
+}
+__device__ __forceinline__ float4 ln_row(float4 v, const float* __restrict__ g, const float* __restrict__ b, int lane) {
+  float4 n = ln_row_noaffine(v);
+  float4 gg = *reinterpret_cast<const float4*>(g + 4 * lane);
+  float4 bb = *reinterpret_cast<const float4*>(b + 4 * lane);
+  return make_float4(n.x * gg.x + bb.x, n.y * gg.y + bb.y, n.z * gg.z + bb.z, n.w * gg.w + bb.w);
+}
+
+// In-place LayerNorm (+ optional ReLU) over `rows` rows of a [rows][ld] smem tile of width W (64 or 128),
+// one warp per row, all warps of the CTA cooperating.  Caller syncs before and after.
+template <int W>
+__device__ __forceinline__ void ln_tile_inplace(float* tile, int ld, int rows, const float* __restrict__ g,
+                                                const float* __restrict__ b, bool relu) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  constexpr int PER = W / 32;
+  for (int r = warp; r < rows; r += nwarps) {
+    float v[PER];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { v[i] = tile[r * ld + lane * PER + i]; s += v[i]; }
+    float mean = warp_sum(s) * (1.0f / W);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { v[i] -= mean; q += v[i] * v[i]; }
+    float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / W) + LN_EPS);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      float o = v[i] * rstd * g[lane * PER + i] + b[lane * PER + i];
+      tile[r * ld + lane * PER + i] = relu ? fmaxf(o, 0.f) : o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row-tile GEMM on CUDA cores:  Y[r][n] = sum_k X[r][k] * Wt[k][n]   (r < 2*RPT, n < 128)
+//   X  : shared memory, row stride ldx floats (16B aligned rows), K multiple of 4
+//   Wt : global, K-major "transposed" weight [K][ldw] (n contiguous => coalesced across the CTA)
+// 256 threads: thread = (column n = tid & 127, row group tid >> 7); each thread keeps RPT fp32
+// accumulators, every weight it loads is reused RPT times, X reads are warp-broadcast LDS.128.
+// The k loop runs in ascending order for every output => deterministic, batch-invariant sums.
+// ---------------------------------------------------------------------------------------------
+template <int RPT>
+__device__ __forceinline__ void gemm_tile_acc(float (&acc)[RPT], const float* __restrict__ Xs, int ldx, int K,
+                                              const float* __restrict__ Wt, int ldw) {
+  const int n = threadIdx.x & 127;
+  const float* xrow = Xs + (threadIdx.x >> 7) * RPT * ldx;
+  const float* w = Wt + n;
+#pragma unroll 2
+  for (int k = 0; k < K; k += 4) {
+    float w0 = __ldg(w + (k + 0) * ldw);
+    float w1 = __ldg(w + (k + 1) * ldw);
+    float w2 = __ldg(w + (k + 2) * ldw);
+    float w3 = __ldg(w + (k + 3) * ldw);
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      float4 x = *reinterpret_cast<const float4*>(xrow + r * ldx + k);
+      acc[r] = fmaf(x.x, w0, acc[r]);
+      acc[r] = fmaf(x.y, w1, acc[r]);
+      acc[r] = fmaf(x.z, w2, acc[r]);
+      acc[r] = fmaf(x.w, w3, acc[r]);
+    }
+  }
+}
+
+template <int RPT>
+__device__ __forceinline__ void acc_init(float (&acc)[RPT], float v) {
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) acc[r] = v;
+}
+
+// Store this thread's accumulators into a smem tile column (row group aware).
+template <int RPT>
+__device__ __forceinline__ void acc_store_smem(const float (&acc)[RPT], float* Ys, int ldy, bool relu) {
+  const int n = threadIdx.x & 127;
+  float* y = Ys + (threadIdx.x >> 7) * RPT * ldy + n;
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) y[r * ldy] = relu ? fmaxf(acc[r], 0.f) : acc[r];
+}
+
+// Load a [rows x 128] tile from global (row stride 128, optional row index list) into smem (stride ld),
+// zero-filling rows >= nrows.  float4 per thread, coalesced.
+__device__ __forceinline__ void load_tile128(float* dst, int ld, const float* __restrict__ src, int row0, int nrows,
+                                             int tile_rows) {
+  for (int i = threadIdx.x; i < tile_rows * 32; i += blockDim.x) {
+    int r = i >> 5, c = (i & 31) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row0 + r < nrows) v = *reinterpret_cast<const float4*>(src + (size_t)(row0 + r) * D + c);
+    *reinterpret_cast<float4*>(dst + r * ld + c) = v;
+  }
+}
+
+}  // namespace prosim

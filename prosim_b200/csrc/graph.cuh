@@ -1,0 +1,141 @@
+// Neighbour search and per-edge relative positional encoding.
+//
+// Neighbour lists replace torch_cluster.{radius,radius_graph,knn_graph} (un-vendored wheel; call sites
+// prosim/models/scene_encoder/attn_fusion.py:107,109, decoder/sym_coord.py:86,94,
+// policy/act_decoder.py:250,259).  Semantics are those restated in oracle/graph.py and must match it
+// bit for bit: squared distance dx*dx + dy*dy with every operation rounded separately (no FMA),
+// strict `< r^2`, first `cap` hits in ascending source index, kNN ties to the lower index.
+// Layout: fixed-stride rows  nbr[q*stride + j], j < deg[q]  (ascending source index inside a row), so no
+// scan / host round trip is needed and every later kernel can be launched with a grid over rows.
+#pragma once
+#include "common.cuh"
+
+namespace prosim {
+
+__device__ __forceinline__ float sqdist_rn(float2 a, float2 b) {
+  float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y);
+  return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+}
+
+// seg[b] = {start0, len0, start1, len1}: the (up to two) contiguous source ranges of scene b.
+__global__ void __launch_bounds__(256) radius_kernel(const float2* __restrict__ qpos, const int* __restrict__ qscene,
+                                                     int Nq, const float2* __restrict__ spos,
+                                                     const int4* __restrict__ seg, float r2, int cap, int drop_self,
+                                                     int* __restrict__ nbr, int* __restrict__ deg, int stride) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 8 + warp;
+  if (q >= Nq) return;
+  const float2 p = qpos[q];
+  const int4 sg = seg[qscene[q]];
+  const int limit = cap + (drop_self ? 1 : 0);
+  const unsigned lt = (1u << lane) - 1u;
+  int count = 0, self_seen = 0;
+  int* out = nbr + (size_t)q * stride;
+  for (int s = 0; s < 2 && count < limit; ++s) {
+    const int start = s == 0 ? sg.x : sg.z, len = s == 0 ? sg.y : sg.w;
+    for (int base = 0; base < len && count < limit; base += 32) {
+      const int c = base + lane;
+      const int idx = start + c;
+      bool in = false;
+      if (c < len) in = sqdist_rn(p, spos[idx]) < r2;
+      const unsigned bal = __ballot_sync(0xffffffffu, in);
+      const int pos = count + __popc(bal & lt);
+      const bool take = in && pos < limit;
+      const bool is_self = drop_self && idx == q;
+      const unsigned sbal = __ballot_sync(0xffffffffu, take && is_self);
+      const int opos = pos - self_seen - __popc(sbal & lt);
+      if (take && !is_self && opos < stride) out[opos] = idx;
+      count += __popc(bal);
+      self_seen |= (sbal != 0u);
+    }
+  }
+  if (lane == 0) deg[q] = min(min(count, limit) - self_seen, stride);
+}
+
+// k nearest sources (self included when it is among the sources), one CTA of 128 threads per query.
+// dynamic smem: float d2[nmax] + int sel[nmax]
+__global__ void __launch_bounds__(128) knn_kernel(const float2* __restrict__ qpos, const int* __restrict__ qscene, int Nq,
+                                                  const float2* __restrict__ spos, const int4* __restrict__ seg, int k,
+                                                  int nmax, int* __restrict__ nbr, int* __restrict__ deg, int stride) {
+  extern __shared__ __align__(16) float smem[];
+  float* d2 = smem;
+  int* sel = reinterpret_cast<int*>(smem + nmax);
+  const int q = blockIdx.x;
+  const float2 p = qpos[q];
+  const int4 sg = seg[qscene[q]];
+  const int n = min(sg.y + sg.w, nmax);
+  for (int c = threadIdx.x; c < n; c += 128) {
+    const int idx = c < sg.y ? sg.x + c : sg.z + (c - sg.y);
+    d2[c] = sqdist_rn(p, spos[idx]);
+  }
+  __syncthreads();
+  const int keff = min(min(k, n), stride);
+  for (int c = threadIdx.x; c < n; c += 128) {
+    const float my = d2[c];
+    int rank = 0;
+    for (int o = 0; o < n; ++o) {
+      const float v = d2[o];
+      rank += (v < my) || (v == my && o < c);
+    }
+    sel[c] = rank < keff;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const unsigned lt = (1u << lane) - 1u;
+    int count = 0;
+    int* out = nbr + (size_t)q * stride;
+    for (int base = 0; base < n; base += 32) {
+      const int c = base + lane;
+      const bool s = c < n && sel[c];
+      const unsigned bal = __ballot_sync(0xffffffffu, s);
+      if (s) out[count + __popc(bal & lt)] = c < sg.y ? sg.x + c : sg.z + (c - sg.y);
+      count += __popc(bal);
+    }
+    if (lane == 0) deg[q] = count;
+  }
+}
+
+// Per-edge relative PE, LayerNorm-normalised WITHOUT affine (layer independent; the affine is folded into
+// the packed weights).  Reference: policy/act_decoder.py:203-221 + layers/fourier_embedding.py:56-79.
+//   input = [|dp|, wrap(theta_src - theta_dst), phi, phi],  phi = atan2(c x dp, c . dp), c = (cos, sin)(theta_dst)
+//   feature[i*32 + 2m + {0,1}] = {sin, cos}( input_i * 2pi / dim_t[m] ),  dim_t[m] = 10000^(m/16)
+// One CTA (4 warps) per destination row, a warp per edge, lane l owns features 4l..4l+3.
+// extra (optional): per-edge [128] vector added to the PE before the normalisation (condition edges,
+// condition_transformer/condition_attns.py:211-216), indexed like Z.
+__global__ void __launch_bounds__(128) edge_pe_kernel(const float2* __restrict__ dpos, const float* __restrict__ dori,
+                                                      const float2* __restrict__ spos, const float* __restrict__ sori,
+                                                      const int* __restrict__ nbr, const int* __restrict__ deg, int stride,
+                                                      const float* __restrict__ dim_t, const float* __restrict__ extra,
+                                                      float* __restrict__ Z) {
+  const int row = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_e = min(deg[row], stride);
+  const float2 pd = dpos[row];
+  const float od = dori[row];
+  const float cx = cosf(od), cy = sinf(od);
+  const int inp = lane >> 3;
+  const int m0 = (lane & 7) * 2;
+  const float dt0 = dim_t[m0], dt1 = dim_t[m0 + 1];
+  const float TWO_PI_F = 6.28318530717958647692f;
+  for (int e = warp; e < n_e; e += 4) {
+    const size_t ei = (size_t)row * stride + e;
+    const int j = nbr[ei];
+    const float2 ps = spos[j];
+    const float rx = ps.x - pd.x, ry = ps.y - pd.y;
+    float v;
+    if (inp == 0) v = sqrtf(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)));
+    else if (inp == 1) v = wrap_angle(sori[j] - od);
+    else v = atan2f(__fsub_rn(__fmul_rn(cx, ry), __fmul_rn(cy, rx)), __fadd_rn(__fmul_rn(cx, rx), __fmul_rn(cy, ry)));
+    v = v * TWO_PI_F;
+    const float a0 = v / dt0, a1 = v / dt1;
+    float4 f = make_float4(sinf(a0), cosf(a0), sinf(a1), cosf(a1));
+    if (extra != nullptr) {
+      const float4 x = *reinterpret_cast<const float4*>(extra + ei * D + 4 * lane);
+      f.x += x.x; f.y += x.y; f.z += x.z; f.w += x.w;
+    }
+    *reinterpret_cast<float4*>(Z + ei * D + 4 * lane) = ln_row_noaffine(f);
+  }
+}
+
+}  // namespace prosim

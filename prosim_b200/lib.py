@@ -1,0 +1,103 @@
+"""ctypes binding of libprosim_b200.so (include/prosim_b200.h).  No pybind / torch extension layer:
+tensors cross the boundary as raw device pointers (``tensor.data_ptr()``) plus sizes and the CUDA
+stream handle.  There is NO fallback: a missing library, a missing symbol or a non-zero return code
+raises immediately."""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_float, c_int, c_int32, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libprosim_b200.so')
+ABI_VERSION = 1
+
+SYMBOLS = (
+    'prosim_abi_version', 'prosim_attn_layer_floats', 'prosim_pointnet_floats', 'prosim_head_floats',
+    'prosim_mlp2_floats', 'prosim_attn_workspace_floats', 'prosim_pointnet_fwd', 'prosim_build_radius_edges',
+    'prosim_build_knn_edges', 'prosim_edge_pe', 'prosim_attn_kv', 'prosim_attn_layer_fwd', 'prosim_attn_stack_fwd',
+    'prosim_policy_head_fwd', 'prosim_reconst_fwd', 'prosim_mlp2_fwd', 'prosim_init_traj', 'prosim_step_env',
+    'prosim_gather_pose', 'prosim_step_agent_traj',
+)
+
+
+class Graph(Structure):
+    _fields_ = [('z', c_void_p), ('nbr', c_void_p), ('deg', c_void_p), ('stride', c_int32), ('max_deg', c_int32)]
+
+
+class StackSide(Structure):
+    _fields_ = [('w', c_void_p), ('kv', c_void_p), ('kv_layer_stride', c_size_t), ('graph', Graph)]
+
+
+class ProSimLibError(RuntimeError):
+    pass
+
+
+_P = c_void_p
+_SIGS = {
+    'prosim_pointnet_fwd': [c_int, _P, _P, _P, c_int, _P, _P, _P],
+    'prosim_build_radius_edges': [_P, _P, c_int, _P, _P, c_float, c_int, c_int, _P, _P, c_int, _P],
+    'prosim_build_knn_edges': [_P, _P, c_int, _P, _P, c_int, c_int, _P, _P, c_int, _P],
+    'prosim_edge_pe': [_P, _P, c_int, _P, _P, _P, _P, c_int, _P, _P, _P, _P],
+    'prosim_attn_kv': [_P, c_int, _P, c_size_t, c_int, _P, c_size_t, _P],
+    'prosim_attn_layer_fwd': [_P, c_int, _P, c_int, POINTER(Graph), _P, _P, c_size_t, _P, _P],
+    'prosim_attn_stack_fwd': [_P, c_int, c_int, POINTER(StackSide), POINTER(StackSide), _P, c_size_t, _P, _P],
+    'prosim_policy_head_fwd': [_P, _P, c_int, _P, _P, _P],
+    'prosim_reconst_fwd': [_P, c_int, _P, _P, _P],
+    'prosim_mlp2_fwd': [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P],
+    'prosim_init_traj': [_P, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P],
+    'prosim_step_env': [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P],
+    'prosim_gather_pose': [_P, _P, _P, c_int, _P, _P, _P],
+    'prosim_step_agent_traj': [_P, _P, c_int, c_int, c_int, _P, _P, _P],
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; verify every declared symbol and the packed-weight sizes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ProSimLibError(f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                             '(there is no CPU or PyTorch fallback for the rollout path)')
+    lib = ctypes.CDLL(LIB_PATH)
+    missing = [s for s in SYMBOLS if not hasattr(lib, s)]
+    if missing:
+        raise ProSimLibError(f'libprosim_b200.so lacks symbols {missing}')
+    for name in ('prosim_abi_version', 'prosim_attn_layer_floats', 'prosim_pointnet_floats', 'prosim_head_floats',
+                 'prosim_mlp2_floats'):
+        getattr(lib, name).restype = c_int
+        getattr(lib, name).argtypes = []
+    lib.prosim_attn_workspace_floats.restype = c_size_t
+    lib.prosim_attn_workspace_floats.argtypes = [c_int, c_int]
+    for name, sig in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.restype = c_int
+        fn.argtypes = sig
+    if lib.prosim_abi_version() != ABI_VERSION:
+        raise ProSimLibError('libprosim_b200.so ABI version mismatch: rebuild')
+    from . import weights
+    sizes = (lib.prosim_attn_layer_floats(), lib.prosim_pointnet_floats(), lib.prosim_head_floats(),
+             lib.prosim_mlp2_floats())
+    want = (weights.ATTN_LAYER_FLOATS, weights.POINTNET_FLOATS, weights.HEAD_FLOATS, weights.MLP2_FLOATS)
+    if sizes != want:
+        raise ProSimLibError(f'packed weight layout mismatch: library {sizes} vs packer {want}')
+    _lib = lib
+    return lib
+
+
+def check(code, what):
+    if code != 0:
+        kind = 'bad argument' if code == -1 else 'workspace too small' if code == -2 else f'cudaError {code}'
+        raise ProSimLibError(f'{what} failed: {kind}')
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args), name)
+
+
+def ptr(t, offset_elems=0):
+    """Device pointer of a tensor (plus an element offset); None -> NULL."""
+    if t is None:
+        return None
+    return t.data_ptr() + offset_elems * t.element_size()

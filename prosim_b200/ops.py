@@ -1,0 +1,204 @@
+"""Thin tensor-level wrappers over the C ABI (one per entry point of include/prosim_b200.h).
+
+Plumbing only: shape/dtype/device checks, output allocation with torch, pointer extraction.  Every
+function enqueues on ``torch.cuda.current_stream()`` and returns device tensors; nothing here computes.
+"""
+import ctypes
+
+import torch
+
+from . import lib
+from .lib import Graph, StackSide, ptr
+
+D = 128
+HEADS = 8
+ATTN_WS_PER_DST = 2 * (D + HEADS * D + D + D) + HEADS * D + D + 2 * D
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise lib.ProSimLibError(f'{name} must be a CUDA tensor (no CPU fallback on this path)')
+    if t.dtype != dtype:
+        raise TypeError(f'{name}: expected {dtype}, got {t.dtype}')
+    if not t.is_contiguous():
+        raise ValueError(f'{name} must be contiguous')
+
+
+def as_u8(mask):
+    """torch.bool and torch.uint8 share a 1-byte layout: reinterpret without copying."""
+    return mask.view(torch.uint8) if mask.dtype == torch.bool else mask
+
+
+class EdgeList:
+    """Fixed-stride neighbour lists (+ the per-edge normalised relative PE once computed)."""
+
+    def __init__(self, nbr, deg, stride, max_deg, z=None):
+        self.nbr, self.deg, self.stride, self.max_deg, self.z = nbr, deg, int(stride), int(max_deg), z
+
+    @property
+    def n_dst(self):
+        return self.deg.shape[0]
+
+    def c_struct(self):
+        return Graph(ptr(self.z), ptr(self.nbr), ptr(self.deg), self.stride, self.max_deg)
+
+    def to_edge_index(self):
+        """[2, E] (row0 = source, row1 = destination) on the host, for bit-exact comparison with the oracle."""
+        deg = self.deg.cpu().long()
+        nbr = self.nbr.view(self.n_dst, self.stride).cpu().long()
+        j = torch.arange(self.stride)[None, :] < deg[:, None]
+        dst = torch.arange(self.n_dst)[:, None].expand_as(nbr)[j]
+        return torch.stack([nbr[j], dst], dim=0)
+
+
+def pointnet(kind, x, mask, rows, w_arena, w_off, out=None):
+    _chk(x, torch.float32, 'x'), _chk(rows, torch.int32, 'rows')
+    mask = as_u8(mask)
+    _chk(mask, torch.uint8, 'mask')
+    n = rows.shape[0]
+    if out is None:
+        out = torch.empty(n, D, device=x.device, dtype=torch.float32)
+    lib.call('prosim_pointnet_fwd', kind, ptr(x), ptr(mask), ptr(rows), n, ptr(w_arena, w_off), ptr(out), _stream())
+    return out
+
+
+def radius_edges(qpos, qscene, spos, seg, r, cap, stride, drop_self=False, nbr=None, deg=None):
+    for t, n in ((qpos, 'qpos'), (spos, 'spos')):
+        _chk(t, torch.float32, n)
+    _chk(qscene, torch.int32, 'qscene'), _chk(seg, torch.int32, 'seg')
+    nq = qpos.shape[0]
+    stride = max(int(stride), 1)
+    if nbr is None:
+        nbr = torch.empty(nq * stride, device=qpos.device, dtype=torch.int32)
+        deg = torch.empty(nq, device=qpos.device, dtype=torch.int32)
+    lib.call('prosim_build_radius_edges', ptr(qpos), ptr(qscene), nq, ptr(spos), ptr(seg), float(r), int(cap),
+             int(bool(drop_self)), ptr(nbr), ptr(deg), stride, _stream())
+    return EdgeList(nbr, deg, stride, stride)
+
+
+def knn_edges(qpos, qscene, spos, seg, k, nmax, stride):
+    for t, n in ((qpos, 'qpos'), (spos, 'spos')):
+        _chk(t, torch.float32, n)
+    _chk(qscene, torch.int32, 'qscene'), _chk(seg, torch.int32, 'seg')
+    nq = qpos.shape[0]
+    stride = max(int(stride), 1)
+    nbr = torch.empty(nq * stride, device=qpos.device, dtype=torch.int32)
+    deg = torch.empty(nq, device=qpos.device, dtype=torch.int32)
+    lib.call('prosim_build_knn_edges', ptr(qpos), ptr(qscene), nq, ptr(spos), ptr(seg), int(k), int(nmax), ptr(nbr),
+             ptr(deg), stride, _stream())
+    return EdgeList(nbr, deg, stride, stride)
+
+
+def edge_pe(edges, dpos, dori, spos, sori, dim_t16, extra=None, z=None):
+    for t, n in ((dpos, 'dpos'), (dori, 'dori'), (spos, 'spos'), (sori, 'sori'), (dim_t16, 'dim_t16'), (extra, 'extra')):
+        _chk(t, torch.float32, n)
+    n_dst = edges.n_dst
+    if z is None:
+        z = torch.empty(n_dst * edges.stride, D, device=dpos.device, dtype=torch.float32)
+    lib.call('prosim_edge_pe', ptr(dpos), ptr(dori), n_dst, ptr(spos), ptr(sori), ptr(edges.nbr), ptr(edges.deg),
+             edges.stride, ptr(dim_t16), ptr(extra), ptr(z), _stream())
+    edges.z = z
+    return edges
+
+
+def attn_kv(x_src, w_arena, w_off, n_layers, layer_floats, kv=None):
+    _chk(x_src, torch.float32, 'x_src')
+    n = x_src.shape[0]
+    if kv is None:
+        kv = torch.empty(n_layers, n, 2 * D, device=x_src.device, dtype=torch.float32)
+    lib.call('prosim_attn_kv', ptr(x_src), n, ptr(w_arena, w_off), layer_floats, n_layers, ptr(kv), n * 2 * D, _stream())
+    return kv
+
+
+def attn_workspace(n_dst, n_src, device):
+    n = lib.load().prosim_attn_workspace_floats(int(n_dst), int(n_src))
+    return torch.empty(n, device=device, dtype=torch.float32)
+
+
+def attn_layer(x_src, x_dst, edges, w_arena, w_off, out=None, workspace=None):
+    _chk(x_src, torch.float32, 'x_src'), _chk(x_dst, torch.float32, 'x_dst')
+    n_src, n_dst = x_src.shape[0], x_dst.shape[0]
+    if workspace is None:
+        workspace = attn_workspace(n_dst, n_src, x_dst.device)
+    if out is None:
+        out = torch.empty_like(x_dst)
+    g = edges.c_struct()
+    lib.call('prosim_attn_layer_fwd', ptr(x_src), n_src, ptr(x_dst), n_dst, ctypes.byref(g), ptr(w_arena, w_off),
+             ptr(workspace), workspace.numel(), ptr(out), _stream())
+    return out
+
+
+def stack_side(w_arena, w_off, edges, kv=None):
+    return StackSide(ptr(w_arena, w_off), ptr(kv), (kv.shape[1] * kv.shape[2]) if kv is not None else 0, edges.c_struct())
+
+
+def attn_stack(x, n_layers, side_a, side_b=None, out=None, workspace=None):
+    _chk(x, torch.float32, 'x')
+    n = x.shape[0]
+    if workspace is None:
+        workspace = attn_workspace(n, n, x.device)
+    if out is None:
+        out = torch.empty_like(x)
+    lib.call('prosim_attn_stack_fwd', ptr(x), n, int(n_layers), ctypes.byref(side_a),
+             ctypes.byref(side_b) if side_b is not None else None, ptr(workspace), workspace.numel(), ptr(out), _stream())
+    return out
+
+
+def policy_head(feat, agent_type, w_arena, w_off, motion_pred=None):
+    _chk(feat, torch.float32, 'feat'), _chk(agent_type, torch.int32, 'agent_type')
+    P = feat.shape[0]
+    if motion_pred is None:
+        motion_pred = torch.empty(P, 1, 10, 5, device=feat.device, dtype=torch.float32)
+    lib.call('prosim_policy_head_fwd', ptr(feat), ptr(agent_type), P, ptr(w_arena, w_off), ptr(motion_pred), _stream())
+    return motion_pred
+
+
+def reconst(emd, w_arena, w_off):
+    _chk(emd, torch.float32, 'emd')
+    out = torch.empty(emd.shape[0], 2, device=emd.device, dtype=torch.float32)
+    lib.call('prosim_reconst_fwd', ptr(emd), emd.shape[0], ptr(w_arena, w_off), ptr(out), _stream())
+    return out
+
+
+def mlp2(x, k0, use_ln, w_arena, w_off, tpe_col=None, dim_t128=None):
+    _chk(x, torch.float32, 'x')
+    n, ld = x.shape
+    out = torch.empty(n, D, device=x.device, dtype=torch.float32)
+    tpe = ptr(x, tpe_col) if tpe_col is not None else None
+    lib.call('prosim_mlp2_fwd', ptr(x), ld, int(k0), n, int(bool(use_ln)), ptr(w_arena, w_off), tpe, ld,
+             ptr(dim_t128) if tpe_col is not None else None, ptr(out), _stream())
+    return out
+
+
+def init_traj(obs_in, obs_pos, obs_head, p_slot, p_row, T, traj, vel, init_pos, init_heading):
+    lib.call('prosim_init_traj', ptr(obs_in), ptr(obs_pos), ptr(obs_head), ptr(p_slot), ptr(p_row), p_row.shape[0], int(T),
+             ptr(traj), ptr(vel), ptr(init_pos), ptr(init_heading), _stream())
+
+
+def step_env(traj, vel, init_pos, init_heading, p_row, p_slot, T, tidx, p_pos, p_ori, fut=None):
+    """fut: None on the first tick, else (input, mask, position, heading) tensors of fut_obs[t] (written in place)."""
+    f_in = f_mask = f_pos = f_head = None
+    if fut is not None:
+        f_in, f_mask, f_pos, f_head = fut
+        f_mask = as_u8(f_mask)
+        for t, n in ((f_in, 'fut input'), (f_pos, 'fut position'), (f_head, 'fut heading')):
+            _chk(t, torch.float32, n)
+    lib.call('prosim_step_env', ptr(traj), ptr(vel), ptr(init_pos), ptr(init_heading), ptr(p_row), ptr(p_slot),
+             p_row.shape[0], int(T), int(tidx), ptr(p_pos), ptr(p_ori), ptr(f_in), ptr(f_mask), ptr(f_pos), ptr(f_head),
+             _stream())
+
+
+def gather_pose(pos, head, rows, out_pos, out_ori):
+    _chk(pos, torch.float32, 'pos'), _chk(head, torch.float32, 'head')
+    lib.call('prosim_gather_pose', ptr(pos), ptr(head), ptr(rows), rows.shape[0], ptr(out_pos), ptr(out_ori), _stream())
+
+
+def step_agent_traj(motion_pred, p_row, T, tidx, traj, vel):
+    lib.call('prosim_step_agent_traj', ptr(motion_pred), ptr(p_row), p_row.shape[0], int(T), int(tidx), ptr(traj), ptr(vel),
+             _stream())

@@ -139,3 +139,155 @@ def param_shapes_cache(goal_condition):
     if goal_condition not in _SHAPES:
         _SHAPES[goal_condition] = [(n, s) for n, s, _ in param_specs(goal_condition)]
     return _SHAPES[goal_condition]
+
+
+# ----------------------------------------------------------------------------- packing (mirror of csrc/weights_layout.h)
+ATTN_LAYER_FLOATS = 512 + 3 * (16384 + 128) + 2 * 16384 + (16384 + 128) + (2 * 16384 + 128) + (16384 + 128) + 512 \
+    + (65536 + 512) + (65536 + 128) + 256
+POINTNET_FLOATS = (24 * 128 + 384) + (16384 + 384) + (16384 + 128) + (2 * 16384 + 384) + (16384 + 128) + 2 * (16384 + 128)
+_MLP3_FLOATS = 2 * (16384 + 384) + (64 * 128 + 128)
+HEAD_FLOATS = 3 * 128 + 3 * (16384 + 384) + 2 * _MLP3_FLOATS
+MLP2_FLOATS = 8 * 128 + 384 + 16384 + 128
+
+
+def _f64(t):
+    return t.detach().double().cpu()
+
+
+def pack_attn_layer(sd, p):
+    """One AttentionLayer -> the aw:: layout.  LayerNorm(r)'s affine and the 1/sqrt(head_dim) scale are folded
+    into the weights (see weights_layout.h); the folds are evaluated in fp64 and rounded once."""
+    w = lambda n: _f64(sd[f'{p}.{n}'])
+    g_r, b_r = w('attn_prenorm_r.weight'), w('attn_prenorm_r.bias')
+    wkr, wvr = w('to_k_r.weight'), w('to_v_r.weight')
+    wg = w('to_g.weight')
+    parts = [
+        w('attn_prenorm_x_src.weight'), w('attn_prenorm_x_src.bias'),
+        w('attn_prenorm_x_dst.weight'), w('attn_prenorm_x_dst.bias'),
+        (0.25 * w('to_q.weight')).t(), 0.25 * w('to_q.bias'),
+        w('to_k.weight').t(), wkr @ b_r,
+        w('to_v.weight').t(), w('to_v.bias') + wvr @ b_r + w('to_v_r.bias'),
+        wkr * g_r[None, :],
+        (wvr * g_r[None, :]).t(),
+        w('to_s.weight').t(), w('to_s.bias'),
+        wg[:, :D].t(), wg[:, D:].t(), w('to_g.bias'),
+        w('to_out.weight').t(), w('to_out.bias'),
+        w('attn_postnorm.weight'), w('attn_postnorm.bias'),
+        w('ff_prenorm.weight'), w('ff_prenorm.bias'),
+        w('ff_mlp.0.weight').t(), w('ff_mlp.0.bias'),
+        w('ff_mlp.3.weight').t(), w('ff_mlp.3.bias'),
+        w('ff_postnorm.weight'), w('ff_postnorm.bias'),
+    ]
+    out = torch.cat([x.contiguous().reshape(-1) for x in parts]).float()
+    assert out.numel() == ATTN_LAYER_FLOATS
+    return out
+
+
+def _pad_rows(wt, rows):
+    out = torch.zeros(rows, wt.shape[1], dtype=wt.dtype)
+    out[:wt.shape[0]] = wt
+    return out
+
+
+def _pad_cols(wt, cols=D):
+    out = torch.zeros(wt.shape[0], cols, dtype=wt.dtype)
+    out[:, :wt.shape[1]] = wt
+    return out
+
+
+def _pad_vec(v, n=D):
+    out = torch.zeros(n, dtype=v.dtype)
+    out[:v.shape[0]] = v
+    return out
+
+
+def pack_pointnet(sd, p, n_pre):
+    w = lambda n: _f64(sd[f'{p}.{n}'])
+    z = torch.zeros(D, dtype=torch.float64)
+    zw = torch.zeros(D, D, dtype=torch.float64)
+    if n_pre == 1:
+        pre = [_pad_rows(w('pre_mlps.mlp.0.weight').t(), 24), w('pre_mlps.mlp.0.bias'), z, z,
+               zw, z, z, z, zw, z]
+    else:
+        pre = [_pad_rows(w('pre_mlps.mlp.0.weight').t(), 24), w('pre_mlps.mlp.0.bias'),
+               w('pre_mlps.mlp.1.weight'), w('pre_mlps.mlp.1.bias'),
+               w('pre_mlps.mlp.3.weight').t(), w('pre_mlps.mlp.3.bias'),
+               w('pre_mlps.mlp.4.weight'), w('pre_mlps.mlp.4.bias'),
+               w('pre_mlps.mlp.6.weight').t(), w('pre_mlps.mlp.6.bias')]
+    m0 = w('mlps.mlp.0.weight')
+    parts = pre + [m0[:, :D].t(), m0[:, D:].t(), w('mlps.mlp.0.bias'), w('mlps.mlp.1.weight'), w('mlps.mlp.1.bias'),
+                   w('mlps.mlp.3.weight').t(), w('mlps.mlp.3.bias'),
+                   w('out_mlps.mlp.0.weight').t(), w('out_mlps.mlp.0.bias'),
+                   w('out_mlps.mlp.2.weight').t(), w('out_mlps.mlp.2.bias')]
+    out = torch.cat([x.contiguous().reshape(-1) for x in parts]).float()
+    assert out.numel() == POINTNET_FLOATS
+    return out
+
+
+def _pack_mlp3(sd, p):
+    w = lambda n: _f64(sd[f'{p}.{n}'])
+    parts = [w('mlp.0.weight').t(), w('mlp.0.bias'), w('mlp.1.weight'), w('mlp.1.bias'),
+             _pad_cols(w('mlp.3.weight').t()), _pad_vec(w('mlp.3.bias')), _pad_vec(w('mlp.4.weight')),
+             _pad_vec(w('mlp.4.bias')),
+             _pad_cols(w('mlp.6.weight').t()), _pad_vec(w('mlp.6.bias'))]
+    return [x.contiguous().reshape(-1) for x in parts]
+
+
+def pack_head(sd, p='policy.act_decoder'):
+    w = lambda n: _f64(sd[f'{p}.{n}'])
+    parts = [w('motion_anchors.weight').reshape(-1)]
+    for i in range(3):
+        parts += [w(f'CG_decode.CGs.{i}.MLP.0.weight').t().contiguous().reshape(-1), w(f'CG_decode.CGs.{i}.MLP.0.bias'),
+                  w(f'CG_decode.CGs.{i}.MLP.1.weight'), w(f'CG_decode.CGs.{i}.MLP.1.bias')]
+    parts += _pack_mlp3(sd, f'{p}.motion_head') + _pack_mlp3(sd, f'{p}.pred_mlp')
+    out = torch.cat(parts).float()
+    assert out.numel() == HEAD_FLOATS
+    return out
+
+
+def pack_mlp2(sd, p, with_ln):
+    w = lambda n: _f64(sd[f'{p}.{n}'])
+    z = torch.zeros(D, dtype=torch.float64)
+    second = 'mlp.3' if with_ln else 'mlp.2'
+    parts = [_pad_rows(w('mlp.0.weight').t(), 8), w('mlp.0.bias'),
+             w('mlp.1.weight') if with_ln else z, w('mlp.1.bias') if with_ln else z,
+             w(f'{second}.weight').t(), w(f'{second}.bias')]
+    out = torch.cat([x.contiguous().reshape(-1) for x in parts]).float()
+    assert out.numel() == MLP2_FLOATS
+    return out
+
+
+def pack_model(sd, num_layers=6, cond_layers=3):
+    """state_dict -> (arena fp32 [n], {section: float offset}).  Sections are 256-byte aligned."""
+    goal = any(k.startswith('condition_transformers.') for k in sd)
+    sections = OrderedDict()
+    sections['map_enc'] = pack_pointnet(sd, 'scene_encoder.map_encoder', 3)
+    sections['obs_enc'] = pack_pointnet(sd, 'scene_encoder.obs_encoder', 1)
+    stacks = [('enc_a2a', 'scene_encoder.a2a_attn_layers', num_layers),
+              ('enc_s2s', 'scene_encoder.s2s_attn_layers', num_layers),
+              ('dec_p2p', 'decoder.p2p_attn_layers', num_layers),
+              ('dec_s2p', 'decoder.s2p_attn_layers', num_layers),
+              ('pol_a2p', 'policy.act_decoder.a2p_attn_layers', num_layers),
+              ('pol_m2p', 'policy.act_decoder.m2p_attn_layers', num_layers)]
+    if goal:
+        stacks.append(('cond_attn', 'condition_transformers.policy_decoder.condition_attn.attn_layers', cond_layers))
+    for name, prefix, n in stacks:
+        sections[name] = torch.cat([pack_attn_layer(sd, f'{prefix}.{i}') for i in range(n)])
+    sections['prompt_mlp'] = pack_mlp2(sd, 'prompt_encoder.motion_pred.state_encoder', True)
+    if goal:
+        sections['goal_mlp'] = pack_mlp2(sd, 'condition_transformers.policy_decoder.condition_encoders.goal.goal_encoder',
+                                         False)
+    sections['head'] = pack_head(sd)
+    # FourierEmbeddingFix denominators, evaluated by torch exactly as the reference does (fourier_embedding.py:66-67)
+    dt = torch.arange(128 / 4, dtype=torch.float32)
+    sections['dim_t16'] = (10000 ** (2 * (dt // 2) / (128 / 4)))[0::2].contiguous()
+    dt = torch.arange(128, dtype=torch.float32)
+    sections['dim_t128'] = (10000 ** (2 * (dt // 2) / 128)).contiguous()
+    offsets, total = OrderedDict(), 0
+    for k, v in sections.items():
+        offsets[k] = total
+        total += (v.numel() + 63) // 64 * 64
+    arena = torch.zeros(total, dtype=torch.float32)
+    for k, v in sections.items():
+        arena[offsets[k]:offsets[k] + v.numel()] = v
+    return arena, offsets

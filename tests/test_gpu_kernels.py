@@ -1,0 +1,253 @@
+"""GPU (-m gpu): every C-ABI entry point against the matching piece of the CPU oracle, on seeded inputs.
+Tolerances are written per test; integer/index results must be bit exact."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import graph as ograph
+from oracle.prosim_oracle import ProSimOracle, fourier_fix, rel_pe_input
+from prosim_b200 import weights
+from tests.helpers import edge_set
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ctx():
+    from prosim_b200 import lib, ops
+    lib.load()
+    sd = weights.random_state_dict(0, True)
+    arena, off = weights.pack_model(sd)
+    return dict(ops=ops, sd=sd, arena=arena.cuda(), off=off, oracle=ProSimOracle(sd, True))
+
+
+def _scene_points(g, counts, spread):
+    pos, batch = [], []
+    for b, n in enumerate(counts):
+        pos.append((torch.rand(n, 2, generator=g) - 0.5) * spread)
+        batch.append(torch.full((n,), b, dtype=torch.long))
+    return torch.cat(pos), torch.cat(batch)
+
+
+def _seg(counts, extra_counts=None, extra_base=0):
+    rows, off, off2 = [], 0, extra_base
+    for i, n in enumerate(counts):
+        e = extra_counts[i] if extra_counts else 0
+        rows.append([off, n, off2 if extra_counts else 0, e])
+        off += n
+        off2 += e
+    return torch.tensor(rows, dtype=torch.int32)
+
+
+# ------------------------------------------------------------------------------------ pointnet
+@pytest.mark.parametrize('kind', ['obs', 'map'])
+def test_pointnet_matches_oracle(ctx, kind):
+    ops, orc = ctx['ops'], ctx['oracle']
+    g = torch.Generator().manual_seed(3)
+    B, N = 3, 37
+    if kind == 'obs':
+        x = torch.randn(B, N, 11, 24, generator=g)
+        pmask = torch.rand(B, N, 11, generator=g) > 0.25
+        pmask[0, 0] = False            # a polyline with no valid point
+        pmask[1, 3] = True
+        mask = pmask[..., None].expand(B, N, 11, 24).clone()
+        x[~mask] = float('nan')        # the reference leaves NaN under a False mask
+        ref = orc.pointnet('scene_encoder.obs_encoder', torch.nan_to_num(x), pmask, 1, 2)
+        key, k = 'obs_enc', 0
+    else:
+        x = torch.randn(B, N, 19, 11, generator=g)
+        pmask = torch.rand(B, N, 19, generator=g) > 0.25
+        pmask[2, 5] = False
+        mask = pmask
+        ref = orc.pointnet('scene_encoder.map_encoder', x, pmask, 3, 2)
+        key, k = 'map_enc', 1
+    valid = pmask.any(-1).reshape(-1)
+    rows = torch.nonzero(valid).reshape(-1).to(torch.int32)
+    out = ops.pointnet(k, x.cuda(), mask.cuda(), rows.cuda(), ctx['arena'], ctx['off'][key]).cpu()
+    ref = ref.reshape(B * N, 128)[valid]
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max() < 2e-5      # fp32, different summation order only
+
+
+# ------------------------------------------------------------------------------------ neighbour search
+def test_radius_edges_bit_exact(ctx):
+    ops = ctx['ops']
+    g = torch.Generator().manual_seed(5)
+    q_counts, s_counts = [40, 7, 0, 25], [90, 33, 12, 64]
+    qpos, qb = _scene_points(g, q_counts, 120.0)
+    spos, sb = _scene_points(g, s_counts, 120.0)
+    for r, cap in ((50.0, 768), (30.0, 5), (300.0, 16)):
+        ref = ograph.radius(spos, qpos, r, sb, qb, max_num_neighbors=cap)       # [2,E]: row0 = query, row1 = source
+        stride = min(cap, max(s_counts))
+        e = ops.radius_edges(qpos.cuda(), qb.int().cuda(), spos.cuda(), _seg(s_counts).cuda(), r, cap, stride)
+        mine = e.to_edge_index()                                                # row0 = source, row1 = dst(query)
+        assert torch.equal(mine[1], ref[0]) and torch.equal(mine[0], ref[1]), (r, cap)
+
+
+def test_radius_graph_drop_self_bit_exact(ctx):
+    ops = ctx['ops']
+    g = torch.Generator().manual_seed(6)
+    counts = [33, 1, 20]
+    pos, b = _scene_points(g, counts, 60.0)
+    for r, cap in ((300.0, 512), (20.0, 4)):
+        ref = ograph.radius_graph(pos, r, b, loop=False, max_num_neighbors=cap)  # row0 = source, row1 = target
+        e = ops.radius_edges(pos.cuda(), b.int().cuda(), pos.cuda(), _seg(counts).cuda(), r, cap,
+                             min(cap + 1, max(counts)), drop_self=True)
+        assert edge_set(e.to_edge_index()) == edge_set(ref)
+        assert e.to_edge_index().shape[1] == ref.shape[1]
+
+
+def test_knn_edges_bit_exact(ctx):
+    ops = ctx['ops']
+    g = torch.Generator().manual_seed(7)
+    m_counts, a_counts = [50, 9, 70], [20, 3, 40]
+    mpos, mb = _scene_points(g, m_counts, 200.0)
+    apos, ab = _scene_points(g, a_counts, 100.0)
+    pos, b = torch.cat([mpos, apos]), torch.cat([mb, ab])
+    NM = mpos.shape[0]
+    # scene graph: two source segments per scene (map rows, then agent rows), self loops kept
+    ref = ograph.knn_graph(pos, 32, b, loop=True)
+    seg = _seg(m_counts, a_counts, extra_base=NM)
+    nmax = max(m + a for m, a in zip(m_counts, a_counts))
+    e = ops.knn_edges(pos.cuda(), b.int().cuda(), pos.cuda(), seg.cuda(), 32, nmax, min(32, nmax))
+    assert edge_set(e.to_edge_index()) == edge_set(ref)
+    assert e.to_edge_index().shape[1] == ref.shape[1]
+    # agent graph with k larger than some scenes
+    ref = ograph.knn_graph(apos, 16, ab, loop=True)
+    e = ops.knn_edges(apos.cuda(), ab.int().cuda(), apos.cuda(), _seg(a_counts).cuda(), 16, max(a_counts), 16)
+    assert edge_set(e.to_edge_index()) == edge_set(ref)
+
+
+# ------------------------------------------------------------------------------------ relative PE
+def _random_graph(g, n_dst, n_src, stride, empty_row=True):
+    deg = torch.randint(1, min(stride, n_src) + 1, (n_dst,), generator=g)
+    if empty_row:
+        deg[1] = 0
+    nbr = torch.zeros(n_dst, stride, dtype=torch.long)
+    for i in range(n_dst):
+        nbr[i, :deg[i]] = torch.sort(torch.randperm(n_src, generator=g)[:deg[i]])[0]
+    j = torch.arange(stride)[None, :] < deg[:, None]
+    edge_index = torch.stack([nbr[j], torch.arange(n_dst)[:, None].expand(n_dst, stride)[j]])
+    return nbr, deg, j, edge_index
+
+
+def test_edge_pe_matches_oracle(ctx):
+    ops = ctx['ops']
+    g = torch.Generator().manual_seed(9)
+    n_dst, n_src, stride = 50, 80, 24
+    nbr, deg, j, ei = _random_graph(g, n_dst, n_src, stride)
+    dpos, spos = (torch.rand(n_dst, 2, generator=g) - 0.5) * 300, (torch.rand(n_src, 2, generator=g) - 0.5) * 300
+    dori, sori = (torch.rand(n_dst, generator=g) - 0.5) * 2 * math.pi, (torch.rand(n_src, generator=g) - 0.5) * 2 * math.pi
+    spos[nbr[0, 0]] = dpos[0]        # a zero-offset edge: atan2(0, 0) = 0 must be reproduced
+    pe = fourier_fix(rel_pe_input(ei, dori[:, None], dpos, sori[:, None], spos), 128 / 4)
+    ref = F.layer_norm(pe, (128,))
+    e = ops.EdgeList(nbr.reshape(-1).int().cuda(), deg.int().cuda(), stride, stride)
+    dim_t = ctx['arena'][ctx['off']['dim_t16']:ctx['off']['dim_t16'] + 16]
+    ops.edge_pe(e, dpos.cuda(), dori.cuda(), spos.cuda(), sori.cuda(), dim_t)
+    z = e.z.view(n_dst, stride, 128).cpu()[j]
+    # sin/cos arguments reach ~2000 rad: one fp32 ulp of the argument is 1.2e-4, the reference and the GPU round
+    # the argument identically (same mul / div), so only the sin/cos implementations differ (<= 2 ulp)
+    assert (z - ref).abs().max() < 5e-6
+
+
+# ------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize('bipartite', [True, False])
+@pytest.mark.parametrize('n_dst', [23, 300])
+def test_attention_layer_matches_oracle(ctx, bipartite, n_dst):
+    ops, orc = ctx['ops'], ctx['oracle']
+    g = torch.Generator().manual_seed(11 + n_dst)
+    n_src = n_dst if not bipartite else 2 * n_dst + 5
+    stride = 40
+    nbr, deg, j, ei = _random_graph(g, n_dst, n_src, stride)
+    x_src = torch.randn(n_src, 128, generator=g)
+    x_dst = x_src if not bipartite else torch.randn(n_dst, 128, generator=g)
+    r = torch.randn(ei.shape[1], 128, generator=g)
+    prefix = 'policy.act_decoder.m2p_attn_layers.2' if bipartite else 'decoder.p2p_attn_layers.4'
+    key = ('pol_m2p', 2) if bipartite else ('dec_p2p', 4)
+    ref = orc.attention_layer(prefix, x_src, x_dst, r, ei, bipartite)
+    z = torch.zeros(n_dst, stride, 128)
+    z[j] = F.layer_norm(r, (128,))
+    e = ops.EdgeList(nbr.reshape(-1).int().cuda(), deg.int().cuda(), stride, stride, z.reshape(-1, 128).cuda())
+    xs = x_src.cuda()
+    xd = xs if not bipartite else x_dst.cuda()
+    out = ops.attn_layer(xs, xd, e, ctx['arena'], ctx['off'][key[0]] + key[1] * weights.ATTN_LAYER_FLOATS).cpu()
+    assert (out - ref).abs().max() < 2e-5
+
+
+def test_attention_stack_matches_oracle(ctx):
+    """6 x (a2p, m2p) with fixed sources -- the policy tick's core -- and 3 x self-source layers."""
+    ops, orc = ctx['ops'], ctx['oracle']
+    g = torch.Generator().manual_seed(13)
+    P, NA, NM, sa, sm = 70, 64, 150, 30, 50
+    nbr_a, deg_a, ja, ei_a = _random_graph(g, P, NA, sa)
+    nbr_m, deg_m, jm, ei_m = _random_graph(g, P, NM, sm, empty_row=False)
+    x_p, x_a, x_m = torch.randn(P, 128, generator=g), torch.randn(NA, 128, generator=g), torch.randn(NM, 128, generator=g)
+    r_a, r_m = torch.randn(ei_a.shape[1], 128, generator=g), torch.randn(ei_m.shape[1], 128, generator=g)
+    ref = x_p
+    for i in range(6):
+        ref = orc.attention_layer(f'policy.act_decoder.a2p_attn_layers.{i}', x_a, ref, r_a, ei_a, True)
+        ref = orc.attention_layer(f'policy.act_decoder.m2p_attn_layers.{i}', x_m, ref, r_m, ei_m, True)
+
+    def edges(nbr, deg, j, r, stride):
+        z = torch.zeros(P, stride, 128)
+        z[j] = F.layer_norm(r, (128,))
+        return ops.EdgeList(nbr.reshape(-1).int().cuda(), deg.int().cuda(), stride, stride, z.reshape(-1, 128).cuda())
+
+    ar, off, lf = ctx['arena'], ctx['off'], weights.ATTN_LAYER_FLOATS
+    e_a, e_m = edges(nbr_a, deg_a, ja, r_a, sa), edges(nbr_m, deg_m, jm, r_m, sm)
+    kv_a = ops.attn_kv(x_a.cuda(), ar, off['pol_a2p'], 6, lf)
+    kv_m = ops.attn_kv(x_m.cuda(), ar, off['pol_m2p'], 6, lf)
+    out = ops.attn_stack(x_p.cuda(), 6, ops.stack_side(ar, off['pol_a2p'], e_a, kv_a),
+                         ops.stack_side(ar, off['pol_m2p'], e_m, kv_m)).cpu()
+    assert (out - ref).abs().max() < 5e-5       # 12 layers deep
+
+    nbr_s, deg_s, js, ei_s = _random_graph(g, P, P, sa)
+    r_s = torch.randn(ei_s.shape[1], 128, generator=g)
+    ref = x_p
+    ct = 'condition_transformers.policy_decoder.condition_attn.attn_layers'
+    for i in range(3):
+        ref = orc.attention_layer(f'{ct}.{i}', ref, ref, r_s, ei_s, False)
+    out = ops.attn_stack(x_p.cuda(), 3, ops.stack_side(ar, off['cond_attn'], edges(nbr_s, deg_s, js, r_s, sa))).cpu()
+    assert (out - ref).abs().max() < 2e-5
+
+
+# ------------------------------------------------------------------------------------ heads
+def test_policy_head_and_reconst_match_oracle(ctx):
+    ops, orc = ctx['ops'], ctx['oracle']
+    g = torch.Generator().manual_seed(17)
+    P = 45
+    feat, emd = torch.randn(P, 128, generator=g), torch.randn(P, 128, generator=g)
+    a_type = torch.randint(1, 4, (P,), generator=g)
+    ref = orc.policy_head(feat, a_type, emd)
+    mp = ops.policy_head(feat.cuda(), a_type.int().cuda(), ctx['arena'], ctx['off']['head']).cpu()
+    rc = ops.reconst(emd.cuda(), ctx['arena'], ctx['off']['head']).cpu()
+    assert (mp - ref['motion_pred']).abs().max() < 2e-5
+    assert (rc - ref['reconst_pred']).abs().max() < 1e-5
+
+
+def test_prompt_and_goal_encoders_match_oracle(ctx):
+    ops, orc = ctx['ops'], ctx['oracle']
+    g = torch.Generator().manual_seed(19)
+    n = 31
+    x = torch.randn(n, 7, generator=g)
+    ref = orc.mlp('prompt_encoder.motion_pred.state_encoder', x, 2, ret_before_act=True)
+    out = ops.mlp2(x.cuda(), 7, True, ctx['arena'], ctx['off']['prompt_mlp']).cpu()
+    assert (out - ref).abs().max() < 1e-5
+    gi = torch.cat([torch.randn(n, 2, generator=g) * 40, torch.full((n, 1), 80.0), torch.zeros(n, 1)], dim=1)
+    ct = 'condition_transformers.policy_decoder.condition_encoders.goal.goal_encoder'
+    ref = orc.mlp(ct, gi[:, :2], 2, ret_before_act=True, without_norm=True) + fourier_fix(gi[:, 2:3], 128)
+    dim_t128 = ctx['arena'][ctx['off']['dim_t128']:ctx['off']['dim_t128'] + 128]
+    out = ops.mlp2(gi.cuda(), 2, False, ctx['arena'], ctx['off']['goal_mlp'], tpe_col=2, dim_t128=dim_t128).cpu()
+    assert (out - ref).abs().max() < 2e-5
+
+
+def test_bad_arguments_raise(ctx):
+    from prosim_b200 import lib
+    ops = ctx['ops']
+    with pytest.raises(lib.ProSimLibError):
+        ops.pointnet(0, torch.zeros(1, 11, 24), torch.ones(1, 11, 24, dtype=torch.bool), torch.zeros(1, dtype=torch.int32),
+                     ctx['arena'], 0)        # CPU tensors: no fallback
+    with pytest.raises(lib.ProSimLibError):
+        lib.call('prosim_step_agent_traj', None, None, 4, 91, 90, None, None, None)   # tidx + 10 > T
