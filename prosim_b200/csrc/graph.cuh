@@ -124,9 +124,13 @@ __global__ void __launch_bounds__(128) edge_pe_kernel(const float2* __restrict__
     const float2 ps = spos[j];
     const float rx = ps.x - pd.x, ry = ps.y - pd.y;
     float v;
-    if (inp == 0) v = sqrtf(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)));
+    // torch.norm on the CPU reference reduces with acc = fma(v, v, acc): sqrt(fma(ry, ry, rx*rx)) bit for bit;
+    // the dot product is a torch sum over two rounded products starting from +0 (so -0 + -0 becomes +0 and the
+    // zero-offset self edge gets phi = atan2(+-0, +0) = 0, not pi).
+    if (inp == 0) v = sqrtf(fmaf(ry, ry, __fmul_rn(rx, rx)));
     else if (inp == 1) v = wrap_angle(sori[j] - od);
-    else v = atan2f(__fsub_rn(__fmul_rn(cx, ry), __fmul_rn(cy, rx)), __fadd_rn(__fmul_rn(cx, rx), __fmul_rn(cy, ry)));
+    else v = atan2f(__fsub_rn(__fmul_rn(cx, ry), __fmul_rn(cy, rx)),
+                    __fadd_rn(__fadd_rn(0.0f, __fmul_rn(cx, rx)), __fmul_rn(cy, ry)));
     v = v * TWO_PI_F;
     const float a0 = v / dt0, a1 = v / dt1;
     float4 f = make_float4(sinf(a0), cosf(a0), sinf(a1), cosf(a1));

@@ -135,7 +135,9 @@ def attn_layer(x_src, x_dst, edges, w_arena, w_off, out=None, workspace=None):
 
 
 def stack_side(w_arena, w_off, edges, kv=None):
-    return StackSide(ptr(w_arena, w_off), ptr(kv), (kv.shape[1] * kv.shape[2]) if kv is not None else 0, edges.c_struct())
+    side = StackSide(ptr(w_arena, w_off), ptr(kv), (kv.shape[1] * kv.shape[2]) if kv is not None else 0, edges.c_struct())
+    side._keepalive = (w_arena, kv, edges)   # the struct only holds raw addresses
+    return side
 
 
 def attn_stack(x, n_layers, side_a, side_b=None, out=None, workspace=None):
