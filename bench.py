@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Benchmark of the closed-loop rollout hot path (BASELINE.json metric: agent-steps/sec, 128 agents x 80 steps).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = one full ``model.forward(batch, 'val')`` (scene encoder + prompt encoder + policy generator + all
+rollout ticks) over this rank's batch of synthetic Waymo-shaped scenes.  Workload (config.workload): the
+per-GPU shard of BASELINE.json configs[4] -- 32 scenes x 128 agents x 512 map polylines x 80 steps per GPU,
+weak scaling (256 scenes at 8 GPUs); each scene is BASELINE.json configs[2].  Scenes are independent, so ranks
+share no data-path collective (DESIGN.md "Multi-GPU").
+
+  value  device-resident: inputs already in HBM; CUDA events around each forward; max over ranks
+  e2e    reference-facing call with HOST buffers: pinned H2D of the batch + forward + D2H of the trajectories
+  roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md "Measurement"
+
+--impl reference times the CPU restatement of the reference (oracle/prosim_oracle.py, bit-equal to the
+reference's own code on CPU) on a bounded sample of the same workload, on all host threads.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'agent_steps_per_sec'
+UNIT = 'agent-steps/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--scenes-per-gpu', type=int, default=32)
+    ap.add_argument('--agents', type=int, default=128)
+    ap.add_argument('--map', type=int, default=512)
+    ap.add_argument('--rollout-steps', type=int, default=80)
+    ap.add_argument('--ref-scenes', type=int, default=2, help='scenes per step of the CPU reference arm')
+    ap.add_argument('--cpu-baseline-scenes', type=int, default=4)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-single-scene', action='store_true')
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f'{a.scenes_per_gpu} scenes/GPU x {a.agents} agents x {a.map} map polylines x {a.rollout_steps}-step '
+            f'closed-loop rollout (BASELINE configs[2] scenes, configs[4] per-GPU shard)')
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock / throttle reasons with nvidia-smi every 200 ms while the timed region runs."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.idx}', f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])), mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(mx), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def time_oracle(n_scenes, agents, n_map, rsteps, repeats, warmup, first_scene=0):
+    import torch
+    from oracle.prosim_oracle import ProSimOracle
+    from prosim_b200 import synthetic, weights
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    orc = ProSimOracle(weights.random_state_dict(0), faithful_bookkeeping=True)
+    times = []
+    for i in range(warmup + repeats):
+        batch = synthetic.make_batch(n_scenes=n_scenes, n_agents=agents, n_map=n_map, steps=rsteps,
+                                     first_scene=first_scene + i * n_scenes)
+        t0 = time.perf_counter()
+        orc.forward(batch)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return times, cores
+
+
+def run_reference(a):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    times, cores = time_oracle(a.ref_scenes, a.agents, a.map, a.rollout_steps, a.steps, a.warmup)
+    per_step = sum(times) / len(times)
+    value = a.ref_scenes * a.agents * a.rollout_steps / per_step
+    sample = (f'{a.ref_scenes} of the {a.scenes_per_gpu} scenes of one GPU shard per step, {a.steps} steps, oracle port '
+              f'with the reference\'s per-tick string bookkeeping, torch fp32 eager, {cores} threads')
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps,
+        'warmup': a.warmup, 'ms_per_step': per_step * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': workload_name(a), 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+# ----------------------------------------------------------------------------------------------- B200 arm
+def algorithmic_flops_post(n_rows):
+    """attn_post_kernel (+ fused next-layer dst projections), 2 FLOP/MAC: Wvr' contraction 128x128, gate 128x128,
+    out-proj 128x128, FFN 128x512 + 512x128, next q/s/gx 3 x 128x128, Qhat 8 x 16x128  (DESIGN.md)."""
+    macs = 3 * 128 * 128 + 2 * 128 * 512 + 3 * 128 * 128 + 8 * 16 * 128
+    return 2.0 * macs * n_rows
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    from prosim_b200 import lib, synthetic, weights
+    from prosim_b200.model import ProSimB200
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    S, A, M, RS = a.scenes_per_gpu, a.agents, a.map, a.rollout_steps
+    model = ProSimB200(state_dict=weights.random_state_dict(0), device=dev)
+
+    n_var = 3
+    hosts = [synthetic.make_batch(n_scenes=S, n_agents=A, n_map=M, steps=RS, first_scene=(v * world + rank) * S,
+                                  pin_memory=True) for v in range(n_var)]
+    pristine = [synthetic.clone_batch(h, dev)[0] for h in hosts]
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def forward_device(i):
+        batch, _ = synthetic.clone_batch(pristine[i % n_var])
+        flush.fill_(float(i))                      # evict L2 between iterations (256 MB > 126 MB L2)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = model.forward(batch, 'val')
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1), out
+
+    def forward_e2e(i):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        batch, h2d = synthetic.clone_batch(hosts[i % n_var], dev, non_blocking=True)
+        st = model.forward(batch, 'val')['motion_pred']['_state']
+        traj = st['traj'].to('cpu', non_blocking=True)
+        vel = st['vel'].to('cpu', non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        return dt * 1e3, h2d, traj.numel() * 4 + vel.numel() * 4
+
+    with torch.no_grad():
+        for i in range(a.warmup):
+            forward_device(i)
+        barrier()
+        n0 = lib.launch_count()
+        lib.profile_enable('attn_post')
+        with ClockSampler(local) as clk:
+            times = [forward_device(a.warmup + i)[0] for i in range(a.steps)]
+            barrier()
+        post_ms, post_n = lib.profile_read()
+        lib.profile_enable(None)
+        launches = lib.launch_count() - n0
+
+        for i in range(min(a.warmup, 2)):
+            forward_e2e(i)
+        barrier()
+        e2e = [forward_e2e(a.warmup + i) for i in range(a.steps)]
+        barrier()
+
+        single = None
+        if not a.no_single_scene and rank == 0:
+            one = synthetic.clone_batch(synthetic.make_batch(n_scenes=1, n_agents=A, n_map=M, steps=RS), dev)[0]
+            lat = []
+            for i in range(8):
+                b1, _ = synthetic.clone_batch(one)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                model.forward(b1, 'val')
+                e1.record()
+                e1.synchronize()
+                lat.append(e0.elapsed_time(e1))
+            ms = statistics.median(lat[3:])
+            single = {'workload': f'1 scene x {A} agents x {M} polylines x {RS} steps (BASELINE configs[2])',
+                      'ms_per_forward': ms, 'value': A * RS / (ms * 1e-3), 'unit': UNIT}
+
+    total = torch.tensor([sum(times), sum(t for t, _, _ in e2e)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(total[0]), float(total[1])
+    units = world * S * A * RS
+    value = units * a.steps / (total_ms * 1e-3)
+    e2e_value = units * a.steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        # dominant kernel: attn_post_kernel (row-tile fp32 GEMMs of every attention layer).  It computes on the
+        # fp32 CUDA cores (IEEE fp32 is required for parity, DESIGN.md "Numerics"); the fraction is reported
+        # against the tensor-pipe peak the contract names AND against the fp32 FFMA peak it is actually bound by.
+        rows_per_launch = S * A
+        post_launches_policy = None
+        flops_total = None
+        roof = None
+        if post_n > 0:
+            avg_ms = post_ms / post_n
+            # policy ticks: 12 layers x 8 ticks on S*A rows; generator: 12 layers on S*A rows; encoder: 6 on S*A and 6 on
+            # S*(A+M) rows -> average algorithmic FLOPs per launch
+            nt = RS // 10
+            rows_sum = (12 * nt + 12 + 6) * S * A + 6 * S * (A + M)
+            n_launch_step = 12 * nt + 12 + 12
+            flops_per_launch = algorithmic_flops_post(rows_sum / n_launch_step)
+            achieved = flops_per_launch / (avg_ms * 1e-3) / 1e12
+            tensor_peak = peaks.get('bf16_tflops_sustained') or 1400.0
+            sm_mhz = peaks.get('sm_max_mhz', 1965.0)
+            ffma_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+            roof = {'kernel': 'attn_post_kernel', 'bound': 'tensor', 'achieved': achieved, 'peak': tensor_peak,
+                    'unit': 'TFLOP/s', 'frac': achieved / tensor_peak,
+                    'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)'
+                    if peaks else 'fallback 1.4 PFLOP/s',
+                    'traffic': None,
+                    'fp32_ffma': {'peak': ffma_peak, 'frac': achieved / ffma_peak,
+                                  'note': 'kernel runs IEEE fp32 FFMA on CUDA cores; nominal 148 SM x 128 lanes x 2 x max clock'},
+                    'avg_launch_ms': avg_ms, 'launches_timed': post_n, 'share_of_step': post_ms / total_ms
+                    if world == 1 else None}
+        cpu = None
+        if not a.no_cpu_baseline and world == 1:
+            ts, cores = time_oracle(a.cpu_baseline_scenes, A, M, RS, repeats=2, warmup=1)
+            v = a.cpu_baseline_scenes * A * RS / (sum(ts) / len(ts))
+            cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                   'sample': f'{a.cpu_baseline_scenes}-scene batch of the same workload, 2 timed forwards after 1 warm-up, '
+                             f'oracle port (bit-equal to the reference on CPU) incl. the reference\'s string bookkeeping'}
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
+            'ms_per_step': total_ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': workload_name(a), 'scenes_per_gpu': S, 'agents': A, 'map_polylines': M,
+                       'rollout_steps': RS, 'l2': 'L2 flushed with a 256 MB write between timed iterations; 3 rotating input sets',
+                       'weights': 'seeded random init under the reference state_dict names (no checkpoint ships)'},
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': e2e[0][1], 'd2h_bytes_per_step': e2e[0][2],
+                    'ms_per_step': e2e_ms / a.steps},
+            'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': cpu, 'clocks': clk.summary(),
+            'single_scene': single,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+        return
+    if a.gpus > 1 and 'WORLD_SIZE' not in os.environ:
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={a.gpus}',
+               '--master-addr', '127.0.0.1', '--master-port', '29513', os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_b200(a)
+
+
+if __name__ == '__main__':
+    main()

@@ -44,6 +44,17 @@ typedef struct {
 } prosim_stack_side_t;
 
 int prosim_abi_version(void);
+
+/* Launch accounting and optional per-kernel CUDA-event timing (measurement support for bench.py; not part of
+ * the data path).  kernel_class < 0 in prosim_launch_count = all classes; prosim_profile_enable(-1) disables. */
+enum {
+  PROSIM_K_POINTNET = 0, PROSIM_K_RADIUS = 1, PROSIM_K_KNN = 2, PROSIM_K_EDGE_PE = 3, PROSIM_K_ATTN_KV = 4,
+  PROSIM_K_ATTN_DSTPRE = 5, PROSIM_K_ATTN_EDGE = 6, PROSIM_K_ATTN_POST = 7, PROSIM_K_HEAD = 8, PROSIM_K_MLP2 = 9,
+  PROSIM_K_STATE = 10
+};
+long long prosim_launch_count(int kernel_class);
+int prosim_profile_enable(int kernel_class);
+int prosim_profile_read(double* total_ms, int* count);
 /* sizes (in floats) of the packed weight blocks -- cross-checked by the Python packer */
 int prosim_attn_layer_floats(void);
 int prosim_pointnet_floats(void);

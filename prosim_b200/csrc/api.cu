@@ -17,6 +17,32 @@ constexpr int ERR_WORKSPACE = -2;
 
 inline cudaStream_t S(prosim_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// ---- launch accounting (bench.py: "gpu_launches") and optional per-kernel-class CUDA-event timing (roofline).
+// Kernel classes: see PROSIM_K_* in the header.  Timing is off unless prosim_profile_enable() was called.
+constexpr int N_CLASSES = 16;
+constexpr int MAX_REC = 8192;
+long long g_launches[N_CLASSES] = {0};
+int g_prof_class = -1;
+int g_prof_n = 0;
+cudaEvent_t g_ev0[MAX_REC], g_ev1[MAX_REC];
+bool g_ev_made = false;
+
+struct LaunchScope {
+  int cls;
+  cudaStream_t st;
+  bool timed;
+  LaunchScope(int c, cudaStream_t s) : cls(c), st(s), timed(false) {
+    ++g_launches[c];
+    if (c == g_prof_class && g_prof_n < MAX_REC) {
+      timed = true;
+      cudaEventRecord(g_ev0[g_prof_n], st);
+    }
+  }
+  ~LaunchScope() {
+    if (timed) cudaEventRecord(g_ev1[g_prof_n++], st);
+  }
+};
+
 // Row-tile height (2*RPT rows per CTA): the largest tile that still yields >= one CTA per SM.
 inline int pick_rpt(int n_rows) {
   const int sms = 148;
@@ -87,6 +113,7 @@ int launch_kv(const float* x, int n, const float* w, size_t wstride, int layers,
               cudaStream_t st) {
   if (n <= 0) return 0;
   const int rpt = pick_rpt(n * layers);
+  LaunchScope ls(PROSIM_K_ATTN_KV, st);
   DISPATCH_RPT(rpt, attn_kv_kernel<RPT><<<dim3((n + 2 * RPT - 1) / (2 * RPT), layers), 256, 0, st>>>(x, n, w, wstride, kv, kvstride));
   PROSIM_CHECK_LAUNCH();
   return 0;
@@ -95,6 +122,7 @@ int launch_kv(const float* x, int n, const float* w, size_t wstride, int layers,
 int launch_dstpre(const float* x, int n, const float* w, const DstScratch& d, cudaStream_t st) {
   if (n <= 0) return 0;
   const int rpt = pick_rpt(n);
+  LaunchScope ls(PROSIM_K_ATTN_DSTPRE, st);
   DISPATCH_RPT(rpt, attn_dstpre_kernel<RPT><<<(n + 2 * RPT - 1) / (2 * RPT), 256, 0, st>>>(x, n, w, d.q, d.qhat, d.s, d.gx));
   PROSIM_CHECK_LAUNCH();
   return 0;
@@ -106,6 +134,7 @@ int launch_edge(const DstScratch& d, const float* kv, const prosim_graph_t& g, i
   const int sstride = ((g.max_deg < 4 ? 4 : g.max_deg) + 3) & ~3;
   const size_t smem = attn_edge_smem_bytes(sstride);
   if (smem > 200 * 1024) return ERR_ARG;
+  LaunchScope ls(PROSIM_K_ATTN_EDGE, st);
   attn_edge_kernel<<<n_dst, 256, smem, st>>>(d.q, d.qhat, kv, g.z, g.nbr, g.deg, g.stride, sstride, rbar, aggv);
   PROSIM_CHECK_LAUNCH();
   return 0;
@@ -115,6 +144,7 @@ int launch_post(const float* x, int n, const float* rbar, const float* aggv, con
                 float* out, const float* w_next, const DstScratch& nxt, cudaStream_t st) {
   if (n <= 0) return 0;
   const int rpt = pick_rpt(n);
+  LaunchScope ls(PROSIM_K_ATTN_POST, st);
   DISPATCH_RPT(rpt, attn_post_kernel<RPT><<<(n + 2 * RPT - 1) / (2 * RPT), 256, PostSmem<RPT>::bytes, st>>>(
                         x, n, rbar, aggv, cur.s, cur.gx, w, out, w_next, nxt.q, nxt.qhat, nxt.s, nxt.gx));
   PROSIM_CHECK_LAUNCH();
@@ -126,6 +156,41 @@ int launch_post(const float* x, int n, const float* rbar, const float* aggv, con
 extern "C" {
 
 int prosim_abi_version(void) { return 1; }
+
+long long prosim_launch_count(int kernel_class) {
+  if (kernel_class >= 0 && kernel_class < N_CLASSES) return g_launches[kernel_class];
+  long long t = 0;
+  for (int i = 0; i < N_CLASSES; ++i) t += g_launches[i];
+  return t;
+}
+
+int prosim_profile_enable(int kernel_class) {
+  if (kernel_class >= N_CLASSES) return ERR_ARG;
+  if (kernel_class >= 0 && !g_ev_made) {
+    for (int i = 0; i < MAX_REC; ++i) {
+      if (cudaEventCreate(&g_ev0[i]) != cudaSuccess || cudaEventCreate(&g_ev1[i]) != cudaSuccess) return (int)cudaGetLastError();
+    }
+    g_ev_made = true;
+  }
+  g_prof_class = kernel_class;
+  g_prof_n = 0;
+  return 0;
+}
+
+int prosim_profile_read(double* total_ms, int* count) {
+  if (!total_ms || !count) return ERR_ARG;
+  double t = 0.0;
+  for (int i = 0; i < g_prof_n; ++i) {
+    if (cudaEventSynchronize(g_ev1[i]) != cudaSuccess) return (int)cudaGetLastError();
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_ev0[i], g_ev1[i]) != cudaSuccess) return (int)cudaGetLastError();
+    t += ms;
+  }
+  *total_ms = t;
+  *count = g_prof_n;
+  g_prof_n = 0;
+  return 0;
+}
 int prosim_attn_layer_floats(void) { return aw::SIZE; }
 int prosim_pointnet_floats(void) { return pw::SIZE; }
 int prosim_head_floats(void) { return hw::SIZE; }
@@ -140,6 +205,7 @@ int prosim_pointnet_fwd(int kind, const float* x, const uint8_t* mask, const int
   if (n_poly == 0) return 0;
   if (!x || !mask || !rows || !w || !out) return ERR_ARG;
   if (int e = setup_attributes()) return e;
+  LaunchScope ls(PROSIM_K_POINTNET, S(stream));
   if (kind == 0) {
     constexpr int G = PointNetCfg<11>::G;
     pointnet_kernel<24, 24, 1, 11><<<(n_poly + G - 1) / G, 256, PointNetCfg<11>::smem_bytes, S(stream)>>>(
@@ -160,6 +226,7 @@ int prosim_build_radius_edges(const float* qpos, const int32_t* qscene, int n_q,
   if (n_q == 0) return 0;
   if (!qpos || !qscene || !spos || !seg || !nbr || !deg) return ERR_ARG;
   const float r2 = r * r;
+  LaunchScope ls(PROSIM_K_RADIUS, S(stream));
   radius_kernel<<<(n_q + 7) / 8, 256, 0, S(stream)>>>(reinterpret_cast<const float2*>(qpos), qscene, n_q,
                                                       reinterpret_cast<const float2*>(spos),
                                                       reinterpret_cast<const int4*>(seg), r2, cap, drop_self, nbr, deg,
@@ -176,6 +243,7 @@ int prosim_build_knn_edges(const float* qpos, const int32_t* qscene, int n_q, co
   if (int e = setup_attributes()) return e;
   const size_t smem = (size_t)nmax * 8;
   if (smem > 64 * 1024) return ERR_ARG;
+  LaunchScope ls(PROSIM_K_KNN, S(stream));
   knn_kernel<<<n_q, 128, smem, S(stream)>>>(reinterpret_cast<const float2*>(qpos), qscene, n_q,
                                             reinterpret_cast<const float2*>(spos), reinterpret_cast<const int4*>(seg), k,
                                             nmax, nbr, deg, stride);
@@ -189,6 +257,7 @@ int prosim_edge_pe(const float* dpos, const float* dori, int n_dst, const float*
   if (n_dst < 0 || stride <= 0) return ERR_ARG;
   if (n_dst == 0) return 0;
   if (!dpos || !dori || !spos || !sori || !nbr || !deg || !dim_t16 || !z) return ERR_ARG;
+  LaunchScope ls(PROSIM_K_EDGE_PE, S(stream));
   edge_pe_kernel<<<n_dst, 128, 0, S(stream)>>>(reinterpret_cast<const float2*>(dpos), dori,
                                                reinterpret_cast<const float2*>(spos), sori, nbr, deg, stride, dim_t16,
                                                extra, z);
@@ -271,6 +340,7 @@ int prosim_policy_head_fwd(const float* feat, const int32_t* agent_type, int P, 
   if (P == 0) return 0;
   if (!feat || !agent_type || !w || !motion_pred) return ERR_ARG;
   const int rpt = pick_rpt(P);
+  LaunchScope ls(PROSIM_K_HEAD, S(stream));
   DISPATCH_RPT(rpt, policy_head_kernel<RPT><<<(P + 2 * RPT - 1) / (2 * RPT), 256, 0, S(stream)>>>(feat, agent_type, P, w, motion_pred));
   PROSIM_CHECK_LAUNCH();
   return 0;
@@ -281,6 +351,7 @@ int prosim_reconst_fwd(const float* emd, int P, const float* w, float* out, pros
   if (P == 0) return 0;
   if (!emd || !w || !out) return ERR_ARG;
   const int rpt = pick_rpt(P);
+  LaunchScope ls(PROSIM_K_HEAD, S(stream));
   DISPATCH_RPT(rpt, reconst_kernel<RPT><<<(P + 2 * RPT - 1) / (2 * RPT), 256, 0, S(stream)>>>(emd, P, w, out));
   PROSIM_CHECK_LAUNCH();
   return 0;
@@ -292,6 +363,7 @@ int prosim_mlp2_fwd(const float* in, int ld_in, int k0, int n, int use_ln, const
   if (n == 0) return 0;
   if (!in || !w || !out || (tpe_t && !dim_t128)) return ERR_ARG;
   const int rpt = pick_rpt(n);
+  LaunchScope ls(PROSIM_K_MLP2, S(stream));
   DISPATCH_RPT(rpt, mlp2_kernel<RPT><<<(n + 2 * RPT - 1) / (2 * RPT), 256, 0, S(stream)>>>(in, ld_in, k0, n, use_ln, w, tpe_t, tpe_ld, dim_t128, out));
   PROSIM_CHECK_LAUNCH();
   return 0;
@@ -303,6 +375,7 @@ int prosim_init_traj(const float* obs_in, const float* obs_pos, const float* obs
   if (P < 0 || T < HIST) return ERR_ARG;
   if (P == 0) return 0;
   if (!obs_in || !obs_pos || !obs_head || !p_slot || !p_row || !traj || !vel || !init_pos || !init_heading) return ERR_ARG;
+  LaunchScope ls(PROSIM_K_STATE, S(stream));
   init_traj_kernel<<<(P + 127) / 128, 128, 0, S(stream)>>>(obs_in, obs_pos, obs_head, p_slot, p_row, P, T, traj, vel,
                                                            init_pos, init_heading);
   PROSIM_CHECK_LAUNCH();
@@ -317,6 +390,7 @@ int prosim_step_env(const float* traj, const float* vel, const float* init_pos, 
   if (P == 0) return 0;
   if (!traj || !vel || !init_pos || !init_heading || !p_row || !p_pos || !p_ori) return ERR_ARG;
   if (fut_in && (!fut_mask || !fut_pos || !fut_head || !p_slot)) return ERR_ARG;
+  LaunchScope ls(PROSIM_K_STATE, S(stream));
   step_env_kernel<<<(P + 127) / 128, 128, 0, S(stream)>>>(traj, vel, init_pos, init_heading, p_row, p_slot, P, T, tidx,
                                                           p_pos, p_ori, fut_in, fut_mask, fut_pos, fut_head);
   PROSIM_CHECK_LAUNCH();
@@ -328,6 +402,7 @@ int prosim_gather_pose(const float* pos, const float* head, const int32_t* rows,
   if (n < 0) return ERR_ARG;
   if (n == 0) return 0;
   if (!pos || !head || !rows || !out_pos || !out_ori) return ERR_ARG;
+  LaunchScope ls(PROSIM_K_STATE, S(stream));
   gather_pose_kernel<<<(n + 127) / 128, 128, 0, S(stream)>>>(pos, head, rows, n, out_pos, out_ori);
   PROSIM_CHECK_LAUNCH();
   return 0;
@@ -338,6 +413,7 @@ int prosim_step_agent_traj(const float* motion_pred, const int32_t* p_row, int P
   if (P < 0 || tidx < 1 || tidx + STEP > T) return ERR_ARG;
   if (P == 0) return 0;
   if (!motion_pred || !p_row || !traj || !vel) return ERR_ARG;
+  LaunchScope ls(PROSIM_K_STATE, S(stream));
   step_agent_traj_kernel<<<(P + 127) / 128, 128, 0, S(stream)>>>(motion_pred, p_row, P, T, tidx, traj, vel);
   PROSIM_CHECK_LAUNCH();
   return 0;

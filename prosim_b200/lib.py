@@ -15,8 +15,11 @@ SYMBOLS = (
     'prosim_mlp2_floats', 'prosim_attn_workspace_floats', 'prosim_pointnet_fwd', 'prosim_build_radius_edges',
     'prosim_build_knn_edges', 'prosim_edge_pe', 'prosim_attn_kv', 'prosim_attn_layer_fwd', 'prosim_attn_stack_fwd',
     'prosim_policy_head_fwd', 'prosim_reconst_fwd', 'prosim_mlp2_fwd', 'prosim_init_traj', 'prosim_step_env',
-    'prosim_gather_pose', 'prosim_step_agent_traj',
+    'prosim_gather_pose', 'prosim_step_agent_traj', 'prosim_launch_count', 'prosim_profile_enable', 'prosim_profile_read',
 )
+
+KERNEL_CLASSES = {'pointnet': 0, 'radius': 1, 'knn': 2, 'edge_pe': 3, 'attn_kv': 4, 'attn_dstpre': 5, 'attn_edge': 6,
+                  'attn_post': 7, 'head': 8, 'mlp2': 9, 'state': 10}
 
 
 class Graph(Structure):
@@ -68,6 +71,12 @@ def load():
                  'prosim_mlp2_floats'):
         getattr(lib, name).restype = c_int
         getattr(lib, name).argtypes = []
+    lib.prosim_launch_count.restype = ctypes.c_longlong
+    lib.prosim_launch_count.argtypes = [c_int]
+    lib.prosim_profile_enable.restype = c_int
+    lib.prosim_profile_enable.argtypes = [c_int]
+    lib.prosim_profile_read.restype = c_int
+    lib.prosim_profile_read.argtypes = [POINTER(ctypes.c_double), POINTER(c_int)]
     lib.prosim_attn_workspace_floats.restype = c_size_t
     lib.prosim_attn_workspace_floats.argtypes = [c_int, c_int]
     for name, sig in _SIGS.items():
@@ -101,3 +110,19 @@ def ptr(t, offset_elems=0):
     if t is None:
         return None
     return t.data_ptr() + offset_elems * t.element_size()
+
+
+def launch_count(kernel_class=-1):
+    return int(load().prosim_launch_count(kernel_class))
+
+
+def profile_enable(name):
+    """Record a CUDA-event pair around every launch of one kernel class (None disables)."""
+    check(load().prosim_profile_enable(-1 if name is None else KERNEL_CLASSES[name]), 'prosim_profile_enable')
+
+
+def profile_read():
+    """(total milliseconds, launches) recorded since the last enable/read."""
+    ms, n = ctypes.c_double(0.0), c_int(0)
+    check(load().prosim_profile_read(ctypes.byref(ms), ctypes.byref(n)), 'prosim_profile_read')
+    return ms.value, n.value

@@ -200,3 +200,31 @@ def _pin(batch):
     for sub in list(ex['prompt'].all_prompts.values()) + list(ex['condition'].all_cond.values()):
         for k, v in sub.items():
             sub[k] = pin(v)
+
+
+def clone_batch(batch, device=None, non_blocking=False):
+    """Deep copy of a batch's tensors (optionally onto ``device``); id lists are shared.  Returns (copy, bytes moved)."""
+    nbytes = [0]
+
+    def mv(x):
+        if not isinstance(x, torch.Tensor):
+            return x
+        nbytes[0] += x.numel() * x.element_size()
+        return x.to(device, non_blocking=non_blocking) if device is not None else x.clone()
+
+    def copy_imd(d):
+        out = InputMaskData.__new__(InputMaskData)
+        out.input, out.mask = mv(d.input), mv(d.mask)
+        out.position, out.heading, out.agent_ids = mv(d.position), mv(d.heading), d.agent_ids
+        return out
+
+    ex = batch.extras
+    new = {
+        'init_obs': copy_imd(ex['init_obs']),
+        'init_map': copy_imd(ex['init_map']),
+        'prompt': BatchPrompt({t: {k: mv(v) for k, v in p.items()} for t, p in ex['prompt'].all_prompts.items()}),
+        'condition': BatchCondition({t: {k: mv(v) for k, v in c.items()} for t, c in ex['condition'].all_cond.items()}),
+        'all_t_indices': ex['all_t_indices'],
+        'fut_obs': BatchDataDict({t: copy_imd(ex['fut_obs'][t]) for t in ex['fut_obs'].keys()}),
+    }
+    return SceneBatch(list(batch.scene_ids), new), nbytes[0]
