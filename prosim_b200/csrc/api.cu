@@ -2,6 +2,7 @@
 #include "../../include/prosim_b200.h"
 
 #include "attn.cuh"
+#include "attn2.cuh"
 #include "common.cuh"
 #include "graph.cuh"
 #include "pointnet.cuh"
@@ -51,6 +52,13 @@ inline int pick_rpt(int n_rows) {
   return 1;
 }
 
+// v2 (gemm_tile.cuh) kernels for throughput-sized launches: rows per CTA = 16*RT; 0 => use the v1 latency kernels
+inline int pick_rt(int n_rows) {
+  if (n_rows >= 64 * 120) return 4;
+  if (n_rows >= 1024) return 2;
+  return 0;
+}
+
 #define DISPATCH_RPT(rpt, ...)                     \
   switch (rpt) {                                   \
     case 8: { constexpr int RPT = 8; __VA_ARGS__; } break; \
@@ -77,6 +85,11 @@ int setup_attributes() {
   acc(allow_smem(pointnet_kernel<24, 24, 1, 11>, PointNetCfg<11>::smem_bytes));
   acc(allow_smem(pointnet_kernel<11, 12, 3, 19>, PointNetCfg<19>::smem_bytes));
   acc(allow_smem(knn_kernel, 64 * 1024));
+  acc(allow_smem(attn_kv2_kernel<2>, Kv2Smem<2>::bytes));
+  acc(allow_smem(attn_kv2_kernel<4>, Kv2Smem<4>::bytes));
+  acc(allow_smem(attn_dstpre2_kernel<2>, Pre2Smem<2>::bytes));
+  acc(allow_smem(attn_dstpre2_kernel<4>, Pre2Smem<4>::bytes));
+  acc(allow_smem(attn_post2_kernel<2>, Post2Smem<2>::bytes));
   state = e == cudaSuccess ? 1 : (int)e + 1000;
   return e == cudaSuccess ? 0 : (int)e;
 }
@@ -114,6 +127,17 @@ int launch_kv(const float* x, int n, const float* w, size_t wstride, int layers,
   if (n <= 0) return 0;
   const int rpt = pick_rpt(n * layers);
   LaunchScope ls(PROSIM_K_ATTN_KV, st);
+  const int rt = pick_rt(n);
+  if (rt == 4) {
+    attn_kv2_kernel<4><<<dim3((n + 63) / 64, layers), 256, Kv2Smem<4>::bytes, st>>>(x, n, w, wstride, kv, kvstride);
+    PROSIM_CHECK_LAUNCH();
+    return 0;
+  }
+  if (rt == 2) {
+    attn_kv2_kernel<2><<<dim3((n + 31) / 32, layers), 256, Kv2Smem<2>::bytes, st>>>(x, n, w, wstride, kv, kvstride);
+    PROSIM_CHECK_LAUNCH();
+    return 0;
+  }
   DISPATCH_RPT(rpt, attn_kv_kernel<RPT><<<dim3((n + 2 * RPT - 1) / (2 * RPT), layers), 256, 0, st>>>(x, n, w, wstride, kv, kvstride));
   PROSIM_CHECK_LAUNCH();
   return 0;
@@ -123,6 +147,17 @@ int launch_dstpre(const float* x, int n, const float* w, const DstScratch& d, cu
   if (n <= 0) return 0;
   const int rpt = pick_rpt(n);
   LaunchScope ls(PROSIM_K_ATTN_DSTPRE, st);
+  const int rt = pick_rt(n);
+  if (rt == 4) {
+    attn_dstpre2_kernel<4><<<(n + 63) / 64, 256, Pre2Smem<4>::bytes, st>>>(x, n, w, d.q, d.qhat, d.s, d.gx);
+    PROSIM_CHECK_LAUNCH();
+    return 0;
+  }
+  if (rt == 2) {
+    attn_dstpre2_kernel<2><<<(n + 31) / 32, 256, Pre2Smem<2>::bytes, st>>>(x, n, w, d.q, d.qhat, d.s, d.gx);
+    PROSIM_CHECK_LAUNCH();
+    return 0;
+  }
   DISPATCH_RPT(rpt, attn_dstpre_kernel<RPT><<<(n + 2 * RPT - 1) / (2 * RPT), 256, 0, st>>>(x, n, w, d.q, d.qhat, d.s, d.gx));
   PROSIM_CHECK_LAUNCH();
   return 0;
@@ -145,6 +180,12 @@ int launch_post(const float* x, int n, const float* rbar, const float* aggv, con
   if (n <= 0) return 0;
   const int rpt = pick_rpt(n);
   LaunchScope ls(PROSIM_K_ATTN_POST, st);
+  if (pick_rt(n) != 0) {
+    attn_post2_kernel<2><<<(n + 31) / 32, 256, Post2Smem<2>::bytes, st>>>(x, n, rbar, aggv, cur.s, cur.gx, w, out, w_next,
+                                                                         nxt.q, nxt.qhat, nxt.s, nxt.gx);
+    PROSIM_CHECK_LAUNCH();
+    return 0;
+  }
   DISPATCH_RPT(rpt, attn_post_kernel<RPT><<<(n + 2 * RPT - 1) / (2 * RPT), 256, PostSmem<RPT>::bytes, st>>>(
                         x, n, rbar, aggv, cur.s, cur.gx, w, out, w_next, nxt.q, nxt.qhat, nxt.s, nxt.gx));
   PROSIM_CHECK_LAUNCH();

@@ -1,0 +1,211 @@
+// Throughput variants of the node-level attention kernels (attn.cuh) built on gemm_tile.cuh: 16*RT rows per
+// CTA, weights streamed once per CTA through a cp.async ring.  Same math, same summation order per output
+// (ascending k), so results are bit-identical to the v1 kernels; api.cu picks v2 for large row counts and v1
+// (2..16 rows per CTA, more CTAs) for small latency-bound launches.
+#pragma once
+#include "attn.cuh"
+#include "gemm_tile.cuh"
+
+namespace prosim {
+
+// ------------------------------------------------------------------------------------------------ K', V'
+template <int RT>
+struct Kv2Smem {
+  static constexpr int M = 16 * RT;
+  static constexpr size_t bytes = WPIPE_BYTES + (size_t)M * LDS_PAD * sizeof(float);
+};
+
+template <int RT>
+__global__ void __launch_bounds__(256) attn_kv2_kernel(const float* __restrict__ X, int N, const float* __restrict__ Wbase,
+                                                       size_t w_layer_stride, float* __restrict__ KV,
+                                                       size_t kv_layer_stride) {
+  constexpr int M = 16 * RT;
+  extern __shared__ __align__(16) float smem[];
+  WPipe p{smem, 0, false};
+  float* xs = smem + WSTAGES * WCHUNK_FLOATS;
+  const float* W = Wbase + (size_t)blockIdx.y * w_layer_stride;
+  float* kv = KV + (size_t)blockIdx.y * kv_layer_stride;
+  const int row0 = blockIdx.x * M;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < M; r += 8) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row0 + r < N) {
+      v = *reinterpret_cast<const float4*>(X + (size_t)(row0 + r) * D + 4 * lane);
+      v = ln_row(v, W + aw::LN_SRC_G, W + aw::LN_SRC_B, lane);
+    }
+    *reinterpret_cast<float4*>(xs + r * LDS_PAD + 4 * lane) = v;
+  }
+  float acc[RT][8];
+  acc2_init_bias<RT>(acc, W + aw::KB);
+  gemm2<RT>(acc, xs, LDS_PAD, D, W + aw::WKT, D, p, W + aw::WVT, D, D);
+  acc2_store_global<RT>(acc, kv, 256, 0, row0, N);
+  acc2_init_bias<RT>(acc, W + aw::VB);
+  gemm2<RT>(acc, xs, LDS_PAD, D, W + aw::WVT, D, p);
+  acc2_store_global<RT>(acc, kv, 256, 128, row0, N);
+}
+
+// ------------------------------------------------------------------------------------------------ dst pre
+// xd: LN_dst-normalised tile in smem; sq: scratch tile.  The caller's pipe may already hold WQT chunk 0.
+template <int RT>
+__device__ __forceinline__ void attn_dst_pre2(const float* xd, float* sq, const float* __restrict__ W, int row0, int N,
+                                              float* __restrict__ Qg, float* __restrict__ Qhat, float* __restrict__ Sg,
+                                              float* __restrict__ Gxg, WPipe& p) {
+  float acc[RT][8];
+  acc2_init_bias<RT>(acc, W + aw::BQ);
+  gemm2<RT>(acc, xd, LDS_PAD, D, W + aw::WQT, D, p, W + aw::WST, D, D);
+  acc2_store_smem<RT>(acc, sq, LDS_PAD, false);
+  acc2_store_global<RT>(acc, Qg, D, 0, row0, N);
+  acc2_init_bias<RT>(acc, W + aw::BS);
+  gemm2<RT>(acc, xd, LDS_PAD, D, W + aw::WST, D, p, W + aw::WGXT, D, D);
+  acc2_store_global<RT>(acc, Sg, D, 0, row0, N);
+  acc2_init_bias<RT>(acc, W + aw::BG);
+  gemm2<RT>(acc, xd, LDS_PAD, D, W + aw::WGXT, D, p, W + aw::WKRG, D, DH);
+  acc2_store_global<RT>(acc, Gxg, D, 0, row0, N);
+#pragma unroll 1
+  for (int h = 0; h < H; ++h) {
+    acc2_init<RT>(acc, 0.f);
+    gemm2<RT>(acc, sq + h * DH, LDS_PAD, DH, W + aw::WKRG + h * DH * D, D, p,
+              h + 1 < H ? W + aw::WKRG + (h + 1) * DH * D : nullptr, D, DH);
+    acc2_store_global<RT>(acc, Qhat, H * D, h * D, row0, N);
+  }
+}
+
+template <int RT>
+struct Pre2Smem {
+  static constexpr int M = 16 * RT;
+  static constexpr size_t bytes = WPIPE_BYTES + 2 * (size_t)M * LDS_PAD * sizeof(float);
+};
+
+template <int RT>
+__global__ void __launch_bounds__(256) attn_dstpre2_kernel(const float* __restrict__ X, int N, const float* __restrict__ W,
+                                                           float* __restrict__ Qg, float* __restrict__ Qhat,
+                                                           float* __restrict__ Sg, float* __restrict__ Gxg) {
+  constexpr int M = 16 * RT;
+  extern __shared__ __align__(16) float smem[];
+  WPipe p{smem, 0, false};
+  float* xd = smem + WSTAGES * WCHUNK_FLOATS;
+  float* sq = xd + M * LDS_PAD;
+  const int row0 = blockIdx.x * M;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < M; r += 8) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row0 + r < N) {
+      v = *reinterpret_cast<const float4*>(X + (size_t)(row0 + r) * D + 4 * lane);
+      v = ln_row(v, W + aw::LN_DST_G, W + aw::LN_DST_B, lane);
+    }
+    *reinterpret_cast<float4*>(xd + r * LDS_PAD + 4 * lane) = v;
+  }
+  attn_dst_pre2<RT>(xd, sq, W, row0, N, Qg, Qhat, Sg, Gxg, p);
+}
+
+// ------------------------------------------------------------------------------------------------ post
+template <int RT>
+struct Post2Smem {
+  static constexpr int M = 16 * RT;
+  static constexpr int LDR = H * D + 4;
+  static constexpr int LDH = 4 * D + 4;
+  static constexpr size_t bytes = WPIPE_BYTES + ((size_t)M * LDR + 2 * (size_t)M * LDS_PAD) * sizeof(float);
+};
+
+template <int RT>
+__global__ void __launch_bounds__(256, 1) attn_post2_kernel(const float* __restrict__ Xdst, int N,
+                                                            const float* __restrict__ Rbar, const float* __restrict__ AggV,
+                                                            const float* __restrict__ Sg, const float* __restrict__ Gxg,
+                                                            const float* __restrict__ W, float* __restrict__ Out,
+                                                            const float* __restrict__ Wn, float* __restrict__ Qg_n,
+                                                            float* __restrict__ Qhat_n, float* __restrict__ Sg_n,
+                                                            float* __restrict__ Gxg_n) {
+  using SM = Post2Smem<RT>;
+  constexpr int M = SM::M;
+  extern __shared__ __align__(16) float smem[];
+  WPipe p{smem, 0, false};
+  float* sR = smem + WSTAGES * WCHUNK_FLOATS;   // [M][LDR], later the FFN hidden tile [M][LDH]
+  float* sA = sR + M * SM::LDR;
+  float* sB = sA + M * LDS_PAD;
+  const int row0 = blockIdx.x * M;
+  const int tx = threadIdx.x & 15;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // the first weight chunk flies while the Rbar tile is loaded
+  wpipe_issue(p.buf, W + aw::WVRGT, D, 0, KC);
+  cp_async_commit();
+  p.primed = true;
+  for (int i = threadIdx.x; i < M * (H * D / 4); i += 256) {
+    const int r = i / (H * D / 4), c = (i % (H * D / 4)) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row0 + r < N) v = __ldg(reinterpret_cast<const float4*>(Rbar + (size_t)(row0 + r) * H * D + c));
+    *reinterpret_cast<float4*>(sR + r * SM::LDR + c) = v;
+  }
+
+  float acc[RT][8], agg[RT][8];
+  // 1. agg = AggV + Wvr' Rbar (block diagonal: the A row of an output column is the Rbar row of its head)
+  acc2_load_global<RT>(acc, AggV, D, row0, N);
+  gemm_tile2<RT, true>(acc, sR + (tx >> 2) * D, sR + (4 + (tx >> 2)) * D, SM::LDR, D, W + aw::WVRGT, D, p,
+                       W + aw::WGAT, D, D);
+  acc2_store_smem<RT>(acc, sA, LDS_PAD, false);
+#pragma unroll
+  for (int r = 0; r < RT; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) agg[r][c] = acc[r][c];
+
+  // 2. gate: g = sigmoid(Wga agg + Gx) ; u = agg + g (S - agg)
+  acc2_load_global<RT>(acc, Gxg, D, row0, N);
+  gemm2<RT>(acc, sA, LDS_PAD, D, W + aw::WGAT, D, p, W + aw::WOT, D, D);
+  {
+    float s[RT][8];
+    acc2_load_global<RT>(s, Sg, D, row0, N);
+#pragma unroll
+    for (int r = 0; r < RT; ++r)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float g = 1.0f / (1.0f + expf(-acc[r][c]));
+        acc[r][c] = agg[r][c] + g * (s[r][c] - agg[r][c]);
+      }
+  }
+  acc2_store_smem<RT>(acc, sB, LDS_PAD, false);
+
+  // 3. out projection, post-norm, residual, FFN pre-norm
+  acc2_init_bias<RT>(acc, W + aw::BO);
+  gemm2<RT>(acc, sB, LDS_PAD, D, W + aw::WOT, D, p, W + aw::W1T, 4 * D, D);
+  acc2_store_smem<RT>(acc, sA, LDS_PAD, false);
+  __syncthreads();
+  for (int r = warp; r < M; r += 8) {
+    float4 o = *reinterpret_cast<const float4*>(sA + r * LDS_PAD + 4 * lane);
+    o = ln_row(o, W + aw::LN_POST_G, W + aw::LN_POST_B, lane);
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row0 + r < N) x = *reinterpret_cast<const float4*>(Xdst + (size_t)(row0 + r) * D + 4 * lane);
+    const float4 x1 = make_float4(x.x + o.x, x.y + o.y, x.z + o.z, x.w + o.w);
+    *reinterpret_cast<float4*>(sB + r * LDS_PAD + 4 * lane) = x1;
+    *reinterpret_cast<float4*>(sA + r * LDS_PAD + 4 * lane) = ln_row(x1, W + aw::LN_FFPRE_G, W + aw::LN_FFPRE_B, lane);
+  }
+
+  // 4. FFN up, ReLU, into the (free) Rbar tile
+  float* sH = sR;
+#pragma unroll 1
+  for (int nb = 0; nb < 4; ++nb) {
+    acc2_init_bias<RT>(acc, W + aw::B1 + nb * D);
+    if (nb < 3) gemm2<RT>(acc, sA, LDS_PAD, D, W + aw::W1T + nb * D, 4 * D, p, W + aw::W1T + (nb + 1) * D, 4 * D, D);
+    else gemm2<RT>(acc, sA, LDS_PAD, D, W + aw::W1T + nb * D, 4 * D, p, W + aw::W2T, D, 4 * D);
+    acc2_store_smem<RT>(acc, sH + nb * D, SM::LDH, true);
+  }
+
+  // 5. FFN down, post-norm, residual
+  acc2_init_bias<RT>(acc, W + aw::B2);
+  gemm2<RT>(acc, sH, SM::LDH, 4 * D, W + aw::W2T, D, p, Wn != nullptr ? Wn + aw::WQT : nullptr, D, D);
+  acc2_store_smem<RT>(acc, sA, LDS_PAD, false);
+  __syncthreads();
+  for (int r = warp; r < M; r += 8) {
+    float4 y = *reinterpret_cast<const float4*>(sA + r * LDS_PAD + 4 * lane);
+    y = ln_row(y, W + aw::LN_FFPOST_G, W + aw::LN_FFPOST_B, lane);
+    const float4 x1 = *reinterpret_cast<const float4*>(sB + r * LDS_PAD + 4 * lane);
+    const float4 o = make_float4(x1.x + y.x, x1.y + y.y, x1.z + y.z, x1.w + y.w);
+    if (row0 + r < N) *reinterpret_cast<float4*>(Out + (size_t)(row0 + r) * D + 4 * lane) = o;
+    if (Wn != nullptr)
+      *reinterpret_cast<float4*>(sA + r * LDS_PAD + 4 * lane) = ln_row(o, Wn + aw::LN_DST_G, Wn + aw::LN_DST_B, lane);
+  }
+  if (Wn == nullptr) return;
+  // 6. next layer's destination-side projections on the fresh rows (its first weight chunk is already in flight)
+  attn_dst_pre2<RT>(sA, sB, Wn, row0, N, Qg_n, Qhat_n, Sg_n, Gxg_n, p);
+}
+
+}  // namespace prosim

@@ -154,7 +154,7 @@ def test_edge_pe_matches_oracle(ctx):
 
 # ------------------------------------------------------------------------------------ attention
 @pytest.mark.parametrize('bipartite', [True, False])
-@pytest.mark.parametrize('n_dst', [23, 300])
+@pytest.mark.parametrize('n_dst', [23, 300, 1100, 7700])
 def test_attention_layer_matches_oracle(ctx, bipartite, n_dst):
     ops, orc = ctx['ops'], ctx['oracle']
     g = torch.Generator().manual_seed(11 + n_dst)
@@ -180,7 +180,7 @@ def test_attention_stack_matches_oracle(ctx):
     """6 x (a2p, m2p) with fixed sources -- the policy tick's core -- and 3 x self-source layers."""
     ops, orc = ctx['ops'], ctx['oracle']
     g = torch.Generator().manual_seed(13)
-    P, NA, NM, sa, sm = 70, 64, 150, 30, 50
+    P, NA, NM, sa, sm = 1100, 1064, 8150, 30, 50    # >= 1024 rows: the gemm_tile (v2) kernels run
     nbr_a, deg_a, ja, ei_a = _random_graph(g, P, NA, sa)
     nbr_m, deg_m, jm, ei_m = _random_graph(g, P, NM, sm, empty_row=False)
     x_p, x_a, x_m = torch.randn(P, 128, generator=g), torch.randn(NA, 128, generator=g), torch.randn(NM, 128, generator=g)
