@@ -27,11 +27,14 @@ typedef void* prosim_stream_t; /* cudaStream_t */
 
 /* Fixed-stride neighbour lists + the per-edge normalised relative PE that go with them. */
 typedef struct {
-  const float* z;      /* [n_dst*stride][128] LayerNorm(rel PE) without affine, row = dst*stride + j */
+  const float* z;      /* [n_dst*stride][zd] LayerNorm(rel PE) without affine, row = dst*stride + j  */
   const int32_t* nbr;  /* [n_dst*stride] source row of edge j of destination dst (ascending)          */
   const int32_t* deg;  /* [n_dst] number of valid edges per destination                               */
   int32_t stride;      /* row stride of nbr / z                                                        */
-  int32_t max_deg;     /* upper bound of deg (sizes the softmax scratch in shared memory)             */
+  int32_t max_deg;     /* upper bound of deg                                                           */
+  int32_t zd;          /* width of a z row: 128, or 96 for pure rel-PE edges (features 96..127 duplicate
+                          64..95 and are dropped; prosim_edge_pe writes either)                         */
+  int32_t warps_per_row; /* hint: 32-edge tiles expected per destination (1,2,3,6); 0 = derive from max_deg */
 } prosim_graph_t;
 
 /* One side of an alternating attention stack (prosim_attn_stack_fwd). */
@@ -84,7 +87,7 @@ int prosim_build_knn_edges(const float* qpos, const int32_t* qscene, int n_q, co
  * the normalisation (condition edges, condition_transformer/condition_attns.py:211-216). */
 int prosim_edge_pe(const float* dpos, const float* dori, int n_dst, const float* spos, const float* sori,
                    const int32_t* nbr, const int32_t* deg, int stride, const float* dim_t16, const float* extra,
-                   float* z, prosim_stream_t stream);
+                   int zd, float* z, prosim_stream_t stream);
 
 /* AttentionLayer pieces (prosim/models/layers/attention_layer.py:56-118) */
 int prosim_attn_kv(const float* x_src, int n_src, const float* w, size_t w_layer_stride, int n_layers, float* kv,

@@ -3,6 +3,7 @@
 
 #include "attn.cuh"
 #include "attn2.cuh"
+#include "edge2.cuh"
 #include "common.cuh"
 #include "graph.cuh"
 #include "pointnet.cuh"
@@ -77,7 +78,14 @@ int setup_attributes() {
   if (state != 0) return state == 1 ? 0 : state;
   cudaError_t e = cudaSuccess;
   auto acc = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
-  acc(allow_smem(attn_edge_kernel, 200 * 1024));
+  acc(allow_smem(attn_edge2_kernel<96, 1>, Edge2Cfg<96>::smem_bytes(6)));
+  acc(allow_smem(attn_edge2_kernel<96, 2>, Edge2Cfg<96>::smem_bytes(3)));
+  acc(allow_smem(attn_edge2_kernel<96, 3>, Edge2Cfg<96>::smem_bytes(2)));
+  acc(allow_smem(attn_edge2_kernel<96, 6>, Edge2Cfg<96>::smem_bytes(1)));
+  acc(allow_smem(attn_edge2_kernel<128, 1>, Edge2Cfg<128>::smem_bytes(6)));
+  acc(allow_smem(attn_edge2_kernel<128, 2>, Edge2Cfg<128>::smem_bytes(3)));
+  acc(allow_smem(attn_edge2_kernel<128, 3>, Edge2Cfg<128>::smem_bytes(2)));
+  acc(allow_smem(attn_edge2_kernel<128, 6>, Edge2Cfg<128>::smem_bytes(1)));
   acc(allow_smem(attn_post_kernel<8>, PostSmem<8>::bytes));
   acc(allow_smem(attn_post_kernel<4>, PostSmem<4>::bytes));
   acc(allow_smem(attn_post_kernel<2>, PostSmem<2>::bytes));
@@ -163,31 +171,52 @@ int launch_dstpre(const float* x, int n, const float* w, const DstScratch& d, cu
   return 0;
 }
 
-int launch_edge(const DstScratch& d, const float* kv, const prosim_graph_t& g, int n_dst, float* rbar, float* aggv,
-                cudaStream_t st) {
-  if (n_dst <= 0) return 0;
-  const int sstride = ((g.max_deg < 4 ? 4 : g.max_deg) + 3) & ~3;
-  const size_t smem = attn_edge_smem_bytes(sstride);
-  if (smem > 200 * 1024) return ERR_ARG;
-  LaunchScope ls(PROSIM_K_ATTN_EDGE, st);
-  attn_edge_kernel<<<n_dst, 256, smem, st>>>(d.q, d.qhat, kv, g.z, g.nbr, g.deg, g.stride, sstride, rbar, aggv);
+template <int ZD, int WPR>
+int launch_edge_t(const DstScratch& d, const float* kv, const prosim_graph_t& g, int n_dst, float* rbar, float* aggv,
+                  cudaStream_t st) {
+  constexpr int RPC = EDGE_NW / WPR;
+  attn_edge2_kernel<ZD, WPR><<<(n_dst + RPC - 1) / RPC, EDGE_NW * 32, Edge2Cfg<ZD>::smem_bytes(RPC), st>>>(
+      d.q, d.qhat, kv, g.z, g.nbr, g.deg, g.stride, n_dst, rbar, aggv);
   PROSIM_CHECK_LAUNCH();
   return 0;
 }
 
-int launch_post(const float* x, int n, const float* rbar, const float* aggv, const DstScratch& cur, const float* w,
+// warps per destination row: one 32-edge tile per warp at the expected degree (hint), else by the degree bound
+inline int pick_wpr(const prosim_graph_t& g) {
+  int w = g.warps_per_row;
+  if (w <= 0) {
+    const int d = g.max_deg < g.stride ? g.max_deg : g.stride;
+    w = d <= 32 ? 1 : d <= 64 ? 2 : d <= 128 ? 3 : 6;
+  }
+  return w >= 6 ? 6 : w >= 3 ? 3 : w == 2 ? 2 : 1;
+}
+
+int launch_edge(const DstScratch& d, const float* kv, const prosim_graph_t& g, int n_dst, float* rbar, float* aggv,
+                cudaStream_t st) {
+  if (n_dst <= 0) return 0;
+  if (g.zd != 96 && g.zd != 128) return ERR_ARG;
+  LaunchScope ls(PROSIM_K_ATTN_EDGE, st);
+  const int wpr = pick_wpr(g);
+#define EDGE_CASE(ZD, W) if (g.zd == ZD && wpr == W) return launch_edge_t<ZD, W>(d, kv, g, n_dst, rbar, aggv, st)
+  EDGE_CASE(96, 1); EDGE_CASE(96, 2); EDGE_CASE(96, 3); EDGE_CASE(96, 6);
+  EDGE_CASE(128, 1); EDGE_CASE(128, 2); EDGE_CASE(128, 3); EDGE_CASE(128, 6);
+#undef EDGE_CASE
+  return ERR_ARG;
+}
+
+int launch_post(const float* x, int n, int zd, const float* rbar, const float* aggv, const DstScratch& cur, const float* w,
                 float* out, const float* w_next, const DstScratch& nxt, cudaStream_t st) {
   if (n <= 0) return 0;
   const int rpt = pick_rpt(n);
   LaunchScope ls(PROSIM_K_ATTN_POST, st);
   if (pick_rt(n) != 0) {
-    attn_post2_kernel<2><<<(n + 31) / 32, 256, Post2Smem<2>::bytes, st>>>(x, n, rbar, aggv, cur.s, cur.gx, w, out, w_next,
+    attn_post2_kernel<2><<<(n + 31) / 32, 256, Post2Smem<2>::bytes, st>>>(x, n, zd, rbar, aggv, cur.s, cur.gx, w, out, w_next,
                                                                          nxt.q, nxt.qhat, nxt.s, nxt.gx);
     PROSIM_CHECK_LAUNCH();
     return 0;
   }
   DISPATCH_RPT(rpt, attn_post_kernel<RPT><<<(n + 2 * RPT - 1) / (2 * RPT), 256, PostSmem<RPT>::bytes, st>>>(
-                        x, n, rbar, aggv, cur.s, cur.gx, w, out, w_next, nxt.q, nxt.qhat, nxt.s, nxt.gx));
+                        x, n, zd, rbar, aggv, cur.s, cur.gx, w, out, w_next, nxt.q, nxt.qhat, nxt.s, nxt.gx));
   PROSIM_CHECK_LAUNCH();
   return 0;
 }
@@ -196,7 +225,7 @@ int launch_post(const float* x, int n, const float* rbar, const float* aggv, con
 
 extern "C" {
 
-int prosim_abi_version(void) { return 1; }
+int prosim_abi_version(void) { return 2; }
 
 long long prosim_launch_count(int kernel_class) {
   if (kernel_class >= 0 && kernel_class < N_CLASSES) return g_launches[kernel_class];
@@ -293,15 +322,20 @@ int prosim_build_knn_edges(const float* qpos, const int32_t* qscene, int n_q, co
 }
 
 int prosim_edge_pe(const float* dpos, const float* dori, int n_dst, const float* spos, const float* sori,
-                   const int32_t* nbr, const int32_t* deg, int stride, const float* dim_t16, const float* extra, float* z,
-                   prosim_stream_t stream) {
-  if (n_dst < 0 || stride <= 0) return ERR_ARG;
+                   const int32_t* nbr, const int32_t* deg, int stride, const float* dim_t16, const float* extra, int zd,
+                   float* z, prosim_stream_t stream) {
+  if (n_dst < 0 || stride <= 0 || (zd != 96 && zd != 128) || (extra && zd != 128)) return ERR_ARG;
   if (n_dst == 0) return 0;
   if (!dpos || !dori || !spos || !sori || !nbr || !deg || !dim_t16 || !z) return ERR_ARG;
   LaunchScope ls(PROSIM_K_EDGE_PE, S(stream));
-  edge_pe_kernel<<<n_dst, 128, 0, S(stream)>>>(reinterpret_cast<const float2*>(dpos), dori,
-                                               reinterpret_cast<const float2*>(spos), sori, nbr, deg, stride, dim_t16,
-                                               extra, z);
+  if (zd == 96)
+    edge_pe_kernel<96><<<n_dst, 128, 0, S(stream)>>>(reinterpret_cast<const float2*>(dpos), dori,
+                                                     reinterpret_cast<const float2*>(spos), sori, nbr, deg, stride,
+                                                     dim_t16, extra, z);
+  else
+    edge_pe_kernel<128><<<n_dst, 128, 0, S(stream)>>>(reinterpret_cast<const float2*>(dpos), dori,
+                                                      reinterpret_cast<const float2*>(spos), sori, nbr, deg, stride,
+                                                      dim_t16, extra, z);
   PROSIM_CHECK_LAUNCH();
   return 0;
 }
@@ -327,7 +361,7 @@ int prosim_attn_layer_fwd(const float* x_src, int n_src, const float* x_dst, int
   if (int e = launch_kv(x_src, n_src, w, 0, 1, ws.kv, 0, st)) return e;
   if (int e = launch_dstpre(x_dst, n_dst, w, ws.set[0], st)) return e;
   if (int e = launch_edge(ws.set[0], ws.kv, *g, n_dst, ws.rbar, ws.aggv, st)) return e;
-  return launch_post(x_dst, n_dst, ws.rbar, ws.aggv, ws.set[0], w, out, nullptr, ws.set[1], st);
+  return launch_post(x_dst, n_dst, g->zd, ws.rbar, ws.aggv, ws.set[0], w, out, nullptr, ws.set[1], st);
 }
 
 int prosim_attn_stack_fwd(const float* x, int n_dst, int n_layers, const prosim_stack_side_t* side_a,
@@ -367,7 +401,7 @@ int prosim_attn_stack_fwd(const float* x, int n_dst, int n_layers, const prosim_
       w_next = sides[ni % n_sides]->w + (size_t)(ni / n_sides) * aw::SIZE;
     }
     float* dst_x = last ? out : (cur_x == ws.x0 ? ws.x1 : ws.x0);
-    if (int e = launch_post(cur_x, n_dst, ws.rbar, ws.aggv, ws.set[cur_set], w, dst_x, w_next, ws.set[cur_set ^ 1], st))
+    if (int e = launch_post(cur_x, n_dst, sd->graph.zd, ws.rbar, ws.aggv, ws.set[cur_set], w, dst_x, w_next, ws.set[cur_set ^ 1], st))
       return e;
     cur_x = dst_x;
     cur_set ^= 1;

@@ -4,7 +4,7 @@
 // Kernels
 //   attn_kv_kernel      source rows  : LN_src -> K', V'                 (row-tile GEMM, batched over layers)
 //   attn_dstpre_kernel  dest rows    : LN_dst -> q, Qhat[8][128], S, Gx (row-tile GEMM)
-//   attn_edge_kernel    one CTA / destination row: scores, segment softmax, sum_e a_e V'_j and sum_e a_e z_e
+//   (edge phase: edge2.cuh)
 //   attn_post_kernel    dest rows    : Wvr-contraction, gate, out-proj, LN, FFN, LN (+ next layer's dstpre fused)
 #pragma once
 #include "common.cuh"
@@ -115,127 +115,6 @@ __global__ void __launch_bounds__(256) attn_dstpre_kernel(const float* __restric
   attn_dst_pre<RPT>(xd, qs, W, row0, N, Qg, Qhat, Sg, Gxg);
 }
 
-// ------------------------------------------------------------------------------------------------ edges
-// One CTA (8 warps) per destination row.  Neighbour list: nbr[row*stride + j], j < deg[row]; the
-// normalised relative PE of that edge is Z[(row*stride + j)*128 ..].  KV rows are [K'(128) | V'(128)].
-// Dynamic smem: scores [8][sstride] where sstride >= max degree (multiple of 4).
-constexpr int EDGE_PART = H * D + D;  // 1152 partial outputs per warp
-__global__ void __launch_bounds__(256) attn_edge_kernel(const float* __restrict__ Qg, const float* __restrict__ Qhat,
-                                                        const float* __restrict__ KV, const float* __restrict__ Z,
-                                                        const int* __restrict__ nbr, const int* __restrict__ deg,
-                                                        int stride, int sstride, float* __restrict__ Rbar,
-                                                        float* __restrict__ AggV) {
-  extern __shared__ __align__(16) float smem[];
-  float* sQhat = smem;                    // [8][128]
-  float* sQ = sQhat + H * D;              // [128]
-  float* sPart = sQ + D;                  // [8 warps][1152]
-  float* sS = sPart + 8 * EDGE_PART;      // [8][sstride]
-  const int row = blockIdx.x;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_e = min(deg[row], stride);
-  const size_t ebase = (size_t)row * stride;
-
-  for (int i = threadIdx.x; i < H * D / 4; i += 256)
-    reinterpret_cast<float4*>(sQhat)[i] = reinterpret_cast<const float4*>(Qhat + (size_t)row * H * D)[i];
-  if (threadIdx.x < D / 4)
-    reinterpret_cast<float4*>(sQ)[threadIdx.x] = reinterpret_cast<const float4*>(Qg + (size_t)row * D)[threadIdx.x];
-  __syncthreads();
-
-  // pass A: lane = edge, all 8 head scores in registers
-  for (int e = warp * 32 + lane; e < n_e; e += 256) {
-    const int j = __ldg(nbr + ebase + e);
-    const float4* kp = reinterpret_cast<const float4*>(KV + (size_t)j * 256);
-    const float4* zp = reinterpret_cast<const float4*>(Z + (ebase + e) * D);
-    float s[H];
-#pragma unroll
-    for (int h = 0; h < H; ++h) s[h] = 0.f;
-#pragma unroll
-    for (int h = 0; h < H; ++h) {
-#pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        float4 k4 = __ldg(kp + h * 4 + c4);
-        float4 q4 = reinterpret_cast<const float4*>(sQ)[h * 4 + c4];
-        s[h] = fmaf(q4.x, k4.x, s[h]);
-        s[h] = fmaf(q4.y, k4.y, s[h]);
-        s[h] = fmaf(q4.z, k4.z, s[h]);
-        s[h] = fmaf(q4.w, k4.w, s[h]);
-      }
-    }
-#pragma unroll 4
-    for (int d4 = 0; d4 < D / 4; ++d4) {
-      float4 z4 = __ldg(zp + d4);
-#pragma unroll
-      for (int h = 0; h < H; ++h) {
-        float4 q4 = reinterpret_cast<const float4*>(sQhat + h * D)[d4];
-        s[h] = fmaf(q4.x, z4.x, s[h]);
-        s[h] = fmaf(q4.y, z4.y, s[h]);
-        s[h] = fmaf(q4.z, z4.z, s[h]);
-        s[h] = fmaf(q4.w, z4.w, s[h]);
-      }
-    }
-#pragma unroll
-    for (int h = 0; h < H; ++h) sS[h * sstride + e] = s[h];
-  }
-  __syncthreads();
-
-  // pass M: warp h normalises head h  (torch_geometric.utils.softmax: exp(s - max) / (sum + 1e-16))
-  {
-    float* sh = sS + warp * sstride;
-    float m = -INFINITY;
-    for (int e = lane; e < n_e; e += 32) m = fmaxf(m, sh[e]);
-    m = warp_max(m);
-    float sum = 0.f;
-    for (int e = lane; e < n_e; e += 32) {
-      float p = expf(sh[e] - m);
-      sh[e] = p;
-      sum += p;
-    }
-    sum = warp_sum(sum);
-    const float inv = 1.0f / (sum + 1e-16f);
-    for (int e = lane; e < n_e; e += 32) sh[e] *= inv;
-  }
-  __syncthreads();
-
-  // pass B: warp takes edges e = warp (mod 8); lane owns 4 columns of every head's Rbar and of AggV
-  float4 rb[H];
-#pragma unroll
-  for (int h = 0; h < H; ++h) rb[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int own_h = lane >> 2;
-  for (int e = warp; e < n_e; e += 8) {
-    const int j = __ldg(nbr + ebase + e);
-    const float4 z4 = __ldg(reinterpret_cast<const float4*>(Z + (ebase + e) * D) + lane);
-    const float4 v4 = __ldg(reinterpret_cast<const float4*>(KV + (size_t)j * 256 + 128) + lane);
-#pragma unroll
-    for (int h = 0; h < H; ++h) {
-      const float a = sS[h * sstride + e];
-      rb[h].x = fmaf(a, z4.x, rb[h].x);
-      rb[h].y = fmaf(a, z4.y, rb[h].y);
-      rb[h].z = fmaf(a, z4.z, rb[h].z);
-      rb[h].w = fmaf(a, z4.w, rb[h].w);
-    }
-    const float ao = sS[own_h * sstride + e];
-    av.x = fmaf(ao, v4.x, av.x);
-    av.y = fmaf(ao, v4.y, av.y);
-    av.z = fmaf(ao, v4.z, av.z);
-    av.w = fmaf(ao, v4.w, av.w);
-  }
-  float* part = sPart + warp * EDGE_PART;
-#pragma unroll
-  for (int h = 0; h < H; ++h) *reinterpret_cast<float4*>(part + h * D + 4 * lane) = rb[h];
-  *reinterpret_cast<float4*>(part + H * D + 4 * lane) = av;
-  __syncthreads();
-  for (int o = threadIdx.x; o < EDGE_PART; o += 256) {
-    float t = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) t += sPart[w * EDGE_PART + o];
-    if (o < H * D) Rbar[(size_t)row * H * D + o] = t;
-    else AggV[(size_t)row * D + (o - H * D)] = t;
-  }
-}
-
-inline size_t attn_edge_smem_bytes(int sstride) { return sizeof(float) * (size_t)(H * D + D + 8 * EDGE_PART + 8 * sstride); }
-
 // ------------------------------------------------------------------------------------------------ post
 // Per tile of R = 2*RPT destination rows:
 //   agg = AggV + Wvr' Rbar ; g = sigmoid(Wga agg + Gx) ; u = agg + g (S - agg) ; o = Wo u + bo
@@ -244,14 +123,14 @@ inline size_t attn_edge_smem_bytes(int sstride) { return sizeof(float) * (size_t
 template <int RPT>
 struct PostSmem {
   static constexpr int R = 2 * RPT;
-  static constexpr int LDR = H * D + 4;   // Rbar tile row stride
+  static constexpr int LDR = H * D + 4;   // Rbar tile row stride (largest case, zd = 128)
   static constexpr int LDH = 4 * D + 4;   // FFN hidden tile row stride
   static constexpr size_t floats = (size_t)R * LDR + 2 * (size_t)R * LDS_PAD;
   static constexpr size_t bytes = floats * sizeof(float);
 };
 
 template <int RPT>
-__global__ void __launch_bounds__(256) attn_post_kernel(const float* __restrict__ Xdst, int N,
+__global__ void __launch_bounds__(256) attn_post_kernel(const float* __restrict__ Xdst, int N, int zd,
                                                         const float* __restrict__ Rbar, const float* __restrict__ AggV,
                                                         const float* __restrict__ Sg, const float* __restrict__ Gxg,
                                                         const float* __restrict__ W, float* __restrict__ Out,
@@ -268,11 +147,13 @@ __global__ void __launch_bounds__(256) attn_post_kernel(const float* __restrict_
   const int n = threadIdx.x & 127, rg = threadIdx.x >> 7;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  for (int i = threadIdx.x; i < R * (H * D / 4); i += 256) {
-    int r = i / (H * D / 4), c = (i % (H * D / 4)) * 4;
+  const int rw = H * zd;            // Rbar row: [8 heads][zd]
+  const int ldr = rw + 4;
+  for (int i = threadIdx.x; i < R * (rw / 4); i += 256) {
+    int r = i / (rw / 4), c = (i % (rw / 4)) * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row0 + r < N) v = *reinterpret_cast<const float4*>(Rbar + (size_t)(row0 + r) * H * D + c);
-    *reinterpret_cast<float4*>(sR + r * SM::LDR + c) = v;
+    if (row0 + r < N) v = *reinterpret_cast<const float4*>(Rbar + (size_t)(row0 + r) * rw + c);
+    *reinterpret_cast<float4*>(sR + r * ldr + c) = v;
   }
   __syncthreads();
 
@@ -283,7 +164,7 @@ __global__ void __launch_bounds__(256) attn_post_kernel(const float* __restrict_
     int row = row0 + rg * RPT + r;
     acc[r] = row < N ? AggV[(size_t)row * D + n] : 0.f;
   }
-  gemm_tile_acc<RPT>(acc, sR + (n >> 4) * D, SM::LDR, D, W + aw::WVRGT, D);
+  gemm_tile_acc<RPT>(acc, sR + (n >> 4) * zd, ldr, zd, W + (zd == 96 ? aw::WVRG96T : aw::WVRGT), D);
   acc_store_smem<RPT>(acc, sA, LDS_PAD, false);
   float agg[RPT];
 #pragma unroll

@@ -108,7 +108,7 @@ struct Post2Smem {
 };
 
 template <int RT>
-__global__ void __launch_bounds__(256, 1) attn_post2_kernel(const float* __restrict__ Xdst, int N,
+__global__ void __launch_bounds__(256, 1) attn_post2_kernel(const float* __restrict__ Xdst, int N, int zd,
                                                             const float* __restrict__ Rbar, const float* __restrict__ AggV,
                                                             const float* __restrict__ Sg, const float* __restrict__ Gxg,
                                                             const float* __restrict__ W, float* __restrict__ Out,
@@ -127,21 +127,22 @@ __global__ void __launch_bounds__(256, 1) attn_post2_kernel(const float* __restr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // the first weight chunk flies while the Rbar tile is loaded
-  wpipe_issue(p.buf, W + aw::WVRGT, D, 0, KC);
+  const float* Wvr = W + (zd == 96 ? aw::WVRG96T : aw::WVRGT);
+  const int rw = H * zd, ldr = rw + 4;            // Rbar row: [8 heads][zd]
+  wpipe_issue(p.buf, Wvr, D, 0, KC);
   cp_async_commit();
   p.primed = true;
-  for (int i = threadIdx.x; i < M * (H * D / 4); i += 256) {
-    const int r = i / (H * D / 4), c = (i % (H * D / 4)) * 4;
+  for (int i = threadIdx.x; i < M * (rw / 4); i += 256) {
+    const int r = i / (rw / 4), c = (i % (rw / 4)) * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row0 + r < N) v = __ldg(reinterpret_cast<const float4*>(Rbar + (size_t)(row0 + r) * H * D + c));
-    *reinterpret_cast<float4*>(sR + r * SM::LDR + c) = v;
+    if (row0 + r < N) v = __ldg(reinterpret_cast<const float4*>(Rbar + (size_t)(row0 + r) * rw + c));
+    *reinterpret_cast<float4*>(sR + r * ldr + c) = v;
   }
 
   float acc[RT][8], agg[RT][8];
   // 1. agg = AggV + Wvr' Rbar (block diagonal: the A row of an output column is the Rbar row of its head)
   acc2_load_global<RT>(acc, AggV, D, row0, N);
-  gemm_tile2<RT, true>(acc, sR + (tx >> 2) * D, sR + (4 + (tx >> 2)) * D, SM::LDR, D, W + aw::WVRGT, D, p,
-                       W + aw::WGAT, D, D);
+  gemm_tile2<RT, true>(acc, sR + (tx >> 2) * zd, sR + (4 + (tx >> 2)) * zd, ldr, zd, Wvr, D, p, W + aw::WGAT, D, D);
   acc2_store_smem<RT>(acc, sA, LDS_PAD, false);
 #pragma unroll
   for (int r = 0; r < RT; ++r)

@@ -103,6 +103,9 @@ __global__ void __launch_bounds__(128) knn_kernel(const float2* __restrict__ qpo
 // One CTA (4 warps) per destination row, a warp per edge, lane l owns features 4l..4l+3.
 // extra (optional): per-edge [128] vector added to the PE before the normalisation (condition edges,
 // condition_transformer/condition_attns.py:211-216), indexed like Z.
+// ZD = 128 stores all features; ZD = 96 (only without `extra`) drops features 96..127, which are bit-identical
+// copies of 64..95 (the embedding gets phi twice); the statistics still run over all 128.
+template <int ZD>
 __global__ void __launch_bounds__(128) edge_pe_kernel(const float2* __restrict__ dpos, const float* __restrict__ dori,
                                                       const float2* __restrict__ spos, const float* __restrict__ sori,
                                                       const int* __restrict__ nbr, const int* __restrict__ deg, int stride,
@@ -138,7 +141,8 @@ __global__ void __launch_bounds__(128) edge_pe_kernel(const float2* __restrict__
       const float4 x = *reinterpret_cast<const float4*>(extra + ei * D + 4 * lane);
       f.x += x.x; f.y += x.y; f.z += x.z; f.w += x.w;
     }
-    *reinterpret_cast<float4*>(Z + ei * D + 4 * lane) = ln_row_noaffine(f);
+    const float4 zn = ln_row_noaffine(f);
+    if (4 * lane < ZD) *reinterpret_cast<float4*>(Z + ei * ZD + 4 * lane) = zn;
   }
 }
 

@@ -22,7 +22,8 @@ constexpr int WVT = KB + 128;            // [128][128]
 constexpr int VB = WVT + 16384;          // b_v + Wvr beta_r + b_vr
 constexpr int WKRG = VB + 128;           // [128 n=h*16+c][128 d] = gamma_r[d] * Wkr[n][d]
 constexpr int WVRGT = WKRG + 16384;      // [128 d][128 c] = gamma_r[d] * Wvr[c][d]
-constexpr int WST = WVRGT + 16384;       // [128][128]
+constexpr int WVRG96T = WVRGT + 16384;   // [96 d][128 c]: WVRGT with rows 96..127 added onto rows 64..95, for 96-wide z
+constexpr int WST = WVRG96T + 12288;     // [128][128]
 constexpr int BS = WST + 16384;
 constexpr int WGAT = BS + 128;           // to_g columns 0..127 (agg part), [128 k][128 n]
 constexpr int WGXT = WGAT + 16384;       // to_g columns 128..255 (x_dst part)

@@ -8,7 +8,7 @@ from ctypes import POINTER, Structure, c_float, c_int, c_int32, c_size_t, c_void
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libprosim_b200.so')
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 SYMBOLS = (
     'prosim_abi_version', 'prosim_attn_layer_floats', 'prosim_pointnet_floats', 'prosim_head_floats',
@@ -23,7 +23,8 @@ KERNEL_CLASSES = {'pointnet': 0, 'radius': 1, 'knn': 2, 'edge_pe': 3, 'attn_kv':
 
 
 class Graph(Structure):
-    _fields_ = [('z', c_void_p), ('nbr', c_void_p), ('deg', c_void_p), ('stride', c_int32), ('max_deg', c_int32)]
+    _fields_ = [('z', c_void_p), ('nbr', c_void_p), ('deg', c_void_p), ('stride', c_int32), ('max_deg', c_int32),
+                ('zd', c_int32), ('warps_per_row', c_int32)]
 
 
 class StackSide(Structure):
@@ -39,7 +40,7 @@ _SIGS = {
     'prosim_pointnet_fwd': [c_int, _P, _P, _P, c_int, _P, _P, _P],
     'prosim_build_radius_edges': [_P, _P, c_int, _P, _P, c_float, c_int, c_int, _P, _P, c_int, _P],
     'prosim_build_knn_edges': [_P, _P, c_int, _P, _P, c_int, c_int, _P, _P, c_int, _P],
-    'prosim_edge_pe': [_P, _P, c_int, _P, _P, _P, _P, c_int, _P, _P, _P, _P],
+    'prosim_edge_pe': [_P, _P, c_int, _P, _P, _P, _P, c_int, _P, _P, c_int, _P, _P],
     'prosim_attn_kv': [_P, c_int, _P, c_size_t, c_int, _P, c_size_t, _P],
     'prosim_attn_layer_fwd': [_P, c_int, _P, c_int, POINTER(Graph), _P, _P, c_size_t, _P, _P],
     'prosim_attn_stack_fwd': [_P, c_int, c_int, POINTER(StackSide), POINTER(StackSide), _P, c_size_t, _P, _P],

@@ -240,8 +240,8 @@ class ProSimB200(nn.Module):
                             min(k_a, max(pl.max_a, 1)))
         e_s = ops.knn_edges(tok_pos, pl.i['tok_scene'], tok_pos, pl.i['seg_scene'].view(-1, 4), k_s, max(pl.max_tok, 1),
                             min(k_s, max(pl.max_tok, 1)))
-        ops.edge_pe(e_a, a_pos, a_ori, a_pos, a_ori, dim_t, z=self._buf('z_enc_a', (NA * e_a.stride, D)))
-        ops.edge_pe(e_s, tok_pos, tok_ori, tok_pos, tok_ori, dim_t, z=self._buf('z_enc_s', (S * e_s.stride, D)))
+        ops.edge_pe(e_a, a_pos, a_ori, a_pos, a_ori, dim_t, z=self._buf('z_enc_a', (NA * e_a.stride, 96)))
+        ops.edge_pe(e_s, tok_pos, tok_ori, tok_pos, tok_ori, dim_t, z=self._buf('z_enc_s', (S * e_s.stride, 96)))
         ws = self._buf('attn_ws', (lib.load().prosim_attn_workspace_floats(S, S),))
         lf = weights.ATTN_LAYER_FLOATS
         xa = tok[NM:]
@@ -293,8 +293,8 @@ class ProSimB200(nn.Module):
                                     min(cap + 1, max(pl.max_p, 1)), drop_self=True)
             e_sp = ops.radius_edges(p_pos, pl.i['p_scene'], tok_pos, pl.i['seg_scene'].view(-1, 4), dcfg.SCENE_RADIUS, cap,
                                     min(cap, max(pl.max_tok, 1)))
-            ops.edge_pe(e_pp, p_pos, p_ori, p_pos, p_ori, dim_t, z=self._buf('z_pp', (P * e_pp.stride, D)))
-            ops.edge_pe(e_sp, p_pos, p_ori, tok_pos, tok_ori, dim_t, z=self._buf('z_sp', (P * e_sp.stride, D)))
+            ops.edge_pe(e_pp, p_pos, p_ori, p_pos, p_ori, dim_t, z=self._buf('z_pp', (P * e_pp.stride, 96)))
+            ops.edge_pe(e_sp, p_pos, p_ori, tok_pos, tok_ori, dim_t, z=self._buf('z_sp', (P * e_sp.stride, 96)))
             kv_s = ops.attn_kv(tok, ar, off['dec_s2p'], self.num_layers, lf, kv=self._buf('kv_dec', (self.num_layers, S, 2 * D)))
             ws = self._buf('attn_ws', (lib.load().prosim_attn_workspace_floats(max(P, S), max(P, S)),))
             emd_flat = ops.attn_stack(x_p, self.num_layers, ops.stack_side(ar, off['dec_p2p'], e_pp),
@@ -384,7 +384,7 @@ class ProSimB200(nn.Module):
         stride_m = min(acfg.MAX_NUM_NEIGH, max(pl.max_m, 1))
         nbr_a, deg_a = self._buf('nbr_a', (P * stride_a,), torch.int32), self._buf('deg_a', (P,), torch.int32)
         nbr_m, deg_m = self._buf('nbr_m', (P * stride_m,), torch.int32), self._buf('deg_m', (P,), torch.int32)
-        z_a, z_m = self._buf('z_a', (P * stride_a, D)), self._buf('z_m', (P * stride_m, D))
+        z_a, z_m = self._buf('z_a', (P * stride_a, 96)), self._buf('z_m', (P * stride_m, 96))
         self._buf('kv_a', (L, max_na, 2 * D))
         x_a_buf = self._buf('x_a', (max_na, D))
         a_pos_buf, a_ori_buf = self._buf('a_pos', (max_na, 2)), self._buf('a_ori', (max_na,))
@@ -412,6 +412,7 @@ class ProSimB200(nn.Module):
                                    acfg.MAX_NUM_NEIGH, stride_a, nbr=nbr_a, deg=deg_a)
             e_m = ops.radius_edges(p_pos, pl.i['p_scene'], m_pos, pl.i['seg_map'].view(-1, 4), acfg.MAP_RADIUS,
                                    acfg.MAX_NUM_NEIGH, stride_m, nbr=nbr_m, deg=deg_m)
+            e_m.warps_per_row = 2     # map radius 50 m: a policy row typically sees ~40 of the scene's polylines
             ops.edge_pe(e_a, p_pos, p_ori, a_pos, a_ori, dim_t, z=z_a)
             ops.edge_pe(e_m, p_pos, p_ori, m_pos, m_ori, dim_t, z=z_m)
             kva = ops.attn_kv(x_a, ar, off['pol_a2p'], L, lf, kv=self._buf('kv_a', (L, na, 2 * D)))

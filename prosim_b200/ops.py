@@ -38,15 +38,16 @@ def as_u8(mask):
 class EdgeList:
     """Fixed-stride neighbour lists (+ the per-edge normalised relative PE once computed)."""
 
-    def __init__(self, nbr, deg, stride, max_deg, z=None):
+    def __init__(self, nbr, deg, stride, max_deg, z=None, zd=128, warps_per_row=0):
         self.nbr, self.deg, self.stride, self.max_deg, self.z = nbr, deg, int(stride), int(max_deg), z
+        self.zd, self.warps_per_row = int(zd), int(warps_per_row)
 
     @property
     def n_dst(self):
         return self.deg.shape[0]
 
     def c_struct(self):
-        return Graph(ptr(self.z), ptr(self.nbr), ptr(self.deg), self.stride, self.max_deg)
+        return Graph(ptr(self.z), ptr(self.nbr), ptr(self.deg), self.stride, self.max_deg, self.zd, self.warps_per_row)
 
     def to_edge_index(self):
         """[2, E] (row0 = source, row1 = destination) on the host, for bit-exact comparison with the oracle."""
@@ -99,11 +100,12 @@ def edge_pe(edges, dpos, dori, spos, sori, dim_t16, extra=None, z=None):
     for t, n in ((dpos, 'dpos'), (dori, 'dori'), (spos, 'spos'), (sori, 'sori'), (dim_t16, 'dim_t16'), (extra, 'extra')):
         _chk(t, torch.float32, n)
     n_dst = edges.n_dst
+    zd = 128 if extra is not None else 96     # pure rel-PE rows carry 96 distinct features (phi is embedded twice)
     if z is None:
-        z = torch.empty(n_dst * edges.stride, D, device=dpos.device, dtype=torch.float32)
+        z = torch.empty(n_dst * edges.stride, zd, device=dpos.device, dtype=torch.float32)
     lib.call('prosim_edge_pe', ptr(dpos), ptr(dori), n_dst, ptr(spos), ptr(sori), ptr(edges.nbr), ptr(edges.deg),
-             edges.stride, ptr(dim_t16), ptr(extra), ptr(z), _stream())
-    edges.z = z
+             edges.stride, ptr(dim_t16), ptr(extra), zd, ptr(z), _stream())
+    edges.z, edges.zd = z, zd
     return edges
 
 

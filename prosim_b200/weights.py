@@ -142,7 +142,7 @@ def param_shapes_cache(goal_condition):
 
 
 # ----------------------------------------------------------------------------- packing (mirror of csrc/weights_layout.h)
-ATTN_LAYER_FLOATS = 512 + 3 * (16384 + 128) + 2 * 16384 + (16384 + 128) + (2 * 16384 + 128) + (16384 + 128) + 512 \
+ATTN_LAYER_FLOATS = 512 + 3 * (16384 + 128) + 2 * 16384 + 12288 + (16384 + 128) + (2 * 16384 + 128) + (16384 + 128) + 512 \
     + (65536 + 512) + (65536 + 128) + 256
 POINTNET_FLOATS = (24 * 128 + 384) + (16384 + 384) + (16384 + 128) + (2 * 16384 + 384) + (16384 + 128) + 2 * (16384 + 128)
 _MLP3_FLOATS = 2 * (16384 + 384) + (64 * 128 + 128)
@@ -152,6 +152,14 @@ MLP2_FLOATS = 8 * 128 + 384 + 16384 + 128
 
 def _f64(t):
     return t.detach().double().cpu()
+
+
+def _fold96(wvrgt):
+    """[128 d][128 c] -> [96 d][128 c]: the PE's feature groups 64..95 and 96..127 are identical, so their weight
+    rows are summed once here instead of per edge."""
+    out = wvrgt[:96].clone()
+    out[64:96] += wvrgt[96:128]
+    return out
 
 
 def pack_attn_layer(sd, p):
@@ -169,6 +177,7 @@ def pack_attn_layer(sd, p):
         w('to_v.weight').t(), w('to_v.bias') + wvr @ b_r + w('to_v_r.bias'),
         wkr * g_r[None, :],
         (wvr * g_r[None, :]).t(),
+        _fold96((wvr * g_r[None, :]).t()),
         w('to_s.weight').t(), w('to_s.bias'),
         wg[:, :D].t(), wg[:, D:].t(), w('to_g.bias'),
         w('to_out.weight').t(), w('to_out.bias'),
