@@ -53,7 +53,7 @@ int prosim_abi_version(void);
 enum {
   PROSIM_K_POINTNET = 0, PROSIM_K_RADIUS = 1, PROSIM_K_KNN = 2, PROSIM_K_EDGE_PE = 3, PROSIM_K_ATTN_KV = 4,
   PROSIM_K_ATTN_DSTPRE = 5, PROSIM_K_ATTN_EDGE = 6, PROSIM_K_ATTN_POST = 7, PROSIM_K_HEAD = 8, PROSIM_K_MLP2 = 9,
-  PROSIM_K_STATE = 10
+  PROSIM_K_STATE = 10, PROSIM_K_EDGE_QK = 11, PROSIM_K_EDGE_AV = 12
 };
 long long prosim_launch_count(int kernel_class);
 int prosim_profile_enable(int kernel_class);
@@ -63,8 +63,9 @@ int prosim_attn_layer_floats(void);
 int prosim_pointnet_floats(void);
 int prosim_head_floats(void);
 int prosim_mlp2_floats(void);
-/* scratch floats needed by prosim_attn_layer_fwd / prosim_attn_stack_fwd for n_dst destination and n_src self-source rows */
-size_t prosim_attn_workspace_floats(int n_dst, int n_src);
+/* scratch floats needed by prosim_attn_layer_fwd / prosim_attn_stack_fwd for n_dst destination rows, n_src self-source
+ * rows and neighbour lists of row stride <= max_stride */
+size_t prosim_attn_workspace_floats(int n_dst, int n_src, int max_stride);
 
 /* PointNet polyline encoder: prosim/models/scene_encoder/pointnet_encoder.py:24-62.
  * kind 0 = agent history (11 points x 24 features, mask uint8 [.,11,24]; obs_encoder.py:75-86)

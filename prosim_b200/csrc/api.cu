@@ -78,14 +78,14 @@ int setup_attributes() {
   if (state != 0) return state == 1 ? 0 : state;
   cudaError_t e = cudaSuccess;
   auto acc = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
-  acc(allow_smem(attn_edge2_kernel<96, 1>, Edge2Cfg<96>::smem_bytes(6)));
-  acc(allow_smem(attn_edge2_kernel<96, 2>, Edge2Cfg<96>::smem_bytes(3)));
-  acc(allow_smem(attn_edge2_kernel<96, 3>, Edge2Cfg<96>::smem_bytes(2)));
-  acc(allow_smem(attn_edge2_kernel<96, 6>, Edge2Cfg<96>::smem_bytes(1)));
-  acc(allow_smem(attn_edge2_kernel<128, 1>, Edge2Cfg<128>::smem_bytes(6)));
-  acc(allow_smem(attn_edge2_kernel<128, 2>, Edge2Cfg<128>::smem_bytes(3)));
-  acc(allow_smem(attn_edge2_kernel<128, 3>, Edge2Cfg<128>::smem_bytes(2)));
-  acc(allow_smem(attn_edge2_kernel<128, 6>, Edge2Cfg<128>::smem_bytes(1)));
+  acc(allow_smem(attn_edge3_kernel<96, 1>, Edge2Cfg<96>::smem_bytes(6)));
+  acc(allow_smem(attn_edge3_kernel<96, 2>, Edge2Cfg<96>::smem_bytes(3)));
+  acc(allow_smem(attn_edge3_kernel<96, 3>, Edge2Cfg<96>::smem_bytes(2)));
+  acc(allow_smem(attn_edge3_kernel<96, 6>, Edge2Cfg<96>::smem_bytes(1)));
+  acc(allow_smem(attn_edge3_kernel<128, 1>, Edge2Cfg<128>::smem_bytes(6)));
+  acc(allow_smem(attn_edge3_kernel<128, 2>, Edge2Cfg<128>::smem_bytes(3)));
+  acc(allow_smem(attn_edge3_kernel<128, 3>, Edge2Cfg<128>::smem_bytes(2)));
+  acc(allow_smem(attn_edge3_kernel<128, 6>, Edge2Cfg<128>::smem_bytes(1)));
   acc(allow_smem(attn_post_kernel<8>, PostSmem<8>::bytes));
   acc(allow_smem(attn_post_kernel<4>, PostSmem<4>::bytes));
   acc(allow_smem(attn_post_kernel<2>, PostSmem<2>::bytes));
@@ -108,12 +108,12 @@ struct DstScratch {
 
 struct StackWs {
   DstScratch set[2];
-  float *rbar, *aggv, *x0, *x1, *kv;
+  float *rbar, *aggv, *x0, *x1, *sk, *pw, *kv;
 };
 
 constexpr size_t WS_PER_DST = 2 * (size_t)(D + H * D + D + D) + H * D + D + 2 * D;
 
-StackWs carve(float* ws, int n_dst) {
+StackWs carve(float* ws, int n_dst, int max_stride) {
   StackWs w;
   float* p = ws;
   for (int i = 0; i < 2; ++i) {
@@ -126,6 +126,8 @@ StackWs carve(float* ws, int n_dst) {
   w.aggv = p; p += (size_t)n_dst * D;
   w.x0 = p;   p += (size_t)n_dst * D;
   w.x1 = p;   p += (size_t)n_dst * D;
+  w.sk = p;   p += (size_t)n_dst * max_stride * 8;
+  w.pw = p;   p += (size_t)n_dst * max_stride * 8;
   w.kv = p;
   return w;
 }
@@ -173,10 +175,21 @@ int launch_dstpre(const float* x, int n, const float* w, const DstScratch& d, cu
 
 template <int ZD, int WPR>
 int launch_edge_t(const DstScratch& d, const float* kv, const prosim_graph_t& g, int n_dst, float* rbar, float* aggv,
-                  cudaStream_t st) {
+                  float* sk, float* pw, cudaStream_t st) {
   constexpr int RPC = EDGE_NW / WPR;
-  attn_edge2_kernel<ZD, WPR><<<(n_dst + RPC - 1) / RPC, EDGE_NW * 32, Edge2Cfg<ZD>::smem_bytes(RPC), st>>>(
-      d.q, d.qhat, kv, g.z, g.nbr, g.deg, g.stride, n_dst, rbar, aggv);
+  {
+    LaunchScope ls(PROSIM_K_EDGE_QK, st);
+    edge_qk_kernel<<<(n_dst + 7) / 8, 256, 0, st>>>(d.q, kv, g.nbr, g.deg, g.stride, n_dst, sk);
+    PROSIM_CHECK_LAUNCH();
+  }
+  {
+    LaunchScope ls(PROSIM_K_ATTN_EDGE, st);
+    attn_edge3_kernel<ZD, WPR><<<(n_dst + RPC - 1) / RPC, EDGE_NW * 32, Edge2Cfg<ZD>::smem_bytes(RPC), st>>>(
+        d.qhat, sk, g.z, g.deg, g.stride, n_dst, rbar, pw);
+    PROSIM_CHECK_LAUNCH();
+  }
+  LaunchScope ls(PROSIM_K_EDGE_AV, st);
+  edge_av_kernel<<<(n_dst + 7) / 8, 256, 0, st>>>(pw, kv, g.nbr, g.deg, g.stride, n_dst, aggv);
   PROSIM_CHECK_LAUNCH();
   return 0;
 }
@@ -188,16 +201,18 @@ inline int pick_wpr(const prosim_graph_t& g) {
     const int d = g.max_deg < g.stride ? g.max_deg : g.stride;
     w = d <= 32 ? 1 : d <= 64 ? 2 : d <= 128 ? 3 : 6;
   }
-  return w >= 6 ? 6 : w >= 3 ? 3 : w == 2 ? 2 : 1;
+  w = w >= 6 ? 6 : w >= 3 ? 3 : w == 2 ? 2 : 1;
+  // a warp remembers the running max of at most Edge2Cfg::MAXT of its tiles
+  while (w < 6 && (g.stride + 32 * w - 1) / (32 * w) > Edge2Cfg<96>::MAXT) w = w == 1 ? 2 : w == 2 ? 3 : 6;
+  return w;
 }
 
 int launch_edge(const DstScratch& d, const float* kv, const prosim_graph_t& g, int n_dst, float* rbar, float* aggv,
-                cudaStream_t st) {
+                float* sk, float* pw, cudaStream_t st) {
   if (n_dst <= 0) return 0;
-  if (g.zd != 96 && g.zd != 128) return ERR_ARG;
-  LaunchScope ls(PROSIM_K_ATTN_EDGE, st);
+  if ((g.zd != 96 && g.zd != 128) || g.stride > 32 * 6 * Edge2Cfg<96>::MAXT) return ERR_ARG;
   const int wpr = pick_wpr(g);
-#define EDGE_CASE(ZD, W) if (g.zd == ZD && wpr == W) return launch_edge_t<ZD, W>(d, kv, g, n_dst, rbar, aggv, st)
+#define EDGE_CASE(ZD, W) if (g.zd == ZD && wpr == W) return launch_edge_t<ZD, W>(d, kv, g, n_dst, rbar, aggv, sk, pw, st)
   EDGE_CASE(96, 1); EDGE_CASE(96, 2); EDGE_CASE(96, 3); EDGE_CASE(96, 6);
   EDGE_CASE(128, 1); EDGE_CASE(128, 2); EDGE_CASE(128, 3); EDGE_CASE(128, 6);
 #undef EDGE_CASE
@@ -225,7 +240,7 @@ int launch_post(const float* x, int n, int zd, const float* rbar, const float* a
 
 extern "C" {
 
-int prosim_abi_version(void) { return 2; }
+int prosim_abi_version(void) { return 3; }
 
 long long prosim_launch_count(int kernel_class) {
   if (kernel_class >= 0 && kernel_class < N_CLASSES) return g_launches[kernel_class];
@@ -265,8 +280,9 @@ int prosim_attn_layer_floats(void) { return aw::SIZE; }
 int prosim_pointnet_floats(void) { return pw::SIZE; }
 int prosim_head_floats(void) { return hw::SIZE; }
 int prosim_mlp2_floats(void) { return mw::SIZE; }
-size_t prosim_attn_workspace_floats(int n_dst, int n_src) {
-  return WS_PER_DST * (size_t)(n_dst < 0 ? 0 : n_dst) + 256 * (size_t)(n_src < 0 ? 0 : n_src) + 64;
+size_t prosim_attn_workspace_floats(int n_dst, int n_src, int max_stride) {
+  const size_t nd = n_dst < 0 ? 0 : n_dst, ns = n_src < 0 ? 0 : n_src, st = max_stride < 1 ? 1 : max_stride;
+  return (WS_PER_DST + 16 * st) * nd + 256 * ns + 64;
 }
 
 int prosim_pointnet_fwd(int kind, const float* x, const uint8_t* mask, const int32_t* rows, int n_poly, const float* w,
@@ -354,13 +370,13 @@ int prosim_attn_layer_fwd(const float* x_src, int n_src, const float* x_dst, int
   if (n_src < 0 || n_dst < 0 || !g) return ERR_ARG;
   if (n_dst == 0) return 0;
   if (!x_src || !x_dst || !w || !workspace || !out || !g->z || !g->nbr || !g->deg) return ERR_ARG;
-  if (workspace_floats < prosim_attn_workspace_floats(n_dst, n_src)) return ERR_WORKSPACE;
+  if (workspace_floats < prosim_attn_workspace_floats(n_dst, n_src, g->stride)) return ERR_WORKSPACE;
   if (int e = setup_attributes()) return e;
   cudaStream_t st = S(stream);
-  StackWs ws = carve(workspace, n_dst);
+  StackWs ws = carve(workspace, n_dst, g->stride);
   if (int e = launch_kv(x_src, n_src, w, 0, 1, ws.kv, 0, st)) return e;
   if (int e = launch_dstpre(x_dst, n_dst, w, ws.set[0], st)) return e;
-  if (int e = launch_edge(ws.set[0], ws.kv, *g, n_dst, ws.rbar, ws.aggv, st)) return e;
+  if (int e = launch_edge(ws.set[0], ws.kv, *g, n_dst, ws.rbar, ws.aggv, ws.sk, ws.pw, st)) return e;
   return launch_post(x_dst, n_dst, g->zd, ws.rbar, ws.aggv, ws.set[0], w, out, nullptr, ws.set[1], st);
 }
 
@@ -371,10 +387,11 @@ int prosim_attn_stack_fwd(const float* x, int n_dst, int n_layers, const prosim_
   if (n_dst == 0) return 0;
   if (!x || !workspace || !out || !side_a->w) return ERR_ARG;
   const bool self_src = side_a->kv == nullptr || (side_b && side_b->kv == nullptr);
-  if (workspace_floats < prosim_attn_workspace_floats(n_dst, self_src ? n_dst : 0)) return ERR_WORKSPACE;
+  const int max_stride = side_b && side_b->graph.stride > side_a->graph.stride ? side_b->graph.stride : side_a->graph.stride;
+  if (workspace_floats < prosim_attn_workspace_floats(n_dst, self_src ? n_dst : 0, max_stride)) return ERR_WORKSPACE;
   if (int e = setup_attributes()) return e;
   cudaStream_t st = S(stream);
-  StackWs ws = carve(workspace, n_dst);
+  StackWs ws = carve(workspace, n_dst, max_stride);
   const prosim_stack_side_t* sides[2] = {side_a, side_b};
   const int n_sides = side_b ? 2 : 1;
   const int total = n_layers * n_sides;
@@ -393,7 +410,7 @@ int prosim_attn_stack_fwd(const float* x, int n_dst, int n_layers, const prosim_
       if (int e = launch_kv(cur_x, n_dst, w, 0, 1, ws.kv, 0, st)) return e;
       kv = ws.kv;
     }
-    if (int e = launch_edge(ws.set[cur_set], kv, sd->graph, n_dst, ws.rbar, ws.aggv, st)) return e;
+    if (int e = launch_edge(ws.set[cur_set], kv, sd->graph, n_dst, ws.rbar, ws.aggv, ws.sk, ws.pw, st)) return e;
     const bool last = i == total - 1;
     const float* w_next = nullptr;
     if (!last) {

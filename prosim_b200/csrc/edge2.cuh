@@ -1,4 +1,4 @@
-// Edge phase of the relative-PE attention layer, version 2: ONE pass over the per-edge data.
+// Edge phase of the relative-PE attention layer: three lean kernels per layer.
 //
 // For destination row i and head h (weights_layout.h, aw::):
 //   s_e   = q_i,h . K'_j,h + Qhat_i,h . z_e                 (both pre-scaled by 1/sqrt(16))
@@ -8,12 +8,16 @@
 // are identical (the reference feeds [d, dtheta, phi, phi] to the embedding) -- Qhat's two halves are summed
 // when the row is staged and the Wvr' contraction uses the matching folded weight (aw::WVRG96T).
 //
-// Mapping: a CTA of EDGE_NW = 6 warps (two CTAs per SM) serves 6/WPR destination rows; each row's edges are cut into 32-edge tiles dealt
-// round-robin to its WPR warps.  A warp stages its tile's z rows in shared memory with cp.async (one coalesced
-// 32*ZD*4-byte stream), scores it with lane = edge (all 8 heads in registers, Qhat broadcast from smem), keeps
-// flash-style running max / sum / accumulators, then aggregates the same staged tile with lane = feature
-// column.  z is read from HBM exactly once per layer; K'|V' rows come from L2.  Partials of the WPR warps are
-// merged in a fixed order (deterministic, batch invariant).
+//   edge_qk_kernel     Sk[e][h] = q . K'_j      gather of K' rows from L2: a warp per row, one coalesced 512 B
+//                      row load per edge, 8 loads in flight per lane, ~40 registers -> full occupancy
+//   attn_edge3_kernel  streams z ONCE from HBM: 32-edge tiles staged in smem by cp.async, scores with
+//                      lane = edge (all 8 heads in registers, Qhat broadcast from smem), flash-style running
+//                      max / sum, aggregation of Rbar with lane = feature column; writes the final
+//                      attention weights a_e[8] back for the third kernel
+//   edge_av_kernel     AggV = sum_e a_e V'_j     gather of V' rows, same shape as edge_qk_kernel
+// The first version fused all three; ncu showed it latency bound on the K'/V' gathers at 12 warps/SM
+// (profiles/r1_edge2_ncu_summary.txt).  Partials of the warps of a row are merged in a fixed order
+// (deterministic, batch invariant).
 #pragma once
 #include "common.cuh"
 #include "gemm_tile.cuh"   // cp_async16
@@ -26,20 +30,22 @@ template <int ZD>
 struct Edge2Cfg {
   static constexpr int ZP = ZD + 4;                 // padded smem row: (ZP/4) odd -> conflict-free LDS.128 per lane-row
   static constexpr int NC = ZD / 32;                // feature columns per lane in the aggregation pass
-  static constexpr int PART = 16 + H * ZD + D;      // per-warp partial: m[8], l[8], Rbar[8][ZD], AggV[128]
+  static constexpr int PART = 16 + H * ZD;          // per-warp partial: m[8], l[8], Rbar[8][ZD]
   static constexpr int WARP_Z = 32 * ZP;            // floats of one warp's z tile
   static_assert(PART <= WARP_Z, "partial must fit in the warp's tile buffer");
+  static constexpr int MAXT = 8;                    // tiles per warp whose running max is remembered for the final rescale
   static constexpr size_t smem_bytes(int rows_per_cta) {
-    return sizeof(float) * (size_t)(EDGE_NW * WARP_Z + EDGE_NW * 32 * 8 + rows_per_cta * (H * ZD + D) + EDGE_NW * 16);
+    return sizeof(float) * (size_t)(EDGE_NW * WARP_Z + EDGE_NW * 32 * 8 + rows_per_cta * H * ZD + EDGE_NW * 16 +
+                                    EDGE_NW * MAXT * 8);
   }
 };
 
 template <int ZD, int WPR>
-__global__ void __launch_bounds__(EDGE_NW * 32, 2) attn_edge2_kernel(const float* __restrict__ Qg, const float* __restrict__ Qhat,
-                                                            const float* __restrict__ KV, const float* __restrict__ Z,
-                                                            const int* __restrict__ nbr, const int* __restrict__ deg,
-                                                            int stride, int n_dst, float* __restrict__ Rbar,
-                                                            float* __restrict__ AggV) {
+__global__ void __launch_bounds__(EDGE_NW * 32, 2) attn_edge3_kernel(const float* __restrict__ Qhat,
+                                                                     const float* __restrict__ Sk,
+                                                                     const float* __restrict__ Z,
+                                                                     const int* __restrict__ deg, int stride, int n_dst,
+                                                                     float* __restrict__ Rbar, float* __restrict__ Pw) {
   using C = Edge2Cfg<ZD>;
   constexpr int ZP = C::ZP, NC = C::NC, RPC = EDGE_NW / WPR, NT = EDGE_NW * 32;
   static_assert(EDGE_NW % WPR == 0, "warps per row must divide the CTA");
@@ -47,8 +53,8 @@ __global__ void __launch_bounds__(EDGE_NW * 32, 2) attn_edge2_kernel(const float
   float* sZ = smem;                               // [NW warps][32][ZP]   (reused for the partials at the end)
   float* sP = sZ + EDGE_NW * C::WARP_Z;           // [NW warps][32 edges][8 heads]
   float* sQh = sP + EDGE_NW * 32 * 8;             // [RPC][8][ZD]
-  float* sQ = sQh + RPC * H * ZD;                 // [RPC][128]
-  float* sScale = sQ + RPC * D;                   // [NW warps][16]: per-head merge scale, 1/(L+eps) folded in
+  float* sScale = sQh + RPC * H * ZD;             // [NW warps][16]: per-head merge scale, 1/(L+eps) folded in
+  float* sMt = sScale + EDGE_NW * 16;             // [NW warps][MAXT][8]: running max after each of the warp's tiles
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lrow = warp / WPR;                    // row slot of this warp inside the CTA
@@ -70,20 +76,15 @@ __global__ void __launch_bounds__(EDGE_NW * 32, 2) attn_edge2_kernel(const float
     }
     sQh[i] = v;
   }
-  for (int i = threadIdx.x; i < RPC * D; i += NT) {
-    const int grow = blockIdx.x * RPC + i / D;
-    sQ[i] = grow < n_dst ? Qg[(size_t)grow * D + (i % D)] : 0.f;
-  }
   __syncthreads();
 
   float* zt = sZ + warp * C::WARP_Z;
   float* pt = sP + warp * 32 * 8;
   const float* qh = sQh + lrow * H * ZD;
-  const float* q = sQ + lrow * D;
+  float* mt_w = sMt + warp * C::MAXT * 8;
 
   float m[H], lsum[H];           // running max (warp uniform) and this lane's share of the running sum
   float racc[H][NC];             // Rbar[h][c*32 + lane]
-  float vacc[4];                 // AggV[c*32 + lane], head = 2c + (lane >> 4)
 #pragma unroll
   for (int h = 0; h < H; ++h) {
     m[h] = -INFINITY;
@@ -91,10 +92,8 @@ __global__ void __launch_bounds__(EDGE_NW * 32, 2) attn_edge2_kernel(const float
 #pragma unroll
     for (int c = 0; c < NC; ++c) racc[h][c] = 0.f;
   }
-#pragma unroll
-  for (int c = 0; c < 4; ++c) vacc[c] = 0.f;
-
-  for (int t0 = wir * 32; t0 < n_e; t0 += WPR * 32) {
+  int tile = 0;
+  for (int t0 = wir * 32; t0 < n_e; t0 += WPR * 32, ++tile) {
     const int nt = min(32, n_e - t0);
     // ---- stage the tile: rows t0..t0+nt-1 of Z are one contiguous stream of nt*ZD floats
     {
@@ -106,26 +105,18 @@ __global__ void __launch_bounds__(EDGE_NW * 32, 2) attn_edge2_kernel(const float
       }
       cp_async_commit();
     }
-    // ---- scores, lane = edge: K' part straight from L2 while the tile lands
+    // ---- scores, lane = edge: the q.K' part was precomputed by edge_qk_kernel (32 B per edge, coalesced)
     const bool valid = lane < nt;
-    const int j = valid ? __ldg(nbr + ebase + t0 + lane) : 0;
     float s[H];
-#pragma unroll
-    for (int h = 0; h < H; ++h) s[h] = 0.f;
-    if (valid) {
-      const float4* kp = reinterpret_cast<const float4*>(KV + (size_t)j * 256);
-#pragma unroll
-      for (int h = 0; h < H; ++h) {
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          const float4 k4 = __ldg(kp + h * 4 + c4);
-          const float4 q4 = reinterpret_cast<const float4*>(q)[h * 4 + c4];
-          s[h] = fmaf(q4.x, k4.x, s[h]);
-          s[h] = fmaf(q4.y, k4.y, s[h]);
-          s[h] = fmaf(q4.z, k4.z, s[h]);
-          s[h] = fmaf(q4.w, k4.w, s[h]);
-        }
+    {
+      float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+      if (valid) {
+        const float4* sp = reinterpret_cast<const float4*>(Sk + (ebase + t0 + lane) * 8);
+        s0 = __ldg(sp);
+        s1 = __ldg(sp + 1);
       }
+      s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w;
+      s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
     }
     cp_async_wait<0>();
     __syncwarp();
@@ -156,47 +147,33 @@ __global__ void __launch_bounds__(EDGE_NW * 32, 2) attn_edge2_kernel(const float
       m[h] = mn;
 #pragma unroll
       for (int c = 0; c < NC; ++c) racc[h][c] *= corr;
-      s[h] = corr;                                            // keep for the AggV rescale below
     }
+    if (tile < C::MAXT) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) vacc[c] *= (lane >> 4) ? s[2 * c + 1] : s[2 * c];
+      for (int h = 0; h < H; ++h)
+        if (lane == h) mt_w[tile * 8 + h] = m[h];
+    }
     *reinterpret_cast<float4*>(pt + lane * 8) = make_float4(p[0], p[1], p[2], p[3]);
     *reinterpret_cast<float4*>(pt + lane * 8 + 4) = make_float4(p[4], p[5], p[6], p[7]);
     __syncwarp();
     // ---- aggregation, lane = feature column, edges of the tile in ascending order
-    // V' rows come from L2 (~600 cycles): fetch them EB edges ahead of their use so the loads of a whole group
-    // are in flight together; edges past the tile end are clamped and get weight 0.
-    constexpr int EB = 4;
-    for (int e0 = 0; e0 < nt; e0 += EB) {
-      float vv[EB][4];
+    for (int e = 0; e < nt; ++e) {
+      const float4 pa = *reinterpret_cast<const float4*>(pt + e * 8);
+      const float4 pb = *reinterpret_cast<const float4*>(pt + e * 8 + 4);
+      const float pe[H] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+      const float* zr = zt + e * ZP + lane;
 #pragma unroll
-      for (int u = 0; u < EB; ++u) {
-        const int je = __shfl_sync(0xffffffffu, j, min(e0 + u, nt - 1));
-        const float* vp = KV + (size_t)je * 256 + 128 + lane;
+      for (int c = 0; c < NC; ++c) {
+        const float zv = zr[c * 32];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) vv[u][c] = __ldg(vp + c * 32);
+        for (int h = 0; h < H; ++h) racc[h][c] = fmaf(pe[h], zv, racc[h][c]);
       }
-#pragma unroll
-      for (int u = 0; u < EB; ++u) {
-        const int e = e0 + u;
-        if (e < nt) {
-          const float4 pa = *reinterpret_cast<const float4*>(pt + e * 8);
-          const float4 pb = *reinterpret_cast<const float4*>(pt + e * 8 + 4);
-          const float pe[H] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
-          const float* zr = zt + e * ZP + lane;
-#pragma unroll
-          for (int c = 0; c < NC; ++c) {
-            const float zv = zr[c * 32];
-#pragma unroll
-            for (int h = 0; h < H; ++h) racc[h][c] = fmaf(pe[h], zv, racc[h][c]);
-          }
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float pv = (lane >> 4) ? pe[2 * c + 1] : pe[2 * c];
-            vacc[c] = fmaf(pv, vv[u][c], vacc[c]);
-          }
-        }
-      }
+    }
+    // unnormalised weights of this tile (relative to the running max stored in mt_w), rescaled at the end
+    if (valid) {
+      float4* pw = reinterpret_cast<float4*>(Pw + (ebase + t0 + lane) * 8);
+      pw[0] = make_float4(p[0], p[1], p[2], p[3]);
+      pw[1] = make_float4(p[4], p[5], p[6], p[7]);
     }
     __syncwarp();   // the tile buffer and pt are rewritten by the next iteration
   }
@@ -212,8 +189,6 @@ __global__ void __launch_bounds__(EDGE_NW * 32, 2) attn_edge2_kernel(const float
 #pragma unroll
     for (int c = 0; c < NC; ++c) zt[16 + h * ZD + c * 32 + lane] = racc[h][c];
   }
-#pragma unroll
-  for (int c = 0; c < 4; ++c) zt[16 + H * ZD + c * 32 + lane] = vacc[c];
   __syncthreads();
   // merge scales: scale[w][h] = exp(m_w - M) / (sum_w exp(m_w - M) l_w + 1e-16); first warp of each row computes them
   if (wir == 0 && lane < H) {
@@ -233,15 +208,98 @@ __global__ void __launch_bounds__(EDGE_NW * 32, 2) attn_edge2_kernel(const float
   if (row_ok) {
     const float* base = sZ + (lrow * WPR) * C::WARP_Z + 16;
     const float* scl = sScale + (lrow * WPR) * 16;
-    for (int o = wir * 32 + lane; o < H * ZD + D; o += WPR * 32) {
-      const int h = o < H * ZD ? o / ZD : (o - H * ZD) >> 4;
+    for (int o = wir * 32 + lane; o < H * ZD; o += WPR * 32) {
+      const int h = o / ZD;
       float t = 0.f;
 #pragma unroll
       for (int w = 0; w < WPR; ++w) t = fmaf(scl[w * 16 + h], base[w * C::WARP_Z + o], t);
-      if (o < H * ZD) Rbar[(size_t)row * H * ZD + o] = t;
-      else AggV[(size_t)row * D + (o - H * ZD)] = t;
+      Rbar[(size_t)row * H * ZD + o] = t;
+    }
+    // final attention weights: a_e = p_e * exp(m_tile - M) / (L + 1e-16) = p_e * exp(m_tile - m_warp) * scale_warp
+    const float* myscale = sScale + warp * 16;
+    tile = 0;
+    for (int t0 = wir * 32; t0 < n_e; t0 += WPR * 32, ++tile) {
+      if (t0 + lane < n_e) {
+        float4* pw = reinterpret_cast<float4*>(Pw + (ebase + t0 + lane) * 8);
+        float4 a = pw[0], b = pw[1];
+        const float* mtt = mt_w + (tile < C::MAXT ? tile : C::MAXT - 1) * 8;
+        float f[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) f[h] = expf(mtt[h] - m[h]) * myscale[h];
+        a.x *= f[0]; a.y *= f[1]; a.z *= f[2]; a.w *= f[3];
+        b.x *= f[4]; b.y *= f[5]; b.z *= f[6]; b.w *= f[7];
+        pw[0] = a;
+        pw[1] = b;
+      }
     }
   }
+}
+
+// ---- gather kernels: a warp per destination row, lane = 4 of the 128 columns, EB edges in flight per lane
+constexpr int GATHER_EB = 8;
+
+// Sk[row*stride + e][h] = sum_c q[row][h*16+c] * K'[nbr[e]][h*16+c]
+__global__ void __launch_bounds__(256) edge_qk_kernel(const float* __restrict__ Qg, const float* __restrict__ KV,
+                                                      const int* __restrict__ nbr, const int* __restrict__ deg, int stride,
+                                                      int n_dst, float* __restrict__ Sk) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n_dst) return;
+  const int n_e = min(deg[row], stride);
+  const size_t ebase = (size_t)row * stride;
+  const float4 q4 = __ldg(reinterpret_cast<const float4*>(Qg + (size_t)row * D) + lane);
+  for (int e0 = 0; e0 < n_e; e0 += 32) {
+    const int jl = e0 + lane < n_e ? __ldg(nbr + ebase + e0 + lane) : 0;
+    const int nt = min(32, n_e - e0);
+    for (int g = 0; g < nt; g += GATHER_EB) {
+      float4 k4[GATHER_EB];
+#pragma unroll
+      for (int u = 0; u < GATHER_EB; ++u) {
+        const int j = __shfl_sync(0xffffffffu, jl, min(g + u, nt - 1));
+        k4[u] = __ldg(reinterpret_cast<const float4*>(KV + (size_t)j * 256) + lane);
+      }
+#pragma unroll
+      for (int u = 0; u < GATHER_EB; ++u) {
+        float d = fmaf(q4.w, k4[u].w, fmaf(q4.z, k4[u].z, fmaf(q4.y, k4[u].y, q4.x * k4[u].x)));
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        if ((lane & 3) == 0 && g + u < nt) Sk[(ebase + e0 + g + u) * 8 + (lane >> 2)] = d;
+      }
+    }
+  }
+}
+
+// AggV[row][c] = sum_e a[e][c/16] * V'[nbr[e]][c]   (edges in ascending order)
+__global__ void __launch_bounds__(256) edge_av_kernel(const float* __restrict__ Pw, const float* __restrict__ KV,
+                                                      const int* __restrict__ nbr, const int* __restrict__ deg, int stride,
+                                                      int n_dst, float* __restrict__ AggV) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n_dst) return;
+  const int n_e = min(deg[row], stride);
+  const size_t ebase = (size_t)row * stride;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int e0 = 0; e0 < n_e; e0 += 32) {
+    const int jl = e0 + lane < n_e ? __ldg(nbr + ebase + e0 + lane) : 0;
+    const int nt = min(32, n_e - e0);
+    for (int g = 0; g < nt; g += GATHER_EB) {
+      float4 v4[GATHER_EB];
+      float a[GATHER_EB];
+#pragma unroll
+      for (int u = 0; u < GATHER_EB; ++u) {
+        const int eu = min(g + u, nt - 1);
+        const int j = __shfl_sync(0xffffffffu, jl, eu);
+        v4[u] = __ldg(reinterpret_cast<const float4*>(KV + (size_t)j * 256 + 128) + lane);
+        a[u] = g + u < nt ? __ldg(Pw + (ebase + e0 + eu) * 8 + (lane >> 2)) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < GATHER_EB; ++u) {
+        acc.x = fmaf(a[u], v4[u].x, acc.x);
+        acc.y = fmaf(a[u], v4[u].y, acc.y);
+        acc.z = fmaf(a[u], v4[u].z, acc.z);
+        acc.w = fmaf(a[u], v4[u].w, acc.w);
+      }
+    }
+  }
+  *reinterpret_cast<float4*>(AggV + (size_t)row * D + 4 * lane) = acc;
 }
 
 }  // namespace prosim

@@ -8,7 +8,7 @@ from ctypes import POINTER, Structure, c_float, c_int, c_int32, c_size_t, c_void
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libprosim_b200.so')
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 SYMBOLS = (
     'prosim_abi_version', 'prosim_attn_layer_floats', 'prosim_pointnet_floats', 'prosim_head_floats',
@@ -19,7 +19,7 @@ SYMBOLS = (
 )
 
 KERNEL_CLASSES = {'pointnet': 0, 'radius': 1, 'knn': 2, 'edge_pe': 3, 'attn_kv': 4, 'attn_dstpre': 5, 'attn_edge': 6,
-                  'attn_post': 7, 'head': 8, 'mlp2': 9, 'state': 10}
+                  'attn_post': 7, 'head': 8, 'mlp2': 9, 'state': 10, 'edge_qk': 11, 'edge_av': 12}
 
 
 class Graph(Structure):
@@ -79,7 +79,7 @@ def load():
     lib.prosim_profile_read.restype = c_int
     lib.prosim_profile_read.argtypes = [POINTER(ctypes.c_double), POINTER(c_int)]
     lib.prosim_attn_workspace_floats.restype = c_size_t
-    lib.prosim_attn_workspace_floats.argtypes = [c_int, c_int]
+    lib.prosim_attn_workspace_floats.argtypes = [c_int, c_int, c_int]
     for name, sig in _SIGS.items():
         fn = getattr(lib, name)
         fn.restype = c_int

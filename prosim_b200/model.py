@@ -14,6 +14,8 @@ Device data layout (all fp32 / int32, allocated once per batch shape):
   K'|V'       [layers][rows][256]; the map side of the policy is computed once per scene and reused
               by every tick (the reference recomputes it 8 times)
 """
+from collections.abc import Mapping
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -30,6 +32,52 @@ D = 128
 class _Plan:
     """Integer bookkeeping of one batch, built once on the host and uploaded in a single copy."""
     pass
+
+
+class _RolloutTrajs(Mapping):
+    """``rollout_trajs`` of the reference (traj_sam.py:582-593): {"b-id": {traj [steps,4], init_pos [2], init_heading [1],
+    vel [steps,2]}} as views of the state buffers.  The per-agent views are created on first access (all of them with four
+    ``unbind`` calls when iterated) instead of 8 Python indexing ops per agent per forward -- 35 ms at 4096 agents."""
+
+    def __init__(self, names, rows, st):
+        self._names, self._rows, self._st = names, [int(r) for r in rows], st
+        self._index = None
+        self._all = None
+
+    def _materialise(self):
+        if self._all is None:
+            st = self._st
+            T = st['traj'].shape[2]
+            traj = st['traj'].view(-1, T, 4)[:, HIST:].unbind(0)
+            vel = st['vel'].view(-1, T, 2)[:, HIST:].unbind(0)
+            pos = st['init_pos'].view(-1, 2).unbind(0)
+            head = st['init_heading'].view(-1, 1).unbind(0)
+            self._all = {n: {'traj': traj[r], 'init_pos': pos[r], 'init_heading': head[r], 'vel': vel[r]}
+                         for n, r in zip(self._names, self._rows)}
+        return self._all
+
+    def __getitem__(self, name):
+        if self._all is not None:
+            return self._all[name]
+        if self._index is None:
+            self._index = {n: r for n, r in zip(self._names, self._rows)}
+        r = self._index[name]
+        st = self._st
+        T = st['traj'].shape[2]
+        return {'traj': st['traj'].view(-1, T, 4)[r, HIST:], 'init_pos': st['init_pos'].view(-1, 2)[r],
+                'init_heading': st['init_heading'].view(-1, 1)[r], 'vel': st['vel'].view(-1, T, 2)[r, HIST:]}
+
+    def __iter__(self):
+        return iter(self._names)
+
+    def __len__(self):
+        return len(self._names)
+
+    def items(self):
+        return self._materialise().items()
+
+    def values(self):
+        return self._materialise().values()
 
 
 def _pad4(a):
@@ -242,14 +290,16 @@ class ProSimB200(nn.Module):
                             min(k_s, max(pl.max_tok, 1)))
         ops.edge_pe(e_a, a_pos, a_ori, a_pos, a_ori, dim_t, z=self._buf('z_enc_a', (NA * e_a.stride, 96)))
         ops.edge_pe(e_s, tok_pos, tok_ori, tok_pos, tok_ori, dim_t, z=self._buf('z_enc_s', (S * e_s.stride, 96)))
-        ws = self._buf('attn_ws', (lib.load().prosim_attn_workspace_floats(S, S),))
+        ws = self._buf('attn_ws', (lib.load().prosim_attn_workspace_floats(S, S, max(e_a.stride, e_s.stride)),))
         lf = weights.ATTN_LAYER_FLOATS
         xa = tok[NM:]
         for i in range(self.num_layers):
             ops.attn_layer(xa, xa, e_a, ar, off['enc_a2a'] + i * lf, out=xa, workspace=ws)
             ops.attn_layer(tok, tok, e_s, ar, off['enc_s2s'] + i * lf, out=tok, workspace=ws)
-        sb = torch.from_numpy(pl.scene_batch_idx_host).to(self._device, non_blocking=True)
-        st = torch.cat([torch.zeros(NM, dtype=torch.long), torch.ones(NA, dtype=torch.long)]).to(self._device)
+        # built from the already-uploaded index arrays: no pageable H2D copy (it would stall the host behind the encoder)
+        sb = pl.i['tok_scene'].long()
+        st = torch.cat([torch.zeros(NM, dtype=torch.long, device=self._device),
+                        torch.ones(NA, dtype=torch.long, device=self._device)])
         pl.edges_enc = (e_a, e_s)
         return {'obs_mask': obs['mask'].all(-1).any(-1), 'map_mask': mp['mask'].any(-1), 'scene_batch_idx': sb,
                 'scene_type': st, 'scene_pos': tok_pos, 'scene_ori': tok_ori.view(-1, 1), 'scene_tokens': tok,
@@ -296,7 +346,7 @@ class ProSimB200(nn.Module):
             ops.edge_pe(e_pp, p_pos, p_ori, p_pos, p_ori, dim_t, z=self._buf('z_pp', (P * e_pp.stride, 96)))
             ops.edge_pe(e_sp, p_pos, p_ori, tok_pos, tok_ori, dim_t, z=self._buf('z_sp', (P * e_sp.stride, 96)))
             kv_s = ops.attn_kv(tok, ar, off['dec_s2p'], self.num_layers, lf, kv=self._buf('kv_dec', (self.num_layers, S, 2 * D)))
-            ws = self._buf('attn_ws', (lib.load().prosim_attn_workspace_floats(max(P, S), max(P, S)),))
+            ws = self._buf('attn_ws', (lib.load().prosim_attn_workspace_floats(P, P, max(e_pp.stride, e_sp.stride)),))
             emd_flat = ops.attn_stack(x_p, self.num_layers, ops.stack_side(ar, off['dec_p2p'], e_pp),
                                       ops.stack_side(ar, off['dec_s2p'], e_sp, kv_s), workspace=ws)
             pl.edges_gen = (e_pp, e_sp)
@@ -390,7 +440,7 @@ class ProSimB200(nn.Module):
         a_pos_buf, a_ori_buf = self._buf('a_pos', (max_na, 2)), self._buf('a_ori', (max_na,))
         p_pos, p_ori = self._buf('p_pos', (P, 2)), self._buf('p_ori', (P,))
         fuse = self._buf('fuse', (P, D))
-        ws = self._buf('attn_ws', (lib.load().prosim_attn_workspace_floats(P, 0),))
+        ws = self._buf('attn_ws', (lib.load().prosim_attn_workspace_floats(P, 0, max(stride_a, stride_m)),))
         motion_pred = torch.empty(n_ticks, P, 1, STEP, 5, device=self._device)
         tidx = int(st['last_step'])
         pl.tick_edges = []
@@ -440,12 +490,6 @@ class ProSimB200(nn.Module):
         for t in all_t:
             names += [f'{n}-{t}' for n in agent_names]
         res['pair_names'] = names
-        traj, vel = st['traj'][:, :, HIST:], st['vel'][:, :, HIST:]
-        rt = {}
-        for k, name in enumerate(agent_names):
-            b, n = int(pl.p_b[k]), int(pl.p_n[k])
-            rt[name] = {'traj': traj[b, n], 'init_pos': st['init_pos'][b, n], 'init_heading': st['init_heading'][b, n],
-                        'vel': vel[b, n]}
-        res['rollout_trajs'] = rt
+        res['rollout_trajs'] = _RolloutTrajs(agent_names, pl.p_b * pl.N + pl.p_n, st)
         res['_state'] = st
         return {task: res}

@@ -118,8 +118,8 @@ def attn_kv(x_src, w_arena, w_off, n_layers, layer_floats, kv=None):
     return kv
 
 
-def attn_workspace(n_dst, n_src, device):
-    n = lib.load().prosim_attn_workspace_floats(int(n_dst), int(n_src))
+def attn_workspace(n_dst, n_src, device, max_stride=768):
+    n = lib.load().prosim_attn_workspace_floats(int(n_dst), int(n_src), int(max_stride))
     return torch.empty(n, device=device, dtype=torch.float32)
 
 
@@ -127,7 +127,7 @@ def attn_layer(x_src, x_dst, edges, w_arena, w_off, out=None, workspace=None):
     _chk(x_src, torch.float32, 'x_src'), _chk(x_dst, torch.float32, 'x_dst')
     n_src, n_dst = x_src.shape[0], x_dst.shape[0]
     if workspace is None:
-        workspace = attn_workspace(n_dst, n_src, x_dst.device)
+        workspace = attn_workspace(n_dst, n_src, x_dst.device, edges.stride)
     if out is None:
         out = torch.empty_like(x_dst)
     g = edges.c_struct()
@@ -146,7 +146,7 @@ def attn_stack(x, n_layers, side_a, side_b=None, out=None, workspace=None):
     _chk(x, torch.float32, 'x')
     n = x.shape[0]
     if workspace is None:
-        workspace = attn_workspace(n, n, x.device)
+        workspace = attn_workspace(n, n, x.device, max(side_a.graph.stride, side_b.graph.stride if side_b is not None else 1))
     if out is None:
         out = torch.empty_like(x)
     lib.call('prosim_attn_stack_fwd', ptr(x), n, int(n_layers), ctypes.byref(side_a),

@@ -29,7 +29,7 @@ def test_library_layout_matches_packer():
     assert l.prosim_pointnet_floats() == weights.POINTNET_FLOATS
     assert l.prosim_head_floats() == weights.HEAD_FLOATS
     assert l.prosim_mlp2_floats() == weights.MLP2_FLOATS
-    assert l.prosim_attn_workspace_floats(10, 0) >= 10 * (2 * (128 + 1024 + 256) + 1024 + 128 + 256)
+    assert l.prosim_attn_workspace_floats(10, 0, 32) >= 10 * (2 * (128 + 1024 + 256) + 1024 + 128 + 256 + 16 * 32)
 
 
 def test_pack_model_sections():

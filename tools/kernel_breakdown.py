@@ -40,3 +40,25 @@ with torch.no_grad():
     lib.profile_enable(None)
 out['sum_ms'] = round(sum(v['ms'] for k, v in out.items() if isinstance(v, dict)), 3)
 print(json.dumps(out))
+
+# host-side cost of the per-batch bookkeeping (index maps, one mask D2H, one index H2D)
+import time  # noqa: E402
+ts = []
+for _ in range(5):
+    b = synthetic.clone_batch(pristine)[0]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    model._plan(b)
+    torch.cuda.synchronize()
+    ts.append((time.perf_counter() - t0) * 1e3)
+print(json.dumps({'plan_ms': [round(t, 2) for t in ts]}))
+with torch.no_grad():
+    b = synthetic.clone_batch(pristine)[0]
+    model._plan(b)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    model.forward(b, 'val')
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+print(json.dumps({'forward_host_enqueue_ms': round((t1 - t0) * 1e3, 2), 'forward_total_ms': round((t2 - t0) * 1e3, 2)}))
