@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) attn_kv2_kernel(const float* __restrict__
     }
     *reinterpret_cast<float4*>(xs + r * LDS_PAD + 4 * lane) = v;
   }
-  float acc[RT][8];
+  float acc[2 * RT][4];
   acc2_init_bias<RT>(acc, W + aw::KB);
   gemm2<RT>(acc, xs, LDS_PAD, D, W + aw::WKT, D, p, W + aw::WVT, D, D);
   acc2_store_global<RT>(acc, kv, 256, 0, row0, N);
@@ -50,7 +50,7 @@ template <int RT>
 __device__ __forceinline__ void attn_dst_pre2(const float* xd, float* sq, const float* __restrict__ W, int row0, int N,
                                               float* __restrict__ Qg, float* __restrict__ Qhat, float* __restrict__ Sg,
                                               float* __restrict__ Gxg, WPipe& p) {
-  float acc[RT][8];
+  float acc[2 * RT][4];
   acc2_init_bias<RT>(acc, W + aw::BQ);
   gemm2<RT>(acc, xd, LDS_PAD, D, W + aw::WQT, D, p, W + aw::WST, D, D);
   acc2_store_smem<RT>(acc, sq, LDS_PAD, false);
@@ -123,7 +123,6 @@ __global__ void __launch_bounds__(256, 1) attn_post2_kernel(const float* __restr
   float* sA = sR + M * SM::LDR;
   float* sB = sA + M * LDS_PAD;
   const int row0 = blockIdx.x * M;
-  const int tx = threadIdx.x & 15;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // the first weight chunk flies while the Rbar tile is loaded
@@ -139,26 +138,26 @@ __global__ void __launch_bounds__(256, 1) attn_post2_kernel(const float* __restr
     *reinterpret_cast<float4*>(sR + r * ldr + c) = v;
   }
 
-  float acc[RT][8], agg[RT][8];
+  float acc[2 * RT][4], agg[2 * RT][4];
   // 1. agg = AggV + Wvr' Rbar (block diagonal: the A row of an output column is the Rbar row of its head)
   acc2_load_global<RT>(acc, AggV, D, row0, N);
-  gemm_tile2<RT, true>(acc, sR + (tx >> 2) * zd, sR + (4 + (tx >> 2)) * zd, ldr, zd, Wvr, D, p, W + aw::WGAT, D, D);
+  gemm_tile2<RT>(acc, sR + (tile_coord<RT>().col >> 4) * zd, ldr, zd, Wvr, D, p, W + aw::WGAT, D, D);
   acc2_store_smem<RT>(acc, sA, LDS_PAD, false);
 #pragma unroll
-  for (int r = 0; r < RT; ++r)
+  for (int r = 0; r < 2 * RT; ++r)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) agg[r][c] = acc[r][c];
+    for (int c = 0; c < 4; ++c) agg[r][c] = acc[r][c];
 
   // 2. gate: g = sigmoid(Wga agg + Gx) ; u = agg + g (S - agg)
   acc2_load_global<RT>(acc, Gxg, D, row0, N);
   gemm2<RT>(acc, sA, LDS_PAD, D, W + aw::WGAT, D, p, W + aw::WOT, D, D);
   {
-    float s[RT][8];
+    float s[2 * RT][4];
     acc2_load_global<RT>(s, Sg, D, row0, N);
 #pragma unroll
-    for (int r = 0; r < RT; ++r)
+    for (int r = 0; r < 2 * RT; ++r)
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         const float g = 1.0f / (1.0f + expf(-acc[r][c]));
         acc[r][c] = agg[r][c] + g * (s[r][c] - agg[r][c]);
       }

@@ -2,8 +2,10 @@
 //
 //   acc[r][c] += sum_k A[row(r)][k] * Wt[k][col(c)]      M = 16*RT rows per CTA, N = 128 columns
 //
-// 256 threads as a 16 x 16 grid: tx = tid & 15 owns columns {4tx..4tx+3} and {64+4tx..64+4tx+3},
-// ty = tid >> 4 owns rows {ty*RT .. ty*RT+RT-1}  ->  RT x 8 fp32 accumulators per thread.
+// 8 warps as 4 row groups x 2 column halves; inside a warp tx = lane & 15 owns 4 columns, ty = lane >> 4 owns
+// TR = 2*RT rows: a warp covers 4*RT rows x 64 columns, a thread keeps TR x 4 fp32 accumulators.  (A first
+// layout gave every warp all 128 columns of 2*RT rows; ncu showed it shared-memory bound -- 82 % of the
+// LDS bandwidth at 31 % FMA -- because each warp re-read the whole weight row for only 16 FMAs.)
 //   * A (activations) lives in shared memory, row-major with a padded stride; reads are LDS.128 with
 //     two distinct addresses per warp (broadcast).
 //   * Wt (K-major weights, n contiguous) is streamed from L2 in chunks of KC = 32 k-rows (16 KB) through a
@@ -11,7 +13,8 @@
 //     16*RT rows, instead of once per thread row-group as in gemm_tile_acc (v1).  The ring keeps running
 //     across consecutive GEMMs of a fused kernel: the last iteration of one GEMM already prefetches the first
 //     chunk of the next (WPipe::primed), so a chain of small GEMMs has no pipeline bubbles.
-//   * B reads are conflict-free LDS.128 (16 lanes x 16 B contiguous), one __syncthreads per chunk.
+//   * B reads are conflict-free LDS.128 (16 lanes x 16 B contiguous: 2 wavefronts per k feed 8*RT FMA instructions
+//     of the warp), one __syncthreads per chunk.
 // Accumulation over k is in ascending order for every output: deterministic and batch invariant.
 #pragma once
 #include "common.cuh"
@@ -47,37 +50,48 @@ __device__ __forceinline__ void wpipe_issue(float* stage, const float* __restric
   }
 }
 
+// thread -> tile coordinates
+struct TileCoord {
+  int row;   // first row of this thread inside the CTA tile
+  int col;   // first of its 4 columns
+};
 template <int RT>
-__device__ __forceinline__ void acc2_init(float (&acc)[RT][8], float v) {
+__device__ __forceinline__ TileCoord tile_coord() {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  TileCoord t;
+  t.row = (warp >> 1) * (4 * RT) + (lane >> 4) * (2 * RT);
+  t.col = (warp & 1) * 64 + (lane & 15) * 4;
+  return t;
+}
+
+template <int RT>
+__device__ __forceinline__ void acc2_init(float (&acc)[2 * RT][4], float v) {
 #pragma unroll
-  for (int r = 0; r < RT; ++r)
+  for (int r = 0; r < 2 * RT; ++r)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[r][c] = v;
+    for (int c = 0; c < 4; ++c) acc[r][c] = v;
 }
 
 // bias (or any per-column vector) into every row's accumulators
 template <int RT>
-__device__ __forceinline__ void acc2_init_bias(float (&acc)[RT][8], const float* __restrict__ bias) {
-  const int tx = threadIdx.x & 15;
-  const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + 4 * tx));
-  const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + 64 + 4 * tx));
+__device__ __forceinline__ void acc2_init_bias(float (&acc)[2 * RT][4], const float* __restrict__ bias) {
+  const float4 b = __ldg(reinterpret_cast<const float4*>(bias + tile_coord<RT>().col));
 #pragma unroll
-  for (int r = 0; r < RT; ++r) {
-    acc[r][0] = b0.x; acc[r][1] = b0.y; acc[r][2] = b0.z; acc[r][3] = b0.w;
-    acc[r][4] = b1.x; acc[r][5] = b1.y; acc[r][6] = b1.z; acc[r][7] = b1.w;
+  for (int r = 0; r < 2 * RT; ++r) {
+    acc[r][0] = b.x; acc[r][1] = b.y; acc[r][2] = b.z; acc[r][3] = b.w;
   }
 }
 
-// A0 feeds columns 0..63 of this thread, A1 columns 64..127 (normally A0 == A1; they differ only for the
-// block-diagonal Wvr' contraction where the A row depends on the output head).
+// All four columns of a thread lie inside one attention head, so the block-diagonal Wvr' contraction is the same
+// routine with a per-thread A base (attn2.cuh).
 // next_Wt != nullptr: prefetch chunk 0 of the next GEMM (next_K rows, clipped to KC) while finishing this one.
-template <int RT, bool TWO_A>
-__device__ __forceinline__ void gemm_tile2(float (&acc)[RT][8], const float* A0, const float* A1, int lda, int K,
+template <int RT>
+__device__ __forceinline__ void gemm_tile2(float (&acc)[2 * RT][4], const float* A, int lda, int K,
                                            const float* __restrict__ Wt, int ldw, WPipe& p,
                                            const float* __restrict__ next_Wt, int next_ldw, int next_K) {
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const float* a0 = A0 + ty * RT * lda;
-  const float* a1 = A1 + ty * RT * lda;
+  constexpr int TR = 2 * RT;
+  const TileCoord tc = tile_coord<RT>();
+  const float* a0 = A + tc.row * lda;
   const int nch = (K + KC - 1) / KC;
   if (!p.primed) {
     wpipe_issue(p.buf + p.st * WCHUNK_FLOATS, Wt, ldw, 0, min(KC, K));
@@ -90,33 +104,24 @@ __device__ __forceinline__ void gemm_tile2(float (&acc)[RT][8], const float* A0,
     cp_async_commit();
     cp_async_wait<1>();
     __syncthreads();
-    const float* Bs = p.buf + p.st * WCHUNK_FLOATS;
+    const float* Bs = p.buf + p.st * WCHUNK_FLOATS + tc.col;
     const int kc = min(KC, K - c * KC);
     const int kbase = c * KC;
 #pragma unroll 2
     for (int kk = 0; kk < kc; kk += 4) {
-      float4 av0[RT], av1[RT];
+      float4 av[TR];
 #pragma unroll
-      for (int r = 0; r < RT; ++r) {
-        av0[r] = *reinterpret_cast<const float4*>(a0 + r * lda + kbase + kk);
-        if (TWO_A) av1[r] = *reinterpret_cast<const float4*>(a1 + r * lda + kbase + kk);
-      }
+      for (int r = 0; r < TR; ++r) av[r] = *reinterpret_cast<const float4*>(a0 + r * lda + kbase + kk);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float4 b0 = *reinterpret_cast<const float4*>(Bs + (kk + j) * 128 + 4 * tx);
-        const float4 b1 = *reinterpret_cast<const float4*>(Bs + (kk + j) * 128 + 64 + 4 * tx);
+        const float4 b = *reinterpret_cast<const float4*>(Bs + (kk + j) * 128);
 #pragma unroll
-        for (int r = 0; r < RT; ++r) {
-          const float x0 = j == 0 ? av0[r].x : j == 1 ? av0[r].y : j == 2 ? av0[r].z : av0[r].w;
-          const float x1 = !TWO_A ? x0 : (j == 0 ? av1[r].x : j == 1 ? av1[r].y : j == 2 ? av1[r].z : av1[r].w);
-          acc[r][0] = fmaf(x0, b0.x, acc[r][0]);
-          acc[r][1] = fmaf(x0, b0.y, acc[r][1]);
-          acc[r][2] = fmaf(x0, b0.z, acc[r][2]);
-          acc[r][3] = fmaf(x0, b0.w, acc[r][3]);
-          acc[r][4] = fmaf(x1, b1.x, acc[r][4]);
-          acc[r][5] = fmaf(x1, b1.y, acc[r][5]);
-          acc[r][6] = fmaf(x1, b1.z, acc[r][6]);
-          acc[r][7] = fmaf(x1, b1.w, acc[r][7]);
+        for (int r = 0; r < TR; ++r) {
+          const float x = j == 0 ? av[r].x : j == 1 ? av[r].y : j == 2 ? av[r].z : av[r].w;
+          acc[r][0] = fmaf(x, b.x, acc[r][0]);
+          acc[r][1] = fmaf(x, b.y, acc[r][1]);
+          acc[r][2] = fmaf(x, b.z, acc[r][2]);
+          acc[r][3] = fmaf(x, b.w, acc[r][3]);
         }
       }
     }
@@ -125,63 +130,51 @@ __device__ __forceinline__ void gemm_tile2(float (&acc)[RT][8], const float* A0,
   p.primed = next_Wt != nullptr;
 }
 
-// convenience wrapper for the common single-A case
+// convenience wrapper with default "no prefetch" arguments
 template <int RT>
-__device__ __forceinline__ void gemm2(float (&acc)[RT][8], const float* A, int lda, int K, const float* __restrict__ Wt,
+__device__ __forceinline__ void gemm2(float (&acc)[2 * RT][4], const float* A, int lda, int K, const float* __restrict__ Wt,
                                       int ldw, WPipe& p, const float* __restrict__ next_Wt = nullptr, int next_ldw = 128,
                                       int next_K = KC) {
-  gemm_tile2<RT, false>(acc, A, A, lda, K, Wt, ldw, p, next_Wt, next_ldw, next_K);
+  gemm_tile2<RT>(acc, A, lda, K, Wt, ldw, p, next_Wt, next_ldw, next_K);
 }
 
-// ---- epilogue helpers for the (tx, ty) accumulator layout
+// ---- epilogue helpers for the accumulator layout
 template <int RT>
-__device__ __forceinline__ void acc2_store_smem(const float (&acc)[RT][8], float* dst, int ld, bool relu) {
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+__device__ __forceinline__ void acc2_store_smem(const float (&acc)[2 * RT][4], float* dst, int ld, bool relu) {
+  const TileCoord tc = tile_coord<RT>();
 #pragma unroll
-  for (int r = 0; r < RT; ++r) {
-    float4 v0 = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-    float4 v1 = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
-    if (relu) {
-      v0 = make_float4(fmaxf(v0.x, 0.f), fmaxf(v0.y, 0.f), fmaxf(v0.z, 0.f), fmaxf(v0.w, 0.f));
-      v1 = make_float4(fmaxf(v1.x, 0.f), fmaxf(v1.y, 0.f), fmaxf(v1.z, 0.f), fmaxf(v1.w, 0.f));
-    }
-    float* d = dst + (ty * RT + r) * ld;
-    *reinterpret_cast<float4*>(d + 4 * tx) = v0;
-    *reinterpret_cast<float4*>(d + 64 + 4 * tx) = v1;
+  for (int r = 0; r < 2 * RT; ++r) {
+    float4 v = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    if (relu) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+    *reinterpret_cast<float4*>(dst + (tc.row + r) * ld + tc.col) = v;
   }
 }
 
-// rows row0 + ty*RT + r < N are written; dst row stride ldg floats, column offset col0
+// rows row0 + r < N are written; dst row stride ldg floats, column offset col0
 template <int RT>
-__device__ __forceinline__ void acc2_store_global(const float (&acc)[RT][8], float* __restrict__ dst, size_t ldg,
+__device__ __forceinline__ void acc2_store_global(const float (&acc)[2 * RT][4], float* __restrict__ dst, size_t ldg,
                                                   int col0, int row0, int N) {
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const TileCoord tc = tile_coord<RT>();
 #pragma unroll
-  for (int r = 0; r < RT; ++r) {
-    const int row = row0 + ty * RT + r;
-    if (row < N) {
-      float* d = dst + (size_t)row * ldg + col0;
-      *reinterpret_cast<float4*>(d + 4 * tx) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-      *reinterpret_cast<float4*>(d + 64 + 4 * tx) = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
-    }
+  for (int r = 0; r < 2 * RT; ++r) {
+    const int row = row0 + tc.row + r;
+    if (row < N)
+      *reinterpret_cast<float4*>(dst + (size_t)row * ldg + col0 + tc.col) =
+          make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
   }
 }
 
 // acc[r][c] = src[row][col(c)] for valid rows, 0 otherwise
 template <int RT>
-__device__ __forceinline__ void acc2_load_global(float (&acc)[RT][8], const float* __restrict__ src, size_t ldg, int row0,
-                                                 int N) {
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+__device__ __forceinline__ void acc2_load_global(float (&acc)[2 * RT][4], const float* __restrict__ src, size_t ldg,
+                                                 int row0, int N) {
+  const TileCoord tc = tile_coord<RT>();
 #pragma unroll
-  for (int r = 0; r < RT; ++r) {
-    const int row = row0 + ty * RT + r;
-    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-    if (row < N) {
-      v0 = *reinterpret_cast<const float4*>(src + (size_t)row * ldg + 4 * tx);
-      v1 = *reinterpret_cast<const float4*>(src + (size_t)row * ldg + 64 + 4 * tx);
-    }
-    acc[r][0] = v0.x; acc[r][1] = v0.y; acc[r][2] = v0.z; acc[r][3] = v0.w;
-    acc[r][4] = v1.x; acc[r][5] = v1.y; acc[r][6] = v1.z; acc[r][7] = v1.w;
+  for (int r = 0; r < 2 * RT; ++r) {
+    const int row = row0 + tc.row + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < N) v = *reinterpret_cast<const float4*>(src + (size_t)row * ldg + tc.col);
+    acc[r][0] = v.x; acc[r][1] = v.y; acc[r][2] = v.z; acc[r][3] = v.w;
   }
 }
 

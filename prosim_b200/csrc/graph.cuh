@@ -136,7 +136,9 @@ __global__ void __launch_bounds__(128) edge_pe_kernel(const float2* __restrict__
                     __fadd_rn(__fadd_rn(0.0f, __fmul_rn(cx, rx)), __fmul_rn(cy, ry)));
     v = v * TWO_PI_F;
     const float a0 = v / dt0, a1 = v / dt1;
-    float4 f = make_float4(sinf(a0), cosf(a0), sinf(a1), cosf(a1));
+    float4 f;
+    sincosf(a0, &f.x, &f.y);     // one shared range reduction per argument (accurate path, no fast-math)
+    sincosf(a1, &f.z, &f.w);
     if (extra != nullptr) {
       const float4 x = *reinterpret_cast<const float4*>(extra + ei * D + 4 * lane);
       f.x += x.x; f.y += x.y; f.z += x.z; f.w += x.w;
