@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(EDGE_NW * 32, 2) attn_edge3_kernel(const float
   extern __shared__ __align__(16) float smem[];
   float* sZ = smem;                               // [NW warps][32][ZP]   (reused for the partials at the end)
   float* sP = sZ + EDGE_NW * C::WARP_Z;           // [NW warps][32 edges][8 heads]
-  float* sQh = sP + EDGE_NW * 32 * 8;             // [RPC][8][ZD]
+  float* sQh = sP + EDGE_NW * 32 * 8;             // [RPC][ZD][8 heads]: head-interleaved so FFMA2 gets natural head pairs
   float* sScale = sQh + RPC * H * ZD;             // [NW warps][16]: per-head merge scale, 1/(L+eps) folded in
   float* sMt = sScale + EDGE_NW * 16;             // [NW warps][MAXT][8]: running max after each of the warp's tiles
 
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(EDGE_NW * 32, 2) attn_edge3_kernel(const float
       v = qh[d];
       if (ZD == 96 && d >= 64) v += qh[d + 32];
     }
-    sQh[i] = v;
+    sQh[r * H * ZD + d * H + h] = v;
   }
   __syncthreads();
 
@@ -126,12 +126,17 @@ __global__ void __launch_bounds__(EDGE_NW * 32, 2) attn_edge3_kernel(const float
       for (int d4 = 0; d4 < ZD / 4; ++d4) {
         const float4 z4 = zr[d4];
 #pragma unroll
-        for (int h = 0; h < H; ++h) {
-          const float4 q4 = reinterpret_cast<const float4*>(qh + h * ZD)[d4];
-          s[h] = fmaf(q4.x, z4.x, s[h]);
-          s[h] = fmaf(q4.y, z4.y, s[h]);
-          s[h] = fmaf(q4.z, z4.z, s[h]);
-          s[h] = fmaf(q4.w, z4.w, s[h]);
+        for (int i = 0; i < 4; ++i) {
+          const float zv = i == 0 ? z4.x : i == 1 ? z4.y : i == 2 ? z4.z : z4.w;
+          const float4 qa = reinterpret_cast<const float4*>(qh + (d4 * 4 + i) * H)[0];   // heads 0..3 of column d
+          const float4 qb = reinterpret_cast<const float4*>(qh + (d4 * 4 + i) * H)[1];   // heads 4..7
+          const float2 zz = make_float2(zv, zv);
+          const float2 s01 = __ffma2_rn(zz, make_float2(qa.x, qa.y), make_float2(s[0], s[1]));
+          const float2 s23 = __ffma2_rn(zz, make_float2(qa.z, qa.w), make_float2(s[2], s[3]));
+          const float2 s45 = __ffma2_rn(zz, make_float2(qb.x, qb.y), make_float2(s[4], s[5]));
+          const float2 s67 = __ffma2_rn(zz, make_float2(qb.z, qb.w), make_float2(s[6], s[7]));
+          s[0] = s01.x; s[1] = s01.y; s[2] = s23.x; s[3] = s23.y;
+          s[4] = s45.x; s[5] = s45.y; s[6] = s67.x; s[7] = s67.y;
         }
       }
     }
@@ -160,13 +165,17 @@ __global__ void __launch_bounds__(EDGE_NW * 32, 2) attn_edge3_kernel(const float
     for (int e = 0; e < nt; ++e) {
       const float4 pa = *reinterpret_cast<const float4*>(pt + e * 8);
       const float4 pb = *reinterpret_cast<const float4*>(pt + e * 8 + 4);
-      const float pe[H] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
       const float* zr = zt + e * ZP + lane;
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         const float zv = zr[c * 32];
-#pragma unroll
-        for (int h = 0; h < H; ++h) racc[h][c] = fmaf(pe[h], zv, racc[h][c]);
+        const float2 zz = make_float2(zv, zv);
+        const float2 r01 = __ffma2_rn(zz, make_float2(pa.x, pa.y), make_float2(racc[0][c], racc[1][c]));
+        const float2 r23 = __ffma2_rn(zz, make_float2(pa.z, pa.w), make_float2(racc[2][c], racc[3][c]));
+        const float2 r45 = __ffma2_rn(zz, make_float2(pb.x, pb.y), make_float2(racc[4][c], racc[5][c]));
+        const float2 r67 = __ffma2_rn(zz, make_float2(pb.z, pb.w), make_float2(racc[6][c], racc[7][c]));
+        racc[0][c] = r01.x; racc[1][c] = r01.y; racc[2][c] = r23.x; racc[3][c] = r23.y;
+        racc[4][c] = r45.x; racc[5][c] = r45.y; racc[6][c] = r67.x; racc[7][c] = r67.y;
       }
     }
     // unnormalised weights of this tile (relative to the running max stored in mt_w), rescaled at the end

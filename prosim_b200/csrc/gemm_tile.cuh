@@ -118,10 +118,10 @@ __device__ __forceinline__ void gemm_tile2(float (&acc)[2 * RT][4], const float*
 #pragma unroll
         for (int r = 0; r < TR; ++r) {
           const float x = j == 0 ? av[r].x : j == 1 ? av[r].y : j == 2 ? av[r].z : av[r].w;
-          acc[r][0] = fmaf(x, b.x, acc[r][0]);
-          acc[r][1] = fmaf(x, b.y, acc[r][1]);
-          acc[r][2] = fmaf(x, b.z, acc[r][2]);
-          acc[r][3] = fmaf(x, b.w, acc[r][3]);
+          // Blackwell packed fp32 FMA (SASS FFMA2, scalar-broadcast first operand): two IEEE fmas per issue slot
+          const float2 lo = __ffma2_rn(make_float2(x, x), make_float2(b.x, b.y), make_float2(acc[r][0], acc[r][1]));
+          const float2 hi = __ffma2_rn(make_float2(x, x), make_float2(b.z, b.w), make_float2(acc[r][2], acc[r][3]));
+          acc[r][0] = lo.x; acc[r][1] = lo.y; acc[r][2] = hi.x; acc[r][3] = hi.y;
         }
       }
     }
