@@ -93,11 +93,11 @@ int setup_attributes() {
   acc(allow_smem(pointnet_kernel<24, 24, 1, 11>, PointNetCfg<11>::smem_bytes));
   acc(allow_smem(pointnet_kernel<11, 12, 3, 19>, PointNetCfg<19>::smem_bytes));
   acc(allow_smem(knn_kernel, 64 * 1024));
-  acc(allow_smem(attn_kv2_kernel<2>, Kv2Smem<2>::bytes));
-  acc(allow_smem(attn_kv2_kernel<4>, Kv2Smem<4>::bytes));
-  acc(allow_smem(attn_dstpre2_kernel<2>, Pre2Smem<2>::bytes));
-  acc(allow_smem(attn_dstpre2_kernel<4>, Pre2Smem<4>::bytes));
-  acc(allow_smem(attn_post2_kernel<2>, Post2Smem<2>::bytes));
+  acc(allow_smem(attn_kv2_kernel<4, 8>, Kv2Smem<4, 8>::bytes));
+  acc(allow_smem(attn_kv2_kernel<8, 8>, Kv2Smem<8, 8>::bytes));
+  acc(allow_smem(attn_dstpre2_kernel<4, 8>, Pre2Smem<4, 8>::bytes));
+  acc(allow_smem(attn_dstpre2_kernel<8, 8>, Pre2Smem<8, 8>::bytes));
+  acc(allow_smem(attn_post2_kernel<4, 8>, Post2Smem<4, 8>::bytes));
   state = e == cudaSuccess ? 1 : (int)e + 1000;
   return e == cudaSuccess ? 0 : (int)e;
 }
@@ -139,12 +139,12 @@ int launch_kv(const float* x, int n, const float* w, size_t wstride, int layers,
   LaunchScope ls(PROSIM_K_ATTN_KV, st);
   const int rt = pick_rt(n);
   if (rt == 4) {
-    attn_kv2_kernel<4><<<dim3((n + 63) / 64, layers), 256, Kv2Smem<4>::bytes, st>>>(x, n, w, wstride, kv, kvstride);
+    attn_kv2_kernel<8, 8><<<dim3((n + 63) / 64, layers), 256, Kv2Smem<8, 8>::bytes, st>>>(x, n, w, wstride, kv, kvstride);
     PROSIM_CHECK_LAUNCH();
     return 0;
   }
   if (rt == 2) {
-    attn_kv2_kernel<2><<<dim3((n + 31) / 32, layers), 256, Kv2Smem<2>::bytes, st>>>(x, n, w, wstride, kv, kvstride);
+    attn_kv2_kernel<4, 8><<<dim3((n + 31) / 32, layers), 256, Kv2Smem<4, 8>::bytes, st>>>(x, n, w, wstride, kv, kvstride);
     PROSIM_CHECK_LAUNCH();
     return 0;
   }
@@ -159,12 +159,12 @@ int launch_dstpre(const float* x, int n, const float* w, const DstScratch& d, cu
   LaunchScope ls(PROSIM_K_ATTN_DSTPRE, st);
   const int rt = pick_rt(n);
   if (rt == 4) {
-    attn_dstpre2_kernel<4><<<(n + 63) / 64, 256, Pre2Smem<4>::bytes, st>>>(x, n, w, d.q, d.qhat, d.s, d.gx);
+    attn_dstpre2_kernel<8, 8><<<(n + 63) / 64, 256, Pre2Smem<8, 8>::bytes, st>>>(x, n, w, d.q, d.qhat, d.s, d.gx);
     PROSIM_CHECK_LAUNCH();
     return 0;
   }
   if (rt == 2) {
-    attn_dstpre2_kernel<2><<<(n + 31) / 32, 256, Pre2Smem<2>::bytes, st>>>(x, n, w, d.q, d.qhat, d.s, d.gx);
+    attn_dstpre2_kernel<4, 8><<<(n + 31) / 32, 256, Pre2Smem<4, 8>::bytes, st>>>(x, n, w, d.q, d.qhat, d.s, d.gx);
     PROSIM_CHECK_LAUNCH();
     return 0;
   }
@@ -224,8 +224,8 @@ int launch_post(const float* x, int n, int zd, const float* rbar, const float* a
   if (n <= 0) return 0;
   const int rpt = pick_rpt(n);
   LaunchScope ls(PROSIM_K_ATTN_POST, st);
-  if (pick_rt(n) != 0) {
-    attn_post2_kernel<2><<<(n + 31) / 32, 256, Post2Smem<2>::bytes, st>>>(x, n, zd, rbar, aggv, cur.s, cur.gx, w, out, w_next,
+  if (pick_rt(n) != 0 && zd == 96) {
+    attn_post2_kernel<4, 8><<<(n + 31) / 32, 256, Post2Smem<4, 8>::bytes, st>>>(x, n, zd, rbar, aggv, cur.s, cur.gx, w, out, w_next,
                                                                          nxt.q, nxt.qhat, nxt.s, nxt.gx);
     PROSIM_CHECK_LAUNCH();
     return 0;
