@@ -127,6 +127,11 @@ int prosim_gather_pose(const float* pos, const float* head, const int32_t* rows,
 int prosim_step_agent_traj(const float* motion_pred, const int32_t* p_row, int P, int T, int tidx, float* traj,
                            float* vel, prosim_stream_t stream);
 
+/* obtain_rollout_trajs_in_world (rollout/gpu_utils.py:230-266) + batch_nd_transform_points_pt / angles_pt
+ * (rollout/utils.py:347-392): agent-t0-frame trajectories -> world (x, y, heading); tf = 3x3 row-major, out [P][steps][3] */
+int prosim_rollout_to_world(const float* traj, const float* init_pos, const float* init_heading, const int32_t* p_row,
+                            int P, int T, int t0, int steps, const float* tf, float* out, prosim_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -455,3 +455,20 @@ class ProSimOracle:
         agent_names = ['-'.join(nm.split('-')[:-1]) for nm in pair_names]
         uniq = sorted(set(agent_names))
         [uniq.index(nm) for nm in agent_names]
+
+
+def rollout_trajs_in_world(result, tf):
+    """rollout/gpu_utils.py:230-281 (obtain_rollout_trajs_in_world) + rollout/utils.py:347-392.
+    result: the 'motion_pred' dict of a forward; tf: [3, 3] centre->world.  Returns ([P, steps, 3], names)."""
+    names = list(result['rollout_trajs'].keys())
+    trajs = torch.stack([result['rollout_trajs'][n]['traj'] for n in names])
+    init_pos = torch.stack([result['rollout_trajs'][n]['init_pos'] for n in names])
+    init_heads = torch.stack([result['rollout_trajs'][n]['init_heading'] for n in names])
+    xy_c = rotate2d(trajs[:, :, :2], init_heads) + init_pos[:, None]
+    hs = torch.arctan2(trajs[:, :, 2], trajs[:, :, 3])
+    hs_c = wrap_angle(hs + init_heads)
+    mat = torch.transpose(tf, -1, -2)
+    xy_w = (xy_c[..., None, :] @ mat[None, None, :2, :2]).squeeze(-2) + mat[None, None, -1:, :2].squeeze(-2)
+    rot = torch.arctan2(tf[1, 0], tf[0, 0])
+    hs_w = (hs_c + rot + math.pi) % (2 * math.pi) - math.pi
+    return torch.cat([xy_w, hs_w[:, :, None]], dim=-1), names

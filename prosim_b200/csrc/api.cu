@@ -240,7 +240,7 @@ int launch_post(const float* x, int n, int zd, const float* rbar, const float* a
 
 extern "C" {
 
-int prosim_abi_version(void) { return 3; }
+int prosim_abi_version(void) { return 4; }
 
 long long prosim_launch_count(int kernel_class) {
   if (kernel_class >= 0 && kernel_class < N_CLASSES) return g_launches[kernel_class];
@@ -507,6 +507,18 @@ int prosim_step_agent_traj(const float* motion_pred, const int32_t* p_row, int P
   if (!motion_pred || !p_row || !traj || !vel) return ERR_ARG;
   LaunchScope ls(PROSIM_K_STATE, S(stream));
   step_agent_traj_kernel<<<(P + 127) / 128, 128, 0, S(stream)>>>(motion_pred, p_row, P, T, tidx, traj, vel);
+  PROSIM_CHECK_LAUNCH();
+  return 0;
+}
+
+int prosim_rollout_to_world(const float* traj, const float* init_pos, const float* init_heading, const int32_t* p_row,
+                            int P, int T, int t0, int steps, const float* tf, float* out, prosim_stream_t stream) {
+  if (P < 0 || steps < 0 || t0 < 0 || t0 + steps > T) return ERR_ARG;
+  if (P == 0 || steps == 0) return 0;
+  if (!traj || !init_pos || !init_heading || !p_row || !tf || !out) return ERR_ARG;
+  LaunchScope ls(PROSIM_K_STATE, S(stream));
+  to_world_kernel<<<(P * steps + 255) / 256, 256, 0, S(stream)>>>(traj, init_pos, init_heading, p_row, P, T, t0, steps, tf,
+                                                                  out);
   PROSIM_CHECK_LAUNCH();
   return 0;
 }

@@ -129,6 +129,30 @@ __global__ void step_agent_traj_kernel(const float* __restrict__ motion_pred, co
   }
 }
 
+// Local (agent t0 frame) -> world: rollout/gpu_utils.py:255-266 (obtain_rollout_trajs_in_world) with
+// rollout/utils.py:347-392 (batch_nd_transform_points_pt / angles_pt, angle_wrap).  tf = 3x3 row-major
+// centre->world transform.  out[p][i] = (x_w, y_w, h_w) for the `steps` rolled-out steps starting at t0.
+// One thread per (agent, step).
+__global__ void to_world_kernel(const float* __restrict__ traj, const float* __restrict__ init_pos,
+                                const float* __restrict__ init_heading, const int* __restrict__ p_row, int P, int T,
+                                int t0, int steps, const float* __restrict__ tf, float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P * steps) return;
+  const int p = idx / steps, i = idx % steps;
+  const int row = p_row[p];
+  const float4 w = reinterpret_cast<const float4*>(traj)[(size_t)row * T + t0 + i];
+  const float ih = init_heading[row];
+  const float2 xy = rot2(w.x, w.y, ih);
+  const float xc = xy.x + init_pos[row * 2 + 0], yc = xy.y + init_pos[row * 2 + 1];
+  const float hc = wrap_angle(atan2f(w.z, w.w) + ih);
+  const float PI_F = 3.14159265358979323846f, TWO_PI_F = 6.28318530717958647692f;
+  const float rot = atan2f(tf[3], tf[0]);
+  float* o = out + (size_t)idx * 3;
+  o[0] = (xc * tf[0] + yc * tf[1]) + tf[2];
+  o[1] = (xc * tf[3] + yc * tf[4]) + tf[5];
+  o[2] = py_mod((hc + rot) + PI_F, TWO_PI_F) - PI_F;       // angle_wrap: (a + pi) % 2pi - pi
+}
+
 // Linear(128->128)+LN+ReLU, Linear(128->64)+LN(64)+ReLU, Linear(64->n_out<=128) on a tile held in sIn;
 // result left in sOut (columns >= n_out are zero).  Weight block layout: hw::MH0_W.. / hw::PM0_W.. pattern.
 template <int RPT>

@@ -206,3 +206,14 @@ def gather_pose(pos, head, rows, out_pos, out_ori):
 def step_agent_traj(motion_pred, p_row, T, tidx, traj, vel):
     lib.call('prosim_step_agent_traj', ptr(motion_pred), ptr(p_row), p_row.shape[0], int(T), int(tidx), ptr(traj), ptr(vel),
              _stream())
+
+
+def rollout_to_world(traj, init_pos, init_heading, p_row, T, t0, steps, tf):
+    """[P, steps, 3] world (x, y, heading) of the rolled-out steps; tf: [3, 3] centre->world transform on the device."""
+    for t, n in ((traj, 'traj'), (init_pos, 'init_pos'), (init_heading, 'init_heading'), (tf, 'tf')):
+        _chk(t, torch.float32, n)
+    P = p_row.shape[0]
+    out = torch.empty(P, steps, 3, device=traj.device, dtype=torch.float32)
+    lib.call('prosim_rollout_to_world', ptr(traj), ptr(init_pos), ptr(init_heading), ptr(p_row), P, int(T), int(t0),
+             int(steps), ptr(tf), ptr(out), _stream())
+    return out

@@ -3,6 +3,7 @@ the CPU oracle and the reference-generated golden vectors.  Protocol: SURVEY.md 
 (1) teacher-forced per-tick parity <= 1e-5, (2) bit-exact index bookkeeping, (3) closed-loop parity judged
 against the reference's own fp64 evaluation where its fp32 noise exceeds 5e-5."""
 import copy
+import math
 
 import numpy as np
 import pytest
@@ -155,3 +156,34 @@ def test_cpu_batch_is_rejected():
     from prosim_b200 import lib
     with pytest.raises(lib.ProSimLibError):
         _model(False).forward(synthetic.make_batch(n_scenes=1, n_agents=4, n_map=8, steps=10), 'val')
+
+
+def test_parallel_rollout_batch_and_world_transform():
+    """The reference's M-replica rollout helpers (rollout/gpu_utils.py:59-281): every replica equals the single rollout
+    bit for bit, and the local->world transform matches the oracle restatement."""
+    from oracle.prosim_oracle import rollout_trajs_in_world
+    from prosim_b200.rollout import obtain_rollout_trajs_in_world, parallel_rollout_batch
+    kw = dict(n_scenes=1, n_agents=20, n_map=48, steps=30)
+    single, _ = _run_gpu(kw, False)
+    model = _model(False)
+    batch = synthetic.make_batch(**kw).to('cuda')
+    M = 3
+    res = parallel_rollout_batch(batch, M, model)
+    assert model.mode == 'rollout'
+    rt = res['motion_pred']['rollout_trajs']
+    assert len(rt) == M * 20
+    for name, r in single['rollout_trajs'].items():
+        aid = name.split('-', 1)[1]
+        for m in range(M):
+            assert torch.equal(r['traj'], rt[f'{m}-{aid}']['traj']) and torch.equal(r['vel'], rt[f'{m}-{aid}']['vel'])
+    th = 0.7
+    tf = torch.tensor([[math.cos(th), -math.sin(th), 120.5], [math.sin(th), math.cos(th), -40.25], [0.0, 0.0, 1.0]])
+    batch.centered_world_from_agent_tf = tf[None].repeat(M, 1, 1)
+    trajs_M, ids_M = obtain_rollout_trajs_in_world(batch, res)
+    assert len(trajs_M) == M and ids_M[0] == [n.split('-')[1] for n in list(rt.keys())[:20]]
+    cpu_res = {'rollout_trajs': {n: {k: v.cpu() for k, v in r.items()} for n, r in rt.items()}}
+    ref, _ = rollout_trajs_in_world(cpu_res, tf)
+    got = np.concatenate(trajs_M, axis=0)
+    assert np.abs(got[..., :2] - ref[..., :2].numpy()).max() < 2e-5
+    dh = np.abs(got[..., 2] - ref[..., 2].numpy())
+    assert np.minimum(dh, 2 * math.pi - dh).max() < 1e-5

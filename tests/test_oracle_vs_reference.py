@@ -39,3 +39,22 @@ def test_oracle_bit_equal_to_reference(goal):
         for key in ('input', 'mask', 'position', 'heading'):
             a, b = b_ref.extras['fut_obs'][t][key], b_orc.extras['fut_obs'][t][key]
             assert torch.equal(torch.nan_to_num(a.float()), torch.nan_to_num(b.float())), (t, key)
+
+
+def test_world_transform_equals_reference():
+    """oracle.rollout_trajs_in_world == the reference's obtain_rollout_trajs_in_world (rollout/gpu_utils.py:230-281)."""
+    import math
+    import types
+    import numpy as np
+    ref_shim.install_shims()
+    from prosim.rollout.gpu_utils import obtain_rollout_trajs_in_world
+    from oracle.prosim_oracle import rollout_trajs_in_world
+    sd = weights.random_state_dict(0)
+    out = ProSimOracle(sd).forward(synthetic.make_batch(agents_per_scene=[6, 4], map_per_scene=[20, 16], steps=20))
+    th = -1.1
+    tf = torch.tensor([[math.cos(th), -math.sin(th), 33.0], [math.sin(th), math.cos(th), 7.5], [0.0, 0.0, 1.0]])
+    fake = types.SimpleNamespace(centered_world_from_agent_tf=tf[None].repeat(2, 1, 1))
+    trajs_M, ids_M = obtain_rollout_trajs_in_world(fake, out)
+    mine, names = rollout_trajs_in_world(out['motion_pred'], tf)
+    assert np.array_equal(np.concatenate(trajs_M, axis=0), mine.numpy())
+    assert [i for ids in ids_M for i in ids] == [n.split('-')[1] for n in names]
