@@ -156,8 +156,6 @@ class ProSimB200(nn.Module):
         ex = batch.extras
         obs, mp = ex['init_obs'], ex['init_map']
         prm = ex['prompt'][self.tasks[0]]
-        if not obs['input'].is_cuda:
-            raise lib.ProSimLibError('ProSimB200 needs the batch on the GPU (batch.to(device)); there is no CPU path')
         pl = _Plan()
         pl.all_t = sorted(int(t) for t in ex['all_t_indices'].cpu().numpy().tolist())
         pl.B, pl.A = obs['input'].shape[:2]
@@ -243,7 +241,10 @@ class ProSimB200(nn.Module):
             pos += v.size
         host = torch.from_numpy(np.concatenate(chunks)).pin_memory()
         dev = host.to(self._device, non_blocking=True)
+        pl.int_host, pl.int_dev = host, dev
         pl.i = {k: dev[o:o + n] for k, (o, n) in offs.items()}
+        pl.key = (B, A, M, N, pl.P, pl.NM, tuple(pl.NA), pl.max_a, pl.max_m, pl.max_p, pl.max_tok, tuple(pl.all_t),
+                  int(host.numel()))
         pl.steps = len(pl.all_t) * STEP
         pl.T = HIST + pl.steps
         batch._b200_plan = pl
@@ -252,6 +253,8 @@ class ProSimB200(nn.Module):
     # ------------------------------------------------------------------ reference API
     def forward(self, batch, mode):
         """traj_sam.py:59-71."""
+        if not batch.extras['init_obs']['input'].is_cuda:
+            raise lib.ProSimLibError('ProSimB200 needs the batch on the GPU (batch.to(device)); there is no CPU path')
         self.mode = mode
         scene_embs = self.encode_scene(batch)
         prompt_encs = self.encode_prompt(batch)

@@ -187,3 +187,22 @@ def test_parallel_rollout_batch_and_world_transform():
     assert np.abs(got[..., :2] - ref[..., :2].numpy()).max() < 2e-5
     dh = np.abs(got[..., 2] - ref[..., 2].numpy())
     assert np.minimum(dh, 2 * math.pi - dh).max() < 1e-5
+
+
+def test_graphed_forward_matches_eager_and_accepts_host_batches():
+    """CUDA-graph replay (graph_runner.GraphedForward): bit-identical to the eager forward, reusable for a new batch of
+    the same shape, fed straight from pinned host memory."""
+    from prosim_b200.graph_runner import GraphedForward
+    model = _model(False)
+    runner = GraphedForward(model)
+    kw = dict(n_scenes=2, n_agents=24, n_map=40, steps=30)
+    for first in (0, 5, 0):
+        eager, _ = _run_gpu(dict(kw, first_scene=first), False)
+        host = synthetic.make_batch(**kw, first_scene=first, pin_memory=True)
+        out = runner(host, 'val')['motion_pred']
+        torch.cuda.synchronize()
+        assert out['pair_names'] == eager['pair_names']
+        assert torch.equal(out['motion_pred'], eager['motion_pred'])
+        for name, r in eager['rollout_trajs'].items():
+            assert torch.equal(r['traj'], out['rollout_trajs'][name]['traj']), (first, name)
+    assert len(runner._cache) == 1
