@@ -132,6 +132,10 @@ int prosim_step_agent_traj(const float* motion_pred, const int32_t* p_row, int P
 int prosim_rollout_to_world(const float* traj, const float* init_pos, const float* init_heading, const int32_t* p_row,
                             int P, int T, int t0, int steps, const float* tf, float* out, prosim_stream_t stream);
 
+/* tcgen05 / TMEM building block under validation (csrc/tc_gemm.cuh): c[m][128] = a[m][128] * w[128][128]^T with
+ * kind::tf32 tensor-core MMAs, accumulators in tensor memory; split3 = 1 selects the fp32-class 3xTF32 scheme. */
+int prosim_tc_gemm_test(const float* a, const float* w, float* c, int m, int split3, prosim_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

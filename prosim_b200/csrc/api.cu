@@ -8,6 +8,7 @@
 #include "graph.cuh"
 #include "pointnet.cuh"
 #include "rollout.cuh"
+#include "tc_gemm.cuh"
 #include "weights_layout.h"
 
 using namespace prosim;
@@ -519,6 +520,19 @@ int prosim_rollout_to_world(const float* traj, const float* init_pos, const floa
   LaunchScope ls(PROSIM_K_STATE, S(stream));
   to_world_kernel<<<(P * steps + 255) / 256, 256, 0, S(stream)>>>(traj, init_pos, init_heading, p_row, P, T, t0, steps, tf,
                                                                   out);
+  PROSIM_CHECK_LAUNCH();
+  return 0;
+}
+
+int prosim_tc_gemm_test(const float* a, const float* w, float* c, int m, int split3, prosim_stream_t stream) {
+  if (m <= 0 || !a || !w || !c) return ERR_ARG;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tc::tc_gemm_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::TEST_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  tc::tc_gemm_test_kernel<<<(m + 127) / 128, 128, tc::TEST_SMEM, S(stream)>>>(a, w, c, m, split3);
   PROSIM_CHECK_LAUNCH();
   return 0;
 }

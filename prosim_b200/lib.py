@@ -16,7 +16,7 @@ SYMBOLS = (
     'prosim_build_knn_edges', 'prosim_edge_pe', 'prosim_attn_kv', 'prosim_attn_layer_fwd', 'prosim_attn_stack_fwd',
     'prosim_policy_head_fwd', 'prosim_reconst_fwd', 'prosim_mlp2_fwd', 'prosim_init_traj', 'prosim_step_env',
     'prosim_gather_pose', 'prosim_step_agent_traj', 'prosim_launch_count', 'prosim_profile_enable', 'prosim_profile_read',
-    'prosim_rollout_to_world',
+    'prosim_rollout_to_world', 'prosim_tc_gemm_test',
 )
 
 KERNEL_CLASSES = {'pointnet': 0, 'radius': 1, 'knn': 2, 'edge_pe': 3, 'attn_kv': 4, 'attn_dstpre': 5, 'attn_edge': 6,
@@ -53,6 +53,7 @@ _SIGS = {
     'prosim_gather_pose': [_P, _P, _P, c_int, _P, _P, _P],
     'prosim_step_agent_traj': [_P, _P, c_int, c_int, c_int, _P, _P, _P],
     'prosim_rollout_to_world': [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P],
+    'prosim_tc_gemm_test': [_P, _P, _P, c_int, c_int, _P],
 }
 
 _lib = None

@@ -253,3 +253,21 @@ def test_bad_arguments_raise(ctx):
                      ctx['arena'], 0)        # CPU tensors: no fallback
     with pytest.raises(lib.ProSimLibError):
         lib.call('prosim_step_agent_traj', None, None, 4, 91, 90, None, None, None)   # tidx + 10 > T
+
+
+@pytest.mark.parametrize('split3', [0, 1])
+def test_tcgen05_gemm_block(ctx, split3):
+    """tcgen05 / TMEM building block: one TF32 pass is ~1e-3 accurate, the 3xTF32 scheme is fp32-class."""
+    from prosim_b200 import lib
+    g = torch.Generator().manual_seed(23)
+    m = 300
+    a, w = torch.randn(m, 128, generator=g), torch.randn(128, 128, generator=g) / 11.3
+    c = torch.full((m, 128), float('nan'), device='cuda')
+    a_d, w_d = a.cuda(), w.cuda()
+    lib.call('prosim_tc_gemm_test', lib.ptr(a_d), lib.ptr(w_d), lib.ptr(c), m, split3,
+             torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ref = (a.double() @ w.double().t()).float()
+    err = (c.cpu() - ref).abs().max().item()
+    print('tcgen05 gemm split3 =', split3, 'max err', err)
+    assert err < (2e-5 if split3 else 2e-2)
