@@ -36,7 +36,7 @@ UNIT = 'agent-steps/s'
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--scenes-per-gpu', type=int, default=32)
@@ -68,7 +68,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.idx}', f'--query-gpu={self.Q}',
-                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
@@ -143,6 +143,19 @@ def run_reference(a):
 
 
 # ----------------------------------------------------------------------------------------------- B200 arm
+def edge_kernel_bytes(edge_log):
+    """Algorithmic HBM bytes of all attn_edge3 launches of one forward: per edge 384 B of z (read once),
+    32 B of q.K' scores in, 32 B of attention weights out and their 64 B in-place rescale; per destination row 4 KB of
+    Qhat in and 3 KB of Rbar out."""
+    total_edges, total_bytes, launches = 0, 0.0, 0
+    for kind, esum, n_dst, n_layers in edge_log:
+        e = int(esum)
+        total_edges += e * n_layers
+        total_bytes += n_layers * (e * (384 + 32 + 32 + 64) + n_dst * (8 * 128 * 4 + 8 * 96 * 4))
+        launches += n_layers
+    return total_edges, total_bytes, launches
+
+
 def algorithmic_flops_post(n_rows):
     """attn_post_kernel (+ fused next-layer dst projections), 2 FLOP/MAC: Wvr' contraction 128x128, gate 128x128,
     out-proj 128x128, FFN 128x512 + 512x128, next q/s/gx 3 x 128x128, Qhat 8 x 16x128  (DESIGN.md)."""
@@ -204,13 +217,21 @@ def run_b200(a):
             forward_device(i)
         barrier()
         n0 = lib.launch_count()
-        lib.profile_enable('attn_post')
+        lib.profile_enable('attn_edge')
         with ClockSampler(local) as clk:
             times = [forward_device(a.warmup + i)[0] for i in range(a.steps)]
             barrier()
-        post_ms, post_n = lib.profile_read()
+        edge_ms, edge_n = lib.profile_read()
         lib.profile_enable(None)
         launches = lib.launch_count() - n0
+        # untimed extra forwards: edge counts of every attention launch, and the dense node kernel's share
+        model.edge_log = []
+        forward_device(0)
+        edge_log, model.edge_log = model.edge_log, None
+        lib.profile_enable('attn_post')
+        t_extra = forward_device(1)[0]
+        post_ms, post_n = lib.profile_read()
+        lib.profile_enable(None)
 
         for i in range(min(a.warmup, 2)):
             forward_e2e(i)
@@ -232,8 +253,21 @@ def run_b200(a):
                 e1.synchronize()
                 lat.append(e0.elapsed_time(e1))
             ms = statistics.median(lat[3:])
+            from prosim_b200.graph_runner import GraphedForward
+            runner = GraphedForward(model)
+            one_host = synthetic.make_batch(n_scenes=1, n_agents=A, n_map=M, steps=RS, pin_memory=True)
+            glat = []
+            for i in range(8):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                st1 = runner(one_host, 'val')['motion_pred']['_state']
+                st1['traj'].to('cpu', non_blocking=True)
+                torch.cuda.synchronize()
+                glat.append((time.perf_counter() - t0) * 1e3)
+            gms = statistics.median(glat[3:])
             single = {'workload': f'1 scene x {A} agents x {M} polylines x {RS} steps (BASELINE configs[2])',
-                      'ms_per_forward': ms, 'value': A * RS / (ms * 1e-3), 'unit': UNIT}
+                      'ms_per_forward': ms, 'value': A * RS / (ms * 1e-3), 'unit': UNIT,
+                      'cuda_graph_e2e_ms': gms, 'cuda_graph_e2e_value': A * RS / (gms * 1e-3)}
 
     total = torch.tensor([sum(times), sum(t for t, _, _ in e2e)], device=dev, dtype=torch.float64)
     if world > 1:
@@ -252,10 +286,25 @@ def run_b200(a):
         # dominant kernel: attn_post_kernel (row-tile fp32 GEMMs of every attention layer).  It computes on the
         # fp32 CUDA cores (IEEE fp32 is required for parity, DESIGN.md "Numerics"); the fraction is reported
         # against the tensor-pipe peak the contract names AND against the fp32 FFMA peak it is actually bound by.
-        rows_per_launch = S * A
-        post_launches_policy = None
-        flops_total = None
         roof = None
+        sm_mhz = peaks.get('sm_max_mhz', 1965.0)
+        ffma_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        if edge_n > 0:
+            # dominant kernel by time: attn_edge3_kernel (z streaming + per-edge 8x96 contractions).  Arithmetic intensity
+            # 3.1 kFLOP / 512 B = 6 FLOP/B is below the fp32 machine balance (11 FLOP/B): HBM is its roofline.
+            n_edges, n_bytes, n_launch = edge_kernel_bytes(edge_log)
+            avg_ms = edge_ms / edge_n
+            achieved = n_bytes / n_launch / (avg_ms * 1e-3) / 1e9
+            hbm_peak = peaks.get('hbm_gbs') or 6650.0
+            roof = {'kernel': 'attn_edge3_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
+                    'frac': achieved / hbm_peak,
+                    'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6.65 TB/s',
+                    'traffic': None, 'avg_launch_ms': avg_ms, 'launches_timed': edge_n,
+                    'algorithmic_bytes_per_launch': n_bytes / n_launch, 'edges_per_forward': n_edges,
+                    'share_of_step': edge_ms / total_ms if world == 1 else None,
+                    'fp32_ffma_frac': (n_edges * 3072.0 / n_launch) / (avg_ms * 1e-3) / 1e12 / ffma_peak,
+                    'note': 'latency/issue bound today (profiles/): 12 warps per SM, see DESIGN.md section 5'}
+        roof2 = None
         if post_n > 0:
             avg_ms = post_ms / post_n
             # policy ticks: 12 layers x 8 ticks on S*A rows; generator: 12 layers on S*A rows; encoder: 6 on S*A and 6 on
@@ -266,16 +315,14 @@ def run_b200(a):
             flops_per_launch = algorithmic_flops_post(rows_sum / n_launch_step)
             achieved = flops_per_launch / (avg_ms * 1e-3) / 1e12
             tensor_peak = peaks.get('bf16_tflops_sustained') or 1400.0
-            sm_mhz = peaks.get('sm_max_mhz', 1965.0)
-            ffma_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-            roof = {'kernel': 'attn_post_kernel', 'bound': 'tensor', 'achieved': achieved, 'peak': tensor_peak,
+            roof2 = {'kernel': 'attn_post2_kernel', 'bound': 'tensor', 'achieved': achieved, 'peak': tensor_peak,
                     'unit': 'TFLOP/s', 'frac': achieved / tensor_peak,
                     'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)'
                     if peaks else 'fallback 1.4 PFLOP/s',
                     'traffic': None,
                     'fp32_ffma': {'peak': ffma_peak, 'frac': achieved / ffma_peak,
                                   'note': 'kernel runs IEEE fp32 FFMA on CUDA cores; nominal 148 SM x 128 lanes x 2 x max clock'},
-                    'avg_launch_ms': avg_ms, 'launches_timed': post_n, 'share_of_step': post_ms / total_ms
+                    'avg_launch_ms': avg_ms, 'launches_timed': post_n, 'share_of_step': post_ms / t_extra
                     if world == 1 else None}
         cpu = None
         if not a.no_cpu_baseline and world == 1:
@@ -293,7 +340,8 @@ def run_b200(a):
                        'weights': 'seeded random init under the reference state_dict names (no checkpoint ships)'},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': e2e[0][1], 'd2h_bytes_per_step': e2e[0][2],
                     'ms_per_step': e2e_ms / a.steps},
-            'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': cpu, 'clocks': clk.summary(),
+            'gpu_launches': launches, 'roofline': roof, 'roofline_dense_kernel': roof2, 'cpu_baseline': cpu,
+            'clocks': clk.summary(),
             'single_scene': single,
         }
         print(json.dumps(line))

@@ -140,6 +140,11 @@ class ProSimB200(nn.Module):
     def eval(self):
         return self
 
+    def _note_edges(self, kind, edges, n_layers):
+        """Measurement support (bench.py roofline): remember the edge count of every attention launch of a forward."""
+        if getattr(self, 'edge_log', None) is not None:
+            self.edge_log.append((kind, edges.deg.sum(), edges.n_dst, n_layers))
+
     def _buf(self, name, shape, dtype=torch.float32):
         shape = tuple(int(s) for s in shape)
         b = self._bufs.get(name)
@@ -293,6 +298,8 @@ class ProSimB200(nn.Module):
                             min(k_s, max(pl.max_tok, 1)))
         ops.edge_pe(e_a, a_pos, a_ori, a_pos, a_ori, dim_t, z=self._buf('z_enc_a', (NA * e_a.stride, 96)))
         ops.edge_pe(e_s, tok_pos, tok_ori, tok_pos, tok_ori, dim_t, z=self._buf('z_enc_s', (S * e_s.stride, 96)))
+        self._note_edges('enc_a2a', e_a, self.num_layers)
+        self._note_edges('enc_s2s', e_s, self.num_layers)
         ws = self._buf('attn_ws', (lib.load().prosim_attn_workspace_floats(S, S, max(e_a.stride, e_s.stride)),))
         lf = weights.ATTN_LAYER_FLOATS
         xa = tok[NM:]
@@ -353,6 +360,8 @@ class ProSimB200(nn.Module):
             emd_flat = ops.attn_stack(x_p, self.num_layers, ops.stack_side(ar, off['dec_p2p'], e_pp),
                                       ops.stack_side(ar, off['dec_s2p'], e_sp, kv_s), workspace=ws)
             pl.edges_gen = (e_pp, e_sp)
+            self._note_edges('gen_p2p', e_pp, self.num_layers)
+            self._note_edges('gen_s2p', e_sp, self.num_layers)
             if self.use_condition and 'policy_decoder' in self.config.MODEL.CONDITION_TRANSFORMER.CONDITION_LOCATIONS:
                 emd_flat = self._goal_condition(batch.extras['condition'], emd_flat, p_pos, p_ori, pl, ws)
             emd = torch.zeros(pl.B * pl.N, D, device=self._device)
@@ -471,6 +480,8 @@ class ProSimB200(nn.Module):
             kva = ops.attn_kv(x_a, ar, off['pol_a2p'], L, lf, kv=self._buf('kv_a', (L, na, 2 * D)))
             ops.attn_stack(emd_flat, L, ops.stack_side(ar, off['pol_a2p'], e_a, kva),
                            ops.stack_side(ar, off['pol_m2p'], e_m, kv_m), out=fuse, workspace=ws)
+            self._note_edges('pol_a2p', e_a, L)
+            self._note_edges('pol_m2p', e_m, L)
             ops.policy_head(fuse, a_type, ar, off['head'], motion_pred=motion_pred[k])
             ops.step_agent_traj(motion_pred[k], pl.i['p_row'], T, tidx, traj, vel)
             tidx += STEP
