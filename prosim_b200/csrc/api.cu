@@ -4,12 +4,15 @@
 #include "attn.cuh"
 #include "attn2.cuh"
 #include "edge2.cuh"
+#include "edge4.cuh"
 #include "common.cuh"
 #include "graph.cuh"
 #include "pointnet.cuh"
 #include "rollout.cuh"
 #include "tc_gemm.cuh"
 #include "weights_layout.h"
+
+#include <cudaTypedefs.h>
 
 using namespace prosim;
 
@@ -79,14 +82,10 @@ int setup_attributes() {
   if (state != 0) return state == 1 ? 0 : state;
   cudaError_t e = cudaSuccess;
   auto acc = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
-  acc(allow_smem(attn_edge3_kernel<96, 1>, Edge2Cfg<96>::smem_bytes(6)));
-  acc(allow_smem(attn_edge3_kernel<96, 2>, Edge2Cfg<96>::smem_bytes(3)));
-  acc(allow_smem(attn_edge3_kernel<96, 3>, Edge2Cfg<96>::smem_bytes(2)));
-  acc(allow_smem(attn_edge3_kernel<96, 6>, Edge2Cfg<96>::smem_bytes(1)));
-  acc(allow_smem(attn_edge3_kernel<128, 1>, Edge2Cfg<128>::smem_bytes(6)));
-  acc(allow_smem(attn_edge3_kernel<128, 2>, Edge2Cfg<128>::smem_bytes(3)));
-  acc(allow_smem(attn_edge3_kernel<128, 3>, Edge2Cfg<128>::smem_bytes(2)));
-  acc(allow_smem(attn_edge3_kernel<128, 6>, Edge2Cfg<128>::smem_bytes(1)));
+#define E4_ATTR(ZD, NW) acc(allow_smem(attn_edge4_kernel<ZD, NW>, Edge4Cfg<ZD>::smem_bytes(NW)))
+  E4_ATTR(96, 1); E4_ATTR(96, 2); E4_ATTR(96, 4); E4_ATTR(96, 8); E4_ATTR(96, 12);
+  E4_ATTR(128, 1); E4_ATTR(128, 2); E4_ATTR(128, 4); E4_ATTR(128, 8); E4_ATTR(128, 10);
+#undef E4_ATTR
   acc(allow_smem(attn_post_kernel<8>, PostSmem<8>::bytes));
   acc(allow_smem(attn_post_kernel<4>, PostSmem<4>::bytes));
   acc(allow_smem(attn_post_kernel<2>, PostSmem<2>::bytes));
@@ -109,7 +108,7 @@ struct DstScratch {
 
 struct StackWs {
   DstScratch set[2];
-  float *rbar, *aggv, *x0, *x1, *sk, *pw, *kv;
+  float *rbar, *aggv, *x0, *x1, *sk, *pw, *ft, *kv;
 };
 
 constexpr size_t WS_PER_DST = 2 * (size_t)(D + H * D + D + D) + H * D + D + 2 * D;
@@ -129,6 +128,7 @@ StackWs carve(float* ws, int n_dst, int max_stride) {
   w.x1 = p;   p += (size_t)n_dst * D;
   w.sk = p;   p += (size_t)n_dst * max_stride * 8;
   w.pw = p;   p += (size_t)n_dst * max_stride * 8;
+  w.ft = p;   p += (size_t)n_dst * ((max_stride + 31) / 32) * 8;
   w.kv = p;
   return w;
 }
@@ -174,50 +174,83 @@ int launch_dstpre(const float* x, int n, const float* w, const DstScratch& d, cu
   return 0;
 }
 
-template <int ZD, int WPR>
-int launch_edge_t(const DstScratch& d, const float* kv, const prosim_graph_t& g, int n_dst, float* rbar, float* aggv,
-                  float* sk, float* pw, cudaStream_t st) {
-  constexpr int RPC = EDGE_NW / WPR;
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// z as a 2-D tensor [rows][zd] of fp32, fetched in boxes of 8 rows x 32 floats (1 KB) with the 128-byte swizzle
+int make_z_map(CUtensorMap* tm, const float* z, size_t rows, int zd) {
+  PFN_cuTensorMapEncodeTiled_v12000 enc = tensor_map_encoder();
+  if (!enc) return ERR_ARG - 10;
+  const cuuint64_t dims[2] = {(cuuint64_t)zd, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)zd * sizeof(float)};
+  const cuuint32_t box[2] = {32, 8};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(z), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : ERR_ARG - 11;
+}
+
+template <int ZD, int NW>
+int launch_edge4(const CUtensorMap& tm, const DstScratch& d, const prosim_graph_t& g, int n_dst, float* rbar, float* sk,
+                 float* pw, float* ft, int ft_tiles, cudaStream_t st) {
+  const int grid = (n_dst + NW - 1) / NW < 148 ? (n_dst + NW - 1) / NW : 148;
+  attn_edge4_kernel<ZD, NW><<<grid, NW * 32, Edge4Cfg<ZD>::smem_bytes(NW), st>>>(tm, d.qhat, sk, g.deg, g.stride, n_dst, rbar,
+                                                                              pw, ft, ft_tiles);
+  PROSIM_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_edge(const DstScratch& d, const float* kv, const prosim_graph_t& g, int n_dst, float* rbar, float* aggv,
+                float* sk, float* pw, float* ft, cudaStream_t st) {
+  if (n_dst <= 0) return 0;
+  if ((g.zd != 96 && g.zd != 128) || g.stride > 32 * Edge4Cfg<96>::MT_TILES) return ERR_ARG;
+  const size_t z_rows = (size_t)n_dst * g.stride;
+  if (z_rows > 0x7fffffffull || (reinterpret_cast<uintptr_t>(g.z) & 15) != 0) return ERR_ARG;
+  alignas(64) CUtensorMap tm;
+  if (int e = make_z_map(&tm, g.z, z_rows, g.zd)) return e;
+  const int ft_tiles = (g.stride + 31) / 32;
   {
     LaunchScope ls(PROSIM_K_EDGE_QK, st);
     edge_qk_kernel<<<(n_dst + 7) / 8, 256, 0, st>>>(d.q, kv, g.nbr, g.deg, g.stride, n_dst, sk);
     PROSIM_CHECK_LAUNCH();
   }
   {
+    // one warp per destination row; fewer warps per CTA when the launch has fewer rows than the chip has warp slots
     LaunchScope ls(PROSIM_K_ATTN_EDGE, st);
-    attn_edge3_kernel<ZD, WPR><<<(n_dst + RPC - 1) / RPC, EDGE_NW * 32, Edge2Cfg<ZD>::smem_bytes(RPC), st>>>(
-        d.qhat, sk, g.z, g.deg, g.stride, n_dst, rbar, pw);
-    PROSIM_CHECK_LAUNCH();
+    const int per_sm = (n_dst + 147) / 148;
+    int e = ERR_ARG;
+    if (g.zd == 96) {
+      if (per_sm <= 1) e = launch_edge4<96, 1>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, st);
+      else if (per_sm <= 2) e = launch_edge4<96, 2>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, st);
+      else if (per_sm <= 4) e = launch_edge4<96, 4>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, st);
+      else if (per_sm <= 8) e = launch_edge4<96, 8>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, st);
+      else e = launch_edge4<96, 12>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, st);
+    } else {
+      if (per_sm <= 1) e = launch_edge4<128, 1>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, st);
+      else if (per_sm <= 2) e = launch_edge4<128, 2>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, st);
+      else if (per_sm <= 4) e = launch_edge4<128, 4>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, st);
+      else if (per_sm <= 8) e = launch_edge4<128, 8>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, st);
+      else e = launch_edge4<128, 10>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, st);
+    }
+    if (e) return e;
   }
   LaunchScope ls(PROSIM_K_EDGE_AV, st);
-  edge_av_kernel<<<(n_dst + 7) / 8, 256, 0, st>>>(pw, kv, g.nbr, g.deg, g.stride, n_dst, aggv);
+  edge_av_kernel<<<(n_dst + 7) / 8, 256, 0, st>>>(pw, ft, ft_tiles, kv, g.nbr, g.deg, g.stride, n_dst, aggv);
   PROSIM_CHECK_LAUNCH();
   return 0;
-}
-
-// warps per destination row: one 32-edge tile per warp at the expected degree (hint), else by the degree bound
-inline int pick_wpr(const prosim_graph_t& g) {
-  int w = g.warps_per_row;
-  if (w <= 0) {
-    const int d = g.max_deg < g.stride ? g.max_deg : g.stride;
-    w = d <= 32 ? 1 : d <= 64 ? 2 : d <= 128 ? 3 : 6;
-  }
-  w = w >= 6 ? 6 : w >= 3 ? 3 : w == 2 ? 2 : 1;
-  // a warp remembers the running max of at most Edge2Cfg::MAXT of its tiles
-  while (w < 6 && (g.stride + 32 * w - 1) / (32 * w) > Edge2Cfg<96>::MAXT) w = w == 1 ? 2 : w == 2 ? 3 : 6;
-  return w;
-}
-
-int launch_edge(const DstScratch& d, const float* kv, const prosim_graph_t& g, int n_dst, float* rbar, float* aggv,
-                float* sk, float* pw, cudaStream_t st) {
-  if (n_dst <= 0) return 0;
-  if ((g.zd != 96 && g.zd != 128) || g.stride > 32 * 6 * Edge2Cfg<96>::MAXT) return ERR_ARG;
-  const int wpr = pick_wpr(g);
-#define EDGE_CASE(ZD, W) if (g.zd == ZD && wpr == W) return launch_edge_t<ZD, W>(d, kv, g, n_dst, rbar, aggv, sk, pw, st)
-  EDGE_CASE(96, 1); EDGE_CASE(96, 2); EDGE_CASE(96, 3); EDGE_CASE(96, 6);
-  EDGE_CASE(128, 1); EDGE_CASE(128, 2); EDGE_CASE(128, 3); EDGE_CASE(128, 6);
-#undef EDGE_CASE
-  return ERR_ARG;
 }
 
 int launch_post(const float* x, int n, int zd, const float* rbar, const float* aggv, const DstScratch& cur, const float* w,
@@ -283,7 +316,7 @@ int prosim_head_floats(void) { return hw::SIZE; }
 int prosim_mlp2_floats(void) { return mw::SIZE; }
 size_t prosim_attn_workspace_floats(int n_dst, int n_src, int max_stride) {
   const size_t nd = n_dst < 0 ? 0 : n_dst, ns = n_src < 0 ? 0 : n_src, st = max_stride < 1 ? 1 : max_stride;
-  return (WS_PER_DST + 16 * st) * nd + 256 * ns + 64;
+  return (WS_PER_DST + 16 * st + 8 * ((st + 31) / 32)) * nd + 256 * ns + 64;
 }
 
 int prosim_pointnet_fwd(int kind, const float* x, const uint8_t* mask, const int32_t* rows, int n_poly, const float* w,
@@ -377,7 +410,7 @@ int prosim_attn_layer_fwd(const float* x_src, int n_src, const float* x_dst, int
   StackWs ws = carve(workspace, n_dst, g->stride);
   if (int e = launch_kv(x_src, n_src, w, 0, 1, ws.kv, 0, st)) return e;
   if (int e = launch_dstpre(x_dst, n_dst, w, ws.set[0], st)) return e;
-  if (int e = launch_edge(ws.set[0], ws.kv, *g, n_dst, ws.rbar, ws.aggv, ws.sk, ws.pw, st)) return e;
+  if (int e = launch_edge(ws.set[0], ws.kv, *g, n_dst, ws.rbar, ws.aggv, ws.sk, ws.pw, ws.ft, st)) return e;
   return launch_post(x_dst, n_dst, g->zd, ws.rbar, ws.aggv, ws.set[0], w, out, nullptr, ws.set[1], st);
 }
 
@@ -411,7 +444,7 @@ int prosim_attn_stack_fwd(const float* x, int n_dst, int n_layers, const prosim_
       if (int e = launch_kv(cur_x, n_dst, w, 0, 1, ws.kv, 0, st)) return e;
       kv = ws.kv;
     }
-    if (int e = launch_edge(ws.set[cur_set], kv, sd->graph, n_dst, ws.rbar, ws.aggv, ws.sk, ws.pw, st)) return e;
+    if (int e = launch_edge(ws.set[cur_set], kv, sd->graph, n_dst, ws.rbar, ws.aggv, ws.sk, ws.pw, ws.ft, st)) return e;
     const bool last = i == total - 1;
     const float* w_next = nullptr;
     if (!last) {

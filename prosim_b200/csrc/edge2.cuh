@@ -295,9 +295,12 @@ __global__ void __launch_bounds__(256) edge_qk_kernel(const float* __restrict__ 
 }
 
 // AggV[row][c] = sum_e a[e][c/16] * V'[nbr[e]][c]   (edges in ascending order)
-__global__ void __launch_bounds__(256) edge_av_kernel(const float* __restrict__ Pw, const float* __restrict__ KV,
-                                                      const int* __restrict__ nbr, const int* __restrict__ deg, int stride,
-                                                      int n_dst, float* __restrict__ AggV) {
+// Ft (nullable): per (row, 32-edge tile, head) factor that turns the unnormalised weights of attn_edge4_kernel into
+// attention weights; NULL = Pw already holds them (attn_edge3_kernel).
+__global__ void __launch_bounds__(256) edge_av_kernel(const float* __restrict__ Pw, const float* __restrict__ Ft, int ft_tiles,
+                                                      const float* __restrict__ KV, const int* __restrict__ nbr,
+                                                      const int* __restrict__ deg, int stride, int n_dst,
+                                                      float* __restrict__ AggV) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= n_dst) return;
   const int n_e = min(deg[row], stride);
@@ -306,6 +309,7 @@ __global__ void __launch_bounds__(256) edge_av_kernel(const float* __restrict__ 
   for (int e0 = 0; e0 < n_e; e0 += 32) {
     const int jl = e0 + lane < n_e ? __ldg(nbr + ebase + e0 + lane) : 0;
     const int nt = min(32, n_e - e0);
+    const float f = Ft != nullptr ? __ldg(Ft + ((size_t)row * ft_tiles + (e0 >> 5)) * 8 + (lane >> 2)) : 1.0f;
     for (int g = 0; g < nt; g += GATHER_EB) {
       float4 v4[GATHER_EB];
       float a[GATHER_EB];
@@ -314,7 +318,7 @@ __global__ void __launch_bounds__(256) edge_av_kernel(const float* __restrict__ 
         const int eu = min(g + u, nt - 1);
         const int j = __shfl_sync(0xffffffffu, jl, eu);
         v4[u] = __ldg(reinterpret_cast<const float4*>(KV + (size_t)j * 256 + 128) + lane);
-        a[u] = g + u < nt ? __ldg(Pw + (ebase + e0 + eu) * 8 + (lane >> 2)) : 0.f;
+        a[u] = g + u < nt ? __ldg(Pw + (ebase + e0 + eu) * 8 + (lane >> 2)) * f : 0.f;
       }
 #pragma unroll
       for (int u = 0; u < GATHER_EB; ++u) {
