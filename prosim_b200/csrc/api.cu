@@ -109,6 +109,7 @@ struct DstScratch {
 struct StackWs {
   DstScratch set[2];
   float *rbar, *aggv, *x0, *x1, *sk, *pw, *ft, *kv;
+  int* counter;
 };
 
 constexpr size_t WS_PER_DST = 2 * (size_t)(D + H * D + D + D) + H * D + D + 2 * D;
@@ -129,6 +130,7 @@ StackWs carve(float* ws, int n_dst, int max_stride) {
   w.sk = p;   p += (size_t)n_dst * max_stride * 8;
   w.pw = p;   p += (size_t)n_dst * max_stride * 8;
   w.ft = p;   p += (size_t)n_dst * ((max_stride + 31) / 32) * 8;
+  w.counter = reinterpret_cast<int*>(p); p += 16;
   w.kv = p;
   return w;
 }
@@ -205,16 +207,16 @@ int make_z_map(CUtensorMap* tm, const float* z, size_t rows, int zd) {
 
 template <int ZD, int NW>
 int launch_edge4(const CUtensorMap& tm, const DstScratch& d, const prosim_graph_t& g, int n_dst, float* rbar, float* sk,
-                 float* pw, float* ft, int ft_tiles, cudaStream_t st) {
+                 float* pw, float* ft, int ft_tiles, int* counter, cudaStream_t st) {
   const int grid = (n_dst + NW - 1) / NW < 148 ? (n_dst + NW - 1) / NW : 148;
   attn_edge4_kernel<ZD, NW><<<grid, NW * 32, Edge4Cfg<ZD>::smem_bytes(NW), st>>>(tm, d.qhat, sk, g.deg, g.stride, n_dst, rbar,
-                                                                              pw, ft, ft_tiles);
+                                                                              pw, ft, ft_tiles, counter);
   PROSIM_CHECK_LAUNCH();
   return 0;
 }
 
 int launch_edge(const DstScratch& d, const float* kv, const prosim_graph_t& g, int n_dst, float* rbar, float* aggv,
-                float* sk, float* pw, float* ft, cudaStream_t st) {
+                float* sk, float* pw, float* ft, int* counter, cudaStream_t st) {
   if (n_dst <= 0) return 0;
   if ((g.zd != 96 && g.zd != 128) || g.stride > 32 * Edge4Cfg<96>::MT_TILES) return ERR_ARG;
   const size_t z_rows = (size_t)n_dst * g.stride;
@@ -224,7 +226,7 @@ int launch_edge(const DstScratch& d, const float* kv, const prosim_graph_t& g, i
   const int ft_tiles = (g.stride + 31) / 32;
   {
     LaunchScope ls(PROSIM_K_EDGE_QK, st);
-    edge_qk_kernel<<<(n_dst + 7) / 8, 256, 0, st>>>(d.q, kv, g.nbr, g.deg, g.stride, n_dst, sk);
+    edge_qk_kernel<<<(n_dst + 7) / 8, 256, 0, st>>>(d.q, kv, g.nbr, g.deg, g.stride, n_dst, sk, counter);
     PROSIM_CHECK_LAUNCH();
   }
   {
@@ -233,17 +235,17 @@ int launch_edge(const DstScratch& d, const float* kv, const prosim_graph_t& g, i
     const int per_sm = (n_dst + 147) / 148;
     int e = ERR_ARG;
     if (g.zd == 96) {
-      if (per_sm <= 1) e = launch_edge4<96, 1>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, st);
-      else if (per_sm <= 2) e = launch_edge4<96, 2>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, st);
-      else if (per_sm <= 4) e = launch_edge4<96, 4>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, st);
-      else if (per_sm <= 8) e = launch_edge4<96, 8>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, st);
-      else e = launch_edge4<96, 12>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, st);
+      if (per_sm <= 1) e = launch_edge4<96, 1>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
+      else if (per_sm <= 2) e = launch_edge4<96, 2>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
+      else if (per_sm <= 4) e = launch_edge4<96, 4>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
+      else if (per_sm <= 8) e = launch_edge4<96, 8>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
+      else e = launch_edge4<96, 12>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
     } else {
-      if (per_sm <= 1) e = launch_edge4<128, 1>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, st);
-      else if (per_sm <= 2) e = launch_edge4<128, 2>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, st);
-      else if (per_sm <= 4) e = launch_edge4<128, 4>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, st);
-      else if (per_sm <= 8) e = launch_edge4<128, 8>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, st);
-      else e = launch_edge4<128, 10>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, st);
+      if (per_sm <= 1) e = launch_edge4<128, 1>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
+      else if (per_sm <= 2) e = launch_edge4<128, 2>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
+      else if (per_sm <= 4) e = launch_edge4<128, 4>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
+      else if (per_sm <= 8) e = launch_edge4<128, 8>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
+      else e = launch_edge4<128, 10>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
     }
     if (e) return e;
   }
@@ -410,7 +412,7 @@ int prosim_attn_layer_fwd(const float* x_src, int n_src, const float* x_dst, int
   StackWs ws = carve(workspace, n_dst, g->stride);
   if (int e = launch_kv(x_src, n_src, w, 0, 1, ws.kv, 0, st)) return e;
   if (int e = launch_dstpre(x_dst, n_dst, w, ws.set[0], st)) return e;
-  if (int e = launch_edge(ws.set[0], ws.kv, *g, n_dst, ws.rbar, ws.aggv, ws.sk, ws.pw, ws.ft, st)) return e;
+  if (int e = launch_edge(ws.set[0], ws.kv, *g, n_dst, ws.rbar, ws.aggv, ws.sk, ws.pw, ws.ft, ws.counter, st)) return e;
   return launch_post(x_dst, n_dst, g->zd, ws.rbar, ws.aggv, ws.set[0], w, out, nullptr, ws.set[1], st);
 }
 
@@ -444,7 +446,7 @@ int prosim_attn_stack_fwd(const float* x, int n_dst, int n_layers, const prosim_
       if (int e = launch_kv(cur_x, n_dst, w, 0, 1, ws.kv, 0, st)) return e;
       kv = ws.kv;
     }
-    if (int e = launch_edge(ws.set[cur_set], kv, sd->graph, n_dst, ws.rbar, ws.aggv, ws.sk, ws.pw, ws.ft, st)) return e;
+    if (int e = launch_edge(ws.set[cur_set], kv, sd->graph, n_dst, ws.rbar, ws.aggv, ws.sk, ws.pw, ws.ft, ws.counter, st)) return e;
     const bool last = i == total - 1;
     const float* w_next = nullptr;
     if (!last) {

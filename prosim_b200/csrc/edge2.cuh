@@ -267,7 +267,8 @@ constexpr int GATHER_EB = 8;
 // Sk[row*stride + e][h] = sum_c q[row][h*16+c] * K'[nbr[e]][h*16+c]
 __global__ void __launch_bounds__(256) edge_qk_kernel(const float* __restrict__ Qg, const float* __restrict__ KV,
                                                       const int* __restrict__ nbr, const int* __restrict__ deg, int stride,
-                                                      int n_dst, float* __restrict__ Sk) {
+                                                      int n_dst, float* __restrict__ Sk, int* __restrict__ row_counter) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *row_counter = 0;   // dynamic row queue of the attn_edge4 launch that follows
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= n_dst) return;
   const int n_e = min(deg[row], stride);

@@ -77,7 +77,7 @@ template <int ZD, int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
     attn_edge4_kernel(const __grid_constant__ CUtensorMap tmZ, const float* __restrict__ Qhat, const float* __restrict__ Sk,
                       const int* __restrict__ deg, int stride, int n_dst, float* __restrict__ Rbar, float* __restrict__ Pw,
-                      float* __restrict__ Ft, int ft_tiles) {
+                      float* __restrict__ Ft, int ft_tiles, int* __restrict__ row_counter) {
   using C = Edge4Cfg<ZD>;
   constexpr int NSEG = C::NSEG;
   extern __shared__ uint8_t smem_raw[];
@@ -93,8 +93,20 @@ __global__ void __launch_bounds__(NW * 32, 1)
   __syncwarp();
 
   uint32_t phase = 0;
-  const int sw = lane & 7;
-  for (int row = blockIdx.x * NW + warp; row < n_dst; row += gridDim.x * NW) {
+  // swizzled byte offsets inside a tile: zoff[j] = 16-byte chunk j of this lane's row (score pass, lane = edge);
+  // coff[u] = this lane's feature column in edge u of a group of 8 (aggregation pass, lane = column)
+  uint32_t zoff[8], coff[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    zoff[j] = lane * 128 + ((j ^ (lane & 7)) << 4);
+    coff[j] = j * 128 + (((lane >> 2) ^ j) << 4) + (lane & 3) * 4;
+  }
+  // rows are handed out dynamically (row_counter is zeroed by edge_qk_kernel, which always runs first): a warp gets
+  // only 2-5 rows of 1-16 tiles each, so a static split leaves a quarter of the warps idle at the tail
+  int row = blockIdx.x * NW + warp;
+  int row_next = 0;
+  for (; row < n_dst; row = __shfl_sync(0xffffffffu, row_next, 0)) {
+    if (lane == 0) row_next = gridDim.x * NW + atomicAdd(row_counter, 1);   // consumed at the end of this row
     const int n_e = min(__ldg(deg + row), stride);
     const size_t ebase = (size_t)row * stride;
     float* rb = Rbar + (size_t)row * H * ZD;
@@ -153,16 +165,18 @@ __global__ void __launch_bounds__(NW * 32, 1)
       }
       // ---- scores: s_h += sum_d z[d] Qhat[h][d]; even / odd d accumulate in the two halves of an FFMA2
       if (valid) {
-        const uint8_t* zrow = zb + lane * 128;
-#pragma unroll 2
-        for (int d4 = 0; d4 < ZD / 4; ++d4) {
-          const float4 z4 = *reinterpret_cast<const float4*>(zrow + (d4 >> 3) * 4096 + (((d4 & 7) ^ sw) << 4));
-          const float2 zlo = make_float2(z4.x, z4.y), zhi = make_float2(z4.z, z4.w);
 #pragma unroll
-          for (int h = 0; h < H; ++h) {
-            const float4 q4 = *reinterpret_cast<const float4*>(qb + h * D + d4 * 4);
-            acc[h] = __ffma2_rn(zlo, make_float2(q4.x, q4.y), acc[h]);
-            acc[h] = __ffma2_rn(zhi, make_float2(q4.z, q4.w), acc[h]);
+        for (int sg = 0; sg < NSEG; ++sg) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 z4 = *reinterpret_cast<const float4*>(zb + sg * 4096 + zoff[j]);
+            const float2 zlo = make_float2(z4.x, z4.y), zhi = make_float2(z4.z, z4.w);
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+              const float4 q4 = *reinterpret_cast<const float4*>(qb + h * D + sg * 32 + j * 4);
+              acc[h] = __ffma2_rn(zlo, make_float2(q4.x, q4.y), acc[h]);
+              acc[h] = __ffma2_rn(zhi, make_float2(q4.z, q4.w), acc[h]);
+            }
           }
         }
       }
@@ -201,13 +215,10 @@ __global__ void __launch_bounds__(NW * 32, 1)
       }
       __syncwarp();
       // ---- aggregation, lane = feature column of each segment, edges of the tile in ascending order
-      const uint8_t* zcol = zb + (lane & 3) * 4;
-      const int c16 = lane >> 2;
-#pragma unroll 4
-      for (int e = 0; e < nt; ++e) {
+      auto agg_edge = [&](int e, int u) {
         const float4 pa = *reinterpret_cast<const float4*>(pb + e * 8);
         const float4 pq = *reinterpret_cast<const float4*>(pb + e * 8 + 4);
-        const uint8_t* ze = zcol + e * 128 + ((c16 ^ (e & 7)) << 4);
+        const uint8_t* ze = zb + (e - u) * 128 + coff[u];
 #pragma unroll
         for (int c = 0; c < NSEG; ++c) {
           const float zv = *reinterpret_cast<const float*>(ze + c * 4096);
@@ -217,7 +228,15 @@ __global__ void __launch_bounds__(NW * 32, 1)
           r45[c] = __ffma2_rn(zz, make_float2(pq.x, pq.y), r45[c]);
           r67[c] = __ffma2_rn(zz, make_float2(pq.z, pq.w), r67[c]);
         }
+      };
+      const int full = nt & ~7;
+      for (int e0 = 0; e0 < full; e0 += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) agg_edge(e0 + u, u);
       }
+#pragma unroll
+      for (int u = 0; u < 7; ++u)
+        if (full + u < nt) agg_edge(full + u, u);
     }
 
     // ---- row epilogue: 1 / (sum + 1e-16), Rbar, and the per-tile factors exp(m_tile - m_final) / (sum + 1e-16)
