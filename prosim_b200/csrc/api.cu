@@ -10,6 +10,7 @@
 #include "pointnet.cuh"
 #include "rollout.cuh"
 #include "tc_gemm.cuh"
+#include "tc_post.cuh"
 #include "weights_layout.h"
 
 #include <cudaTypedefs.h>
@@ -18,6 +19,7 @@ using namespace prosim;
 
 namespace {
 
+bool g_use_tc = false;  // node-side GEMMs on tcgen05 (tc_post.cuh); prosim_set_tensor_core(0) selects the FFMA kernels
 constexpr int ERR_ARG = -1;
 constexpr int ERR_WORKSPACE = -2;
 
@@ -98,6 +100,7 @@ int setup_attributes() {
   acc(allow_smem(attn_dstpre2_kernel<4, 8>, Pre2Smem<4, 8>::bytes));
   acc(allow_smem(attn_dstpre2_kernel<8, 8>, Pre2Smem<8, 8>::bytes));
   acc(allow_smem(attn_post2_kernel<4, 8>, Post2Smem<4, 8>::bytes));
+  acc(allow_smem(tcp::attn_post_tc_kernel, tcp::SMEM_BYTES));
   state = e == cudaSuccess ? 1 : (int)e + 1000;
   return e == cudaSuccess ? 0 : (int)e;
 }
@@ -260,6 +263,12 @@ int launch_post(const float* x, int n, int zd, const float* rbar, const float* a
   if (n <= 0) return 0;
   const int rpt = pick_rpt(n);
   LaunchScope ls(PROSIM_K_ATTN_POST, st);
+  if (pick_rt(n) != 0 && g_use_tc) {
+    tcp::attn_post_tc_kernel<<<(n + 127) / 128, tcp::THREADS, tcp::SMEM_BYTES, st>>>(x, n, zd, rbar, aggv, cur.s, cur.gx, w, out,
+                                                                                 w_next, nxt.q, nxt.qhat, nxt.s, nxt.gx);
+    PROSIM_CHECK_LAUNCH();
+    return 0;
+  }
   if (pick_rt(n) != 0 && zd == 96) {
     attn_post2_kernel<4, 8><<<(n + 31) / 32, 256, Post2Smem<4, 8>::bytes, st>>>(x, n, zd, rbar, aggv, cur.s, cur.gx, w, out, w_next,
                                                                          nxt.q, nxt.qhat, nxt.s, nxt.gx);
@@ -276,7 +285,11 @@ int launch_post(const float* x, int n, int zd, const float* rbar, const float* a
 
 extern "C" {
 
-int prosim_abi_version(void) { return 4; }
+int prosim_abi_version(void) { return 5; }
+int prosim_set_tensor_core(int on) {
+  g_use_tc = on != 0;
+  return 0;
+}
 
 long long prosim_launch_count(int kernel_class) {
   if (kernel_class >= 0 && kernel_class < N_CLASSES) return g_launches[kernel_class];

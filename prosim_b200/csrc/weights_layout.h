@@ -40,7 +40,22 @@ constexpr int W2T = B1 + 512;            // [512 k][128 n]
 constexpr int B2 = W2T + 65536;
 constexpr int LN_FFPOST_G = B2 + 128;
 constexpr int LN_FFPOST_B = LN_FFPOST_G + 128;
-constexpr int SIZE = LN_FFPOST_B + 128;
+constexpr int FP32_SIZE = LN_FFPOST_B + 128;
+// ---- tensor-core operand copies of the dense weights (tc_post.cuh): every [N][K] B-operand chunk is stored as
+// tf32 "hi" then tf32 "lo" (hi = rna_tf32(w), lo = rna_tf32(w - hi)), each in the tcgen05 K-major no-swizzle
+// core-matrix order  idx(n, k) = (n / 8) * (8 K) + (k / 4) * 32 + (n % 8) * 4 + k % 4,  chunks in the order the
+// kernel's MMA warp consumes them, so the producer warp streams the block with plain bulk copies.
+constexpr int TC_VR96 = FP32_SIZE;             // 8 heads x [16 c][96 d]   (WVRG96T columns of the head)
+constexpr int TC_VR128 = TC_VR96 + 8 * 3072;   // 8 heads x [16 c][128 d]  (WVRGT)
+constexpr int TC_GA = TC_VR128 + 8 * 4096;     // 4 k-chunks x [128 n][32 k]
+constexpr int TC_O = TC_GA + 4 * 8192;         // 4 k-chunks x [128 n][32 k]
+constexpr int TC_FF = TC_O + 4 * 8192;         // up_0, then (up_{j+1}, down_j) for j = 0..14, down_15:
+                                               //   up_j = W1 rows 32j..32j+31 [32 n][128 k], down_j = W2[:, 32j..] [128 n][32 k]
+constexpr int TC_Q = TC_FF + 32 * 8192;        // 4 k-chunks each: to_q (pre-scaled), to_s, to_g[x part]
+constexpr int TC_S = TC_Q + 4 * 8192;
+constexpr int TC_GX = TC_S + 4 * 8192;
+constexpr int TC_KRG = TC_GX + 4 * 8192;       // 8 heads x [128 d][16 c]  (WKRG rows of the head, transposed)
+constexpr int SIZE = TC_KRG + 8 * 4096;
 }  // namespace aw
 
 namespace pw {  // PointNet polyline encoder (scene_encoder/pointnet_encoder.py:13-62)

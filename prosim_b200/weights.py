@@ -142,8 +142,10 @@ def param_shapes_cache(goal_condition):
 
 
 # ----------------------------------------------------------------------------- packing (mirror of csrc/weights_layout.h)
-ATTN_LAYER_FLOATS = 512 + 3 * (16384 + 128) + 2 * 16384 + 12288 + (16384 + 128) + (2 * 16384 + 128) + (16384 + 128) + 512 \
+ATTN_FP32_FLOATS = 512 + 3 * (16384 + 128) + 2 * 16384 + 12288 + (16384 + 128) + (2 * 16384 + 128) + (16384 + 128) + 512 \
     + (65536 + 512) + (65536 + 128) + 256
+ATTN_TC_FLOATS = 8 * 3072 + 8 * 4096 + 2 * 4 * 8192 + 32 * 8192 + 3 * 4 * 8192 + 8 * 4096
+ATTN_LAYER_FLOATS = ATTN_FP32_FLOATS + ATTN_TC_FLOATS
 POINTNET_FLOATS = (24 * 128 + 384) + (16384 + 384) + (16384 + 128) + (2 * 16384 + 384) + (16384 + 128) + 2 * (16384 + 128)
 _MLP3_FLOATS = 2 * (16384 + 384) + (64 * 128 + 128)
 HEAD_FLOATS = 3 * 128 + 3 * (16384 + 384) + 2 * _MLP3_FLOATS
@@ -159,6 +161,47 @@ def _fold96(wvrgt):
     rows are summed once here instead of per edge."""
     out = wvrgt[:96].clone()
     out[64:96] += wvrgt[96:128]
+    return out
+
+
+def _tf32_rna(x):
+    """cvt.rna.tf32.f32: round the fp32 mantissa to 10 bits, ties away from zero (the low 13 bits end up zero)."""
+    b = x.contiguous().view(torch.int32)
+    return ((b + 0x1000) & -8192).view(torch.float32)
+
+
+def _umma_chunk(b):
+    """[N][K] fp32 B operand -> flat [hi | lo], each in the tcgen05 K-major no-swizzle core-matrix order
+    idx(n, k) = (n // 8) * 8K + (k // 4) * 32 + (n % 8) * 4 + k % 4   (weights_layout.h, aw::TC_*)."""
+    b = b.contiguous().float()
+    n, k = b.shape
+    hi = _tf32_rna(b)
+    lo = _tf32_rna(b - hi)
+    lay = lambda m: m.reshape(n // 8, 8, k // 4, 4).permute(0, 2, 1, 3).contiguous().reshape(-1)
+    return torch.cat([lay(hi), lay(lo)])
+
+
+def _pack_attn_tc(wqt, wkrg, wvrgt, wvrg96t, wst, wgat, wgxt, wot, w1t, w2t):
+    """Tensor-core operand block of one layer from the fp32-rounded K-major weights the FFMA kernels use."""
+    f = lambda x: x.float()
+    wqt, wkrg, wvrgt, wvrg96t, wst, wgat, wgxt, wot, w1t, w2t = map(f, (wqt, wkrg, wvrgt, wvrg96t, wst, wgat, wgxt, wot,
+                                                                       w1t, w2t))
+    out = []
+    out += [_umma_chunk(wvrg96t[:, h * 16:(h + 1) * 16].t()) for h in range(HEADS)]
+    out += [_umma_chunk(wvrgt[:, h * 16:(h + 1) * 16].t()) for h in range(HEADS)]
+    kchunks = lambda wt: [_umma_chunk(wt.t()[:, 32 * c:32 * c + 32]) for c in range(4)]
+    out += kchunks(wgat) + kchunks(wot)
+    w1, w2 = w1t.t(), w2t.t()                         # [512][128], [128][512]
+    up = lambda j: _umma_chunk(w1[32 * j:32 * j + 32, :])
+    down = lambda j: _umma_chunk(w2[:, 32 * j:32 * j + 32])
+    out.append(up(0))
+    for j in range(15):
+        out += [up(j + 1), down(j)]
+    out.append(down(15))
+    out += kchunks(wqt) + kchunks(wst) + kchunks(wgxt)
+    out += [_umma_chunk(wkrg[h * 16:(h + 1) * 16, :].t()) for h in range(HEADS)]
+    out = torch.cat(out)
+    assert out.numel() == ATTN_TC_FLOATS
     return out
 
 
@@ -187,9 +230,11 @@ def pack_attn_layer(sd, p):
         w('ff_mlp.3.weight').t(), w('ff_mlp.3.bias'),
         w('ff_postnorm.weight'), w('ff_postnorm.bias'),
     ]
+    tc = _pack_attn_tc(wqt=parts[4], wkrg=parts[10], wvrgt=parts[11], wvrg96t=parts[12], wst=parts[13], wgat=parts[15],
+                       wgxt=parts[16], wot=parts[18], w1t=parts[24], w2t=parts[26])
     out = torch.cat([x.contiguous().reshape(-1) for x in parts]).float()
-    assert out.numel() == ATTN_LAYER_FLOATS
-    return out
+    assert out.numel() == ATTN_FP32_FLOATS
+    return torch.cat([out, tc])
 
 
 def _pad_rows(wt, rows):
