@@ -144,14 +144,14 @@ def run_reference(a):
 
 # ----------------------------------------------------------------------------------------------- B200 arm
 def edge_kernel_bytes(edge_log):
-    """Algorithmic HBM bytes of all attn_edge3 launches of one forward: per edge 384 B of z (read once),
-    32 B of q.K' scores in, 32 B of attention weights out and their 64 B in-place rescale; per destination row 4 KB of
-    Qhat in and 3 KB of Rbar out."""
+    """Algorithmic HBM bytes of all attn_edge4 launches of one forward: per edge 384 B of z (read once),
+    32 B of q.K' scores in, 32 B of unnormalised attention weights out; per destination row 4 KB of Qhat in, 3 KB of
+    Rbar out and 32 B of softmax factors per 32-edge tile."""
     total_edges, total_bytes, launches = 0, 0.0, 0
     for kind, esum, n_dst, n_layers in edge_log:
         e = int(esum)
         total_edges += e * n_layers
-        total_bytes += n_layers * (e * (384 + 32 + 32 + 64) + n_dst * (8 * 128 * 4 + 8 * 96 * 4))
+        total_bytes += n_layers * (e * (384 + 32 + 32) + n_dst * (8 * 128 * 4 + 8 * 96 * 4) + e)
         launches += n_layers
     return total_edges, total_bytes, launches
 
@@ -290,20 +290,20 @@ def run_b200(a):
         sm_mhz = peaks.get('sm_max_mhz', 1965.0)
         ffma_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
         if edge_n > 0:
-            # dominant kernel by time: attn_edge3_kernel (z streaming + per-edge 8x96 contractions).  Arithmetic intensity
-            # 3.1 kFLOP / 512 B = 6 FLOP/B is below the fp32 machine balance (11 FLOP/B): HBM is its roofline.
+            # attn_edge4_kernel (z streaming + per-edge 8x96 contractions).  Arithmetic intensity
+            # 3.1 kFLOP / 448 B = 7 FLOP/B is below the fp32 machine balance (11 FLOP/B): HBM is its roofline.
             n_edges, n_bytes, n_launch = edge_kernel_bytes(edge_log)
             avg_ms = edge_ms / edge_n
             achieved = n_bytes / n_launch / (avg_ms * 1e-3) / 1e9
             hbm_peak = peaks.get('hbm_gbs') or 6650.0
-            roof = {'kernel': 'attn_edge3_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
+            roof = {'kernel': 'attn_edge4_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
                     'frac': achieved / hbm_peak,
                     'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6.65 TB/s',
                     'traffic': None, 'avg_launch_ms': avg_ms, 'launches_timed': edge_n,
                     'algorithmic_bytes_per_launch': n_bytes / n_launch, 'edges_per_forward': n_edges,
                     'share_of_step': edge_ms / total_ms if world == 1 else None,
                     'fp32_ffma_frac': (n_edges * 3072.0 / n_launch) / (avg_ms * 1e-3) / 1e12 / ffma_peak,
-                    'note': 'latency/issue bound today (profiles/): 12 warps per SM, see DESIGN.md section 5'}
+                    'note': 'one warp per row, z tiles by TMA; issue/latency bound at 12 warps per SM (profiles/), DESIGN.md section 5'}
         roof2 = None
         if post_n > 0:
             avg_ms = post_ms / post_n
@@ -315,13 +315,15 @@ def run_b200(a):
             flops_per_launch = algorithmic_flops_post(rows_sum / n_launch_step)
             achieved = flops_per_launch / (avg_ms * 1e-3) / 1e12
             tensor_peak = peaks.get('bf16_tflops_sustained') or 1400.0
-            roof2 = {'kernel': 'attn_post2_kernel', 'bound': 'tensor', 'achieved': achieved, 'peak': tensor_peak,
+            roof2 = {'kernel': 'attn_post_tc_kernel', 'bound': 'tensor', 'achieved': achieved, 'peak': tensor_peak,
                     'unit': 'TFLOP/s', 'frac': achieved / tensor_peak,
                     'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)'
                     if peaks else 'fallback 1.4 PFLOP/s',
                     'traffic': None,
-                    'fp32_ffma': {'peak': ffma_peak, 'frac': achieved / ffma_peak,
-                                  'note': 'kernel runs IEEE fp32 FFMA on CUDA cores; nominal 148 SM x 128 lanes x 2 x max clock'},
+                    'note': 'tcgen05 kind::tf32, 3 MMAs per product (3xTF32 = fp32-class accuracy): the usable peak is 1/6 of '
+                            'the bf16 figure, and a 4096-row launch fills 32 of 148 SMs (DESIGN.md section 5)',
+                    'fp32_ffma_equiv': {'peak': ffma_peak, 'frac': achieved / ffma_peak,
+                                        'note': 'against the fp32 FFMA peak the previous CUDA-core kernel was bound by'},
                     'avg_launch_ms': avg_ms, 'launches_timed': post_n, 'share_of_step': post_ms / t_extra
                     if world == 1 else None}
         cpu = None

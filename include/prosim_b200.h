@@ -50,6 +50,9 @@ int prosim_abi_version(void);
 /* Node-side GEMMs of the AttentionLayer: 1 (default) = tcgen05 / TMEM 3xTF32 kernel (csrc/tc_post.cuh) for launches
  * of >= 1024 rows, 0 = fp32 FFMA kernels everywhere (A/B measurement and parity cross-checks). */
 int prosim_set_tensor_core(int on);
+/* Measurement support: SM-clock timestamps of the phases of CTA 0 of the last tcgen05 node-kernel launch
+ * ([0..15] epilogue thread, [16..31] MMA thread; csrc/tc_post.cuh TCP_MARK). */
+int prosim_tc_debug_read(long long* out32);
 
 /* Launch accounting and optional per-kernel CUDA-event timing (measurement support for bench.py; not part of
  * the data path).  kernel_class < 0 in prosim_launch_count = all classes; prosim_profile_enable(-1) disables. */

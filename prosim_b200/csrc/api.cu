@@ -19,7 +19,7 @@ using namespace prosim;
 
 namespace {
 
-bool g_use_tc = false;  // node-side GEMMs on tcgen05 (tc_post.cuh); prosim_set_tensor_core(0) selects the FFMA kernels
+bool g_use_tc = true;   // node-side GEMMs on tcgen05 (tc_post.cuh); prosim_set_tensor_core(0) selects the FFMA kernels
 constexpr int ERR_ARG = -1;
 constexpr int ERR_WORKSPACE = -2;
 
@@ -194,18 +194,47 @@ PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
   return fn;
 }
 
-// z as a 2-D tensor [rows][zd] of fp32, fetched in boxes of 8 rows x 32 floats (1 KB) with the 128-byte swizzle
-int make_z_map(CUtensorMap* tm, const float* z, size_t rows, int zd) {
+// a row-major fp32 matrix [rows][cols] as a 2-D tensor fetched in boxes of box_rows x 32 floats with the 128-byte swizzle
+int make_map2d(CUtensorMap* tm, const float* base, size_t rows, int cols, int box_rows) {
   PFN_cuTensorMapEncodeTiled_v12000 enc = tensor_map_encoder();
   if (!enc) return ERR_ARG - 10;
-  const cuuint64_t dims[2] = {(cuuint64_t)zd, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)zd * sizeof(float)};
-  const cuuint32_t box[2] = {32, 8};
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+  const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(z), dims, strides, box, estr,
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : ERR_ARG - 11;
+}
+// z of a graph: [n_dst * stride][zd], boxes of 8 edges (edge4.cuh)
+int make_z_map(CUtensorMap* tm, const float* z, size_t rows, int zd) { return make_map2d(tm, z, rows, zd, 8); }
+
+// Tensor maps of the node kernel's [n][cols] row buffers (128-row boxes).  The buffers are a handful of workspace
+// pointers that recur every layer and every forward, so encoded maps are kept in a small table.
+struct MapEntry {
+  const float* base;
+  size_t rows;
+  int cols;
+  CUtensorMap tm;
+};
+int cached_map128(CUtensorMap* out, const float* base, size_t rows, int cols) {
+  constexpr int CAP = 64;
+  static MapEntry table[CAP];
+  static int used = 0, next = 0;
+  for (int i = 0; i < used; ++i)
+    if (table[i].base == base && table[i].rows == rows && table[i].cols == cols) {
+      *out = table[i].tm;
+      return 0;
+    }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || rows == 0 || rows > 0x7fffffffull) return ERR_ARG;
+  MapEntry& e = table[next];
+  if (int err = make_map2d(&e.tm, base, rows, cols, 128)) return err;
+  e.base = base; e.rows = rows; e.cols = cols;
+  *out = e.tm;
+  next = (next + 1) % CAP;
+  if (used < CAP) ++used;
+  return 0;
 }
 
 template <int ZD, int NW>
@@ -264,8 +293,15 @@ int launch_post(const float* x, int n, int zd, const float* rbar, const float* a
   const int rpt = pick_rpt(n);
   LaunchScope ls(PROSIM_K_ATTN_POST, st);
   if (pick_rt(n) != 0 && g_use_tc) {
-    tcp::attn_post_tc_kernel<<<(n + 127) / 128, tcp::THREADS, tcp::SMEM_BYTES, st>>>(x, n, zd, rbar, aggv, cur.s, cur.gx, w, out,
-                                                                                 w_next, nxt.q, nxt.qhat, nxt.s, nxt.gx);
+    alignas(64) tcp::Maps m;
+    const bool nx = w_next != nullptr;
+    int e = 0;
+    auto mk = [&](CUtensorMap* tm, const float* p, int cols) { if (!e) e = cached_map128(tm, p, (size_t)n, cols); };
+    mk(&m.rbar, rbar, H * zd); mk(&m.aggv, aggv, D); mk(&m.s, cur.s, D); mk(&m.gx, cur.gx, D); mk(&m.x, x, D); mk(&m.out, out, D);
+    mk(&m.q_n, nx ? nxt.q : out, D); mk(&m.s_n, nx ? nxt.s : out, D); mk(&m.gx_n, nx ? nxt.gx : out, D);
+    mk(&m.qhat_n, nx ? nxt.qhat : out, nx ? H * D : D);
+    if (e) return e;
+    tcp::attn_post_tc_kernel<<<(n + 127) / 128, tcp::THREADS, tcp::SMEM_BYTES, st>>>(m, n, zd, w, w_next);
     PROSIM_CHECK_LAUNCH();
     return 0;
   }
@@ -286,6 +322,10 @@ int launch_post(const float* x, int n, int zd, const float* rbar, const float* a
 extern "C" {
 
 int prosim_abi_version(void) { return 5; }
+int prosim_tc_debug_read(long long* out32) {
+  if (!out32) return ERR_ARG;
+  return (int)cudaMemcpyFromSymbol(out32, tcp::g_tcp_dbg, 32 * sizeof(long long));
+}
 int prosim_set_tensor_core(int on) {
   g_use_tc = on != 0;
   return 0;

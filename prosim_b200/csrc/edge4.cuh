@@ -46,11 +46,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   } while (!done);
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+// L2 policy for data that is read exactly once (the z stream): do not let it push the layer's reusable buffers
+// (K'|V', Rbar, Qhat, the packed weights) out of the 126 MB L2
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
 // one [8 rows x 32 floats] box of the z tensor (128B swizzle) -> 1 KB of shared memory
-__device__ __forceinline__ void tma_box(uint32_t dst, const CUtensorMap* tm, int col, int row, uint32_t bar) {
+__device__ __forceinline__ void tma_box(uint32_t dst, const CUtensorMap* tm, int col, int row, uint32_t bar, uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
-      "l"(tm), "r"(col), "r"(row), "r"(bar)
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], "
+      "[%4], %5;\n" ::"r"(dst),
+      "l"(tm), "r"(col), "r"(row), "r"(bar), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ void bulk_copy(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -93,6 +101,7 @@ __global__ void __launch_bounds__(NW * 32, 1)
   __syncwarp();
 
   uint32_t phase = 0;
+  const uint64_t z_policy = e4::policy_evict_first();
   // swizzled byte offsets inside a tile: zoff[j] = 16-byte chunk j of this lane's row (score pass, lane = edge);
   // coff[u] = this lane's feature column in edge u of a group of 8 (aggregation pass, lane = column)
   uint32_t zoff[8], coff[8];
@@ -136,7 +145,7 @@ __global__ void __launch_bounds__(NW * 32, 1)
       if (lane < nbox) {
         e4::fence_proxy_async();
         const int g = lane / NSEG, sg = lane % NSEG;
-        e4::tma_box(zb_s + sg * 4096 + g * 1024, &tmZ, sg * 32, (int)(ebase + t0 + g * 8), bar);
+        e4::tma_box(zb_s + sg * 4096 + g * 1024, &tmZ, sg * 32, (int)(ebase + t0 + g * 8), bar, z_policy);
       } else if (t == 0 && lane == 31) {
         e4::fence_proxy_async();
         e4::bulk_copy(qb_s, Qhat + (size_t)row * H * D, C::QBYTES, bar);

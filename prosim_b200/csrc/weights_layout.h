@@ -49,7 +49,7 @@ constexpr int TC_VR96 = FP32_SIZE;             // 8 heads x [16 c][96 d]   (WVRG
 constexpr int TC_VR128 = TC_VR96 + 8 * 3072;   // 8 heads x [16 c][128 d]  (WVRGT)
 constexpr int TC_GA = TC_VR128 + 8 * 4096;     // 4 k-chunks x [128 n][32 k]
 constexpr int TC_O = TC_GA + 4 * 8192;         // 4 k-chunks x [128 n][32 k]
-constexpr int TC_FF = TC_O + 4 * 8192;         // up_0, then (up_{j+1}, down_j) for j = 0..14, down_15:
+constexpr int TC_FF = TC_O + 4 * 8192;         // up_0, up_1, then (up_{j+2}, down_j) for j = 0..13, down_14, down_15:
                                                //   up_j = W1 rows 32j..32j+31 [32 n][128 k], down_j = W2[:, 32j..] [128 n][32 k]
 constexpr int TC_Q = TC_FF + 32 * 8192;        // 4 k-chunks each: to_q (pre-scaled), to_s, to_g[x part]
 constexpr int TC_S = TC_Q + 4 * 8192;

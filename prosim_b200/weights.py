@@ -194,10 +194,10 @@ def _pack_attn_tc(wqt, wkrg, wvrgt, wvrg96t, wst, wgat, wgxt, wot, w1t, w2t):
     w1, w2 = w1t.t(), w2t.t()                         # [512][128], [128][512]
     up = lambda j: _umma_chunk(w1[32 * j:32 * j + 32, :])
     down = lambda j: _umma_chunk(w2[:, 32 * j:32 * j + 32])
-    out.append(up(0))
-    for j in range(15):
-        out += [up(j + 1), down(j)]
-    out.append(down(15))
+    out += [up(0), up(1)]                             # consumption order of the MMA warp (tc_post.cuh)
+    for j in range(14):
+        out += [up(j + 2), down(j)]
+    out += [down(14), down(15)]
     out += kchunks(wqt) + kchunks(wst) + kchunks(wgxt)
     out += [_umma_chunk(wkrg[h * 16:(h + 1) * 16, :].t()) for h in range(HEADS)]
     out = torch.cat(out)

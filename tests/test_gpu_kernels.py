@@ -178,8 +178,19 @@ def test_attention_layer_matches_oracle(ctx, bipartite, n_dst):
     assert (out - ref).abs().max() < 2e-5
 
 
-def test_attention_stack_matches_oracle(ctx):
-    """6 x (a2p, m2p) with fixed sources -- the policy tick's core -- and 3 x self-source layers."""
+@pytest.mark.parametrize('tensor_core', [True, False])
+def test_attention_stack_matches_oracle(ctx, tensor_core):
+    """6 x (a2p, m2p) with fixed sources -- the policy tick's core -- and 3 x self-source layers; with the tcgen05 node
+    kernel (3xTF32, activations in TMEM) and with the FFMA node kernels."""
+    from prosim_b200 import lib
+    lib.set_tensor_core(tensor_core)
+    try:
+        _attention_stack_case(ctx, 1e-4 if tensor_core else 5e-5, 4e-5 if tensor_core else 2e-5)
+    finally:
+        lib.set_tensor_core(True)
+
+
+def _attention_stack_case(ctx, tol12, tol3):
     ops, orc = ctx['ops'], ctx['oracle']
     g = torch.Generator().manual_seed(13)
     P, NA, NM, sa, sm = 1100, 1064, 8150, 30, 50    # >= 1024 rows: the gemm_tile (v2) kernels run
@@ -203,7 +214,9 @@ def test_attention_stack_matches_oracle(ctx):
     kv_m = ops.attn_kv(x_m.cuda(), ar, off['pol_m2p'], 6, lf)
     out = ops.attn_stack(x_p.cuda(), 6, ops.stack_side(ar, off['pol_a2p'], e_a, kv_a),
                          ops.stack_side(ar, off['pol_m2p'], e_m, kv_m)).cpu()
-    assert (out - ref).abs().max() < 5e-5       # 12 layers deep
+    err = float((out - ref).abs().max())
+    print('12-layer stack max err', err, 'of max |ref|', float(ref.abs().max()))
+    assert err < tol12       # 12 layers deep (measured on B200: 5.6e-5 with 3xTF32 tensor-core GEMMs, below 5e-5 with FFMA)
 
     nbr_s, deg_s, js, ei_s = _random_graph(g, P, P, sa)
     r_s = torch.randn(ei_s.shape[1], 128, generator=g)
@@ -212,7 +225,7 @@ def test_attention_stack_matches_oracle(ctx):
     for i in range(3):
         ref = orc.attention_layer(f'{ct}.{i}', ref, ref, r_s, ei_s, False)
     out = ops.attn_stack(x_p.cuda(), 3, ops.stack_side(ar, off['cond_attn'], edges(nbr_s, deg_s, js, r_s, sa))).cpu()
-    assert (out - ref).abs().max() < 2e-5
+    assert (out - ref).abs().max() < tol3
 
 
 # ------------------------------------------------------------------------------------ heads
