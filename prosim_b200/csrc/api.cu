@@ -19,6 +19,7 @@ using namespace prosim;
 
 namespace {
 
+int g_split = 2;        // row-split chains of prosim_attn_stack_fwd (prosim_set_stack_split)
 bool g_use_tc = true;   // node-side GEMMs on tcgen05 (tc_post.cuh); prosim_set_tensor_core(0) selects the FFMA kernels
 constexpr int ERR_ARG = -1;
 constexpr int ERR_WORKSPACE = -2;
@@ -326,6 +327,11 @@ int prosim_tc_debug_read(long long* out32) {
   if (!out32) return ERR_ARG;
   return (int)cudaMemcpyFromSymbol(out32, tcp::g_tcp_dbg, 32 * sizeof(long long));
 }
+int prosim_set_stack_split(int parts) {
+  if (parts < 1 || parts > 4) return ERR_ARG;
+  g_split = parts;
+  return 0;
+}
 int prosim_set_tensor_core(int on) {
   g_use_tc = on != 0;
   return 0;
@@ -469,6 +475,91 @@ int prosim_attn_layer_fwd(const float* x_src, int n_src, const float* x_dst, int
   return launch_post(x_dst, n_dst, g->zd, ws.rbar, ws.aggv, ws.set[0], w, out, nullptr, ws.set[1], st);
 }
 
+// One chain of n_layers x (side A [, side B]) over destination rows [r0, r0 + n): every array of the workspace, of the
+// graphs and of x / out is row indexed, so a row range is just an offset.
+static int run_stack_rows(const float* x, int r0, int n, int n_layers, const prosim_stack_side_t* side_a,
+                          const prosim_stack_side_t* side_b, const StackWs& ws_all, float* out, int part, cudaStream_t st) {
+  auto rows = [&](float* p, size_t per_row) { return p + (size_t)r0 * per_row; };
+  const int max_stride = side_b && side_b->graph.stride > side_a->graph.stride ? side_b->graph.stride : side_a->graph.stride;
+  StackWs ws = ws_all;
+  for (int i = 0; i < 2; ++i) {
+    ws.set[i].q = rows(ws_all.set[i].q, D);
+    ws.set[i].qhat = rows(ws_all.set[i].qhat, H * D);
+    ws.set[i].s = rows(ws_all.set[i].s, D);
+    ws.set[i].gx = rows(ws_all.set[i].gx, D);
+  }
+  ws.rbar = rows(ws_all.rbar, H * D);
+  ws.aggv = rows(ws_all.aggv, D);
+  ws.x0 = rows(ws_all.x0, D);
+  ws.x1 = rows(ws_all.x1, D);
+  ws.sk = rows(ws_all.sk, (size_t)max_stride * 8);
+  ws.pw = rows(ws_all.pw, (size_t)max_stride * 8);
+  ws.ft = rows(ws_all.ft, (size_t)((max_stride + 31) / 32) * 8);
+  ws.counter = ws_all.counter + part;
+  const prosim_stack_side_t* sides[2] = {side_a, side_b};
+  prosim_graph_t g[2];
+  const int n_sides = side_b ? 2 : 1;
+  for (int i = 0; i < n_sides; ++i) {
+    g[i] = sides[i]->graph;
+    g[i].z += (size_t)r0 * g[i].stride * g[i].zd;
+    g[i].nbr += (size_t)r0 * g[i].stride;
+    g[i].deg += r0;
+  }
+  const int total = n_layers * n_sides;
+  // x buffers: input -> x0 -> x1 -> x0 ... ; the last layer writes `out`
+  const float* cur_x = x + (size_t)r0 * D;
+  float* out_rows = out + (size_t)r0 * D;
+  int cur_set = 0;
+  if (int e = launch_dstpre(cur_x, n, side_a->w, ws.set[cur_set], st)) return e;
+  for (int i = 0; i < total; ++i) {
+    const int l = i / n_sides;
+    const prosim_stack_side_t* sd = sides[i % n_sides];
+    const float* w = sd->w + (size_t)l * aw::SIZE;
+    const float* kv;
+    if (sd->kv) {
+      kv = sd->kv + (size_t)l * sd->kv_layer_stride;
+    } else {   // self-source layer (never split: r0 == 0 and n == all rows)
+      if (int e = launch_kv(cur_x, n, w, 0, 1, ws.kv, 0, st)) return e;
+      kv = ws.kv;
+    }
+    if (int e = launch_edge(ws.set[cur_set], kv, g[i % n_sides], n, ws.rbar, ws.aggv, ws.sk, ws.pw, ws.ft, ws.counter, st)) return e;
+    const bool last = i == total - 1;
+    const float* w_next = nullptr;
+    if (!last) {
+      const int ni = i + 1;
+      w_next = sides[ni % n_sides]->w + (size_t)(ni / n_sides) * aw::SIZE;
+    }
+    float* dst_x = last ? out_rows : (cur_x == ws.x0 ? ws.x1 : ws.x0);
+    if (int e = launch_post(cur_x, n, sd->graph.zd, ws.rbar, ws.aggv, ws.set[cur_set], w, dst_x, w_next, ws.set[cur_set ^ 1], st))
+      return e;
+    cur_x = dst_x;
+    cur_set ^= 1;
+  }
+  return 0;
+}
+
+// Side streams for the row-split schedule (one set per device, created on first use)
+struct SplitStreams {
+  cudaStream_t st[3];
+  cudaEvent_t fork, join[3];
+  bool ok;
+};
+static SplitStreams* split_streams() {
+  static SplitStreams per_dev[16];
+  static bool made[16] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  SplitStreams& s = per_dev[dev];
+  if (!made[dev]) {
+    made[dev] = true;
+    s.ok = cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 3 && s.ok; ++i)
+      s.ok = cudaStreamCreateWithFlags(&s.st[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&s.join[i], cudaEventDisableTiming) == cudaSuccess;
+  }
+  return s.ok ? &s : nullptr;
+}
+
 int prosim_attn_stack_fwd(const float* x, int n_dst, int n_layers, const prosim_stack_side_t* side_a,
                           const prosim_stack_side_t* side_b, float* workspace, size_t workspace_floats, float* out,
                           prosim_stream_t stream) {
@@ -481,38 +572,34 @@ int prosim_attn_stack_fwd(const float* x, int n_dst, int n_layers, const prosim_
   if (int e = setup_attributes()) return e;
   cudaStream_t st = S(stream);
   StackWs ws = carve(workspace, n_dst, max_stride);
-  const prosim_stack_side_t* sides[2] = {side_a, side_b};
-  const int n_sides = side_b ? 2 : 1;
-  const int total = n_layers * n_sides;
-  // x buffers: input -> x0 -> x1 -> x0 ... ; the last layer writes `out`
-  const float* cur_x = x;
-  int cur_set = 0;
-  if (int e = launch_dstpre(cur_x, n_dst, side_a->w, ws.set[cur_set], st)) return e;
-  for (int i = 0; i < total; ++i) {
-    const int l = i / n_sides;
-    const prosim_stack_side_t* sd = sides[i % n_sides];
-    const float* w = sd->w + (size_t)l * aw::SIZE;
-    const float* kv;
-    if (sd->kv) {
-      kv = sd->kv + (size_t)l * sd->kv_layer_stride;
-    } else {
-      if (int e = launch_kv(cur_x, n_dst, w, 0, 1, ws.kv, 0, st)) return e;
-      kv = ws.kv;
-    }
-    if (int e = launch_edge(ws.set[cur_set], kv, sd->graph, n_dst, ws.rbar, ws.aggv, ws.sk, ws.pw, ws.ft, ws.counter, st)) return e;
-    const bool last = i == total - 1;
-    const float* w_next = nullptr;
-    if (!last) {
-      const int ni = i + 1;
-      w_next = sides[ni % n_sides]->w + (size_t)(ni / n_sides) * aw::SIZE;
-    }
-    float* dst_x = last ? out : (cur_x == ws.x0 ? ws.x1 : ws.x0);
-    if (int e = launch_post(cur_x, n_dst, sd->graph.zd, ws.rbar, ws.aggv, ws.set[cur_set], w, dst_x, w_next, ws.set[cur_set ^ 1], st))
-      return e;
-    cur_x = dst_x;
-    cur_set ^= 1;
+  // Row-split schedule: with fixed sources (K'|V' precomputed) the destination rows never interact, so the stack is
+  // run as up to g_split independent chains of >= 1024 rows (multiples of 128: identical tiles, bit-identical
+  // results) on side streams.  The tcgen05 node kernel occupies one SM per 128 rows -- alone it leaves 3/4 of the chip
+  // idle -- and the chains fill each other's gaps (edge kernels take their rows from a dynamic queue).
+  int parts = 1;
+  if (!self_src && g_split > 1) {
+    parts = n_dst / 1024;
+    if (parts > g_split) parts = g_split;
+    if (parts < 1) parts = 1;
   }
-  return 0;
+  SplitStreams* ss = parts > 1 ? split_streams() : nullptr;
+  if (!ss) return run_stack_rows(x, 0, n_dst, n_layers, side_a, side_b, ws, out, 0, st);
+  const int per = ((n_dst + parts - 1) / parts + 127) / 128 * 128;
+  if (cudaEventRecord(ss->fork, st) != cudaSuccess) return (int)cudaGetLastError();
+  int err = 0;
+  for (int p = 0; p < parts && !err; ++p) {
+    const int r0 = p * per;
+    const int n = r0 + per <= n_dst ? per : n_dst - r0;
+    if (n <= 0) break;
+    cudaStream_t sp = p == 0 ? st : ss->st[p - 1];
+    if (p > 0 && cudaStreamWaitEvent(sp, ss->fork, 0) != cudaSuccess) err = (int)cudaGetLastError();
+    if (!err) err = run_stack_rows(x, r0, n, n_layers, side_a, side_b, ws, out, p * 4, sp);
+    if (p > 0 && !err) {
+      if (cudaEventRecord(ss->join[p - 1], sp) != cudaSuccess || cudaStreamWaitEvent(st, ss->join[p - 1], 0) != cudaSuccess)
+        err = (int)cudaGetLastError();
+    }
+  }
+  return err;
 }
 
 int prosim_policy_head_fwd(const float* feat, const int32_t* agent_type, int P, const float* w, float* motion_pred,

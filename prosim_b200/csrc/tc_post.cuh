@@ -220,7 +220,7 @@ __device__ __forceinline__ void ln_stats_tmem(uint32_t lane_base, uint32_t acc_c
 __device__ long long g_tcp_dbg[32];
 #define TCP_MARK(slot)                                           \
   do {                                                           \
-    if (blockIdx.x == 0) g_tcp_dbg[slot] = clock64();            \
+    if (blockIdx.x == 0 && has_next) g_tcp_dbg[slot] = clock64(); \
   } while (0)
 
 __global__ void __launch_bounds__(THREADS, 1)

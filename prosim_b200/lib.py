@@ -16,7 +16,7 @@ SYMBOLS = (
     'prosim_build_knn_edges', 'prosim_edge_pe', 'prosim_attn_kv', 'prosim_attn_layer_fwd', 'prosim_attn_stack_fwd',
     'prosim_policy_head_fwd', 'prosim_reconst_fwd', 'prosim_mlp2_fwd', 'prosim_init_traj', 'prosim_step_env',
     'prosim_gather_pose', 'prosim_step_agent_traj', 'prosim_launch_count', 'prosim_profile_enable', 'prosim_profile_read',
-    'prosim_rollout_to_world', 'prosim_tc_gemm_test', 'prosim_set_tensor_core', 'prosim_tc_debug_read',
+    'prosim_rollout_to_world', 'prosim_tc_gemm_test', 'prosim_set_tensor_core', 'prosim_tc_debug_read', 'prosim_set_stack_split',
 )
 
 KERNEL_CLASSES = {'pointnet': 0, 'radius': 1, 'knn': 2, 'edge_pe': 3, 'attn_kv': 4, 'attn_dstpre': 5, 'attn_edge': 6,
@@ -56,6 +56,7 @@ _SIGS = {
     'prosim_tc_gemm_test': [_P, _P, _P, c_int, c_int, _P],
     'prosim_set_tensor_core': [c_int],
     'prosim_tc_debug_read': [_P],
+    'prosim_set_stack_split': [c_int],
 }
 
 _lib = None
@@ -137,3 +138,8 @@ def profile_read():
 def set_tensor_core(on):
     """Node-side GEMMs of launches with >= 1024 rows: True = tcgen05 / TMEM 3xTF32 kernel (default), False = fp32 FFMA kernels."""
     call('prosim_set_tensor_core', 1 if on else 0)
+
+
+def set_stack_split(parts):
+    """Row-split chains of the fixed-source attention stacks (1 = single stream; default 2)."""
+    call('prosim_set_stack_split', int(parts))

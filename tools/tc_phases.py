@@ -7,6 +7,7 @@ from prosim_b200 import lib, synthetic, weights
 from prosim_b200.model import ProSimB200
 dev = torch.device('cuda', 0)
 model = ProSimB200(state_dict=weights.random_state_dict(0), device=dev)
+lib.set_stack_split(1)
 b = synthetic.clone_batch(synthetic.make_batch(n_scenes=32, n_agents=128, n_map=512, steps=20), dev)[0]
 with torch.no_grad():
     model.forward(b, 'val')
@@ -14,7 +15,7 @@ torch.cuda.synchronize()
 buf = (ctypes.c_longlong * 32)()
 lib.call('prosim_tc_debug_read', ctypes.cast(buf, ctypes.c_void_p))
 t = list(buf)
-t0 = min(x for x in t if x > 0)
+t0 = t[0]
 names_e = ['start', 'G1 staged', 'G1 acc', 'agg->A', 'gate acc', 'u->A', 'out acc', 'xn->A', 'ffn done', 'y acc', 'out,xd->A', 'q->A',
            'qhat done', 'stores done']
 print('epilogue:', ' | '.join(f'{n} {t[i] - t0}' for i, n in enumerate(names_e)))
