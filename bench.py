@@ -156,6 +156,15 @@ def edge_kernel_bytes(edge_log):
     return total_edges, total_bytes, launches
 
 
+def ncu_traffic(kernel_key):
+    """DRAM bytes of one launch of a kernel from the committed `ncu --set full` capture (profiles/r1_kernel_traffic.json)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, 'profiles', 'r1_kernel_traffic.json')))[kernel_key]
+        return t
+    except Exception:
+        return None
+
+
 def algorithmic_flops_post(n_rows):
     """attn_post_kernel (+ fused next-layer dst projections), 2 FLOP/MAC: Wvr' contraction 128x128, gate 128x128,
     out-proj 128x128, FFN 128x512 + 512x128, next q/s/gx 3 x 128x128, Qhat 8 x 16x128  (DESIGN.md)."""
@@ -304,6 +313,17 @@ def run_b200(a):
                     'share_of_step': edge_ms / total_ms if world == 1 else None,
                     'fp32_ffma_frac': (n_edges * 3072.0 / n_launch) / (avg_ms * 1e-3) / 1e12 / ffma_peak,
                     'note': 'one warp per row, z tiles by TMA; issue/latency bound at 12 warps per SM (profiles/), DESIGN.md section 5'}
+            cap = ncu_traffic('attn_edge4_kernel a2p')
+            if cap is not None:
+                # the committed ncu --set full capture is ONE launch (first policy a2p layer); its algorithmic bytes are
+                # given beside it so that traffic / algorithmic compares like with like
+                a2p = [(e, n) for k, e, n, _ in edge_log if k == 'pol_a2p']
+                roof['traffic'] = cap['dram_bytes_read'] + cap['dram_bytes_write']
+                roof['traffic_launch'] = cap['launch']
+                if a2p:
+                    e, n = int(a2p[0][0]), a2p[0][1]
+                    roof['traffic_launch_algorithmic_bytes'] = e * (384 + 32 + 32) + n * (8 * 128 * 4 + 8 * 96 * 4) + e
+                roof['traffic_source'] = cap['source']
         roof2 = None
         if post_n > 0:
             avg_ms = post_ms / post_n
@@ -326,6 +346,11 @@ def run_b200(a):
                                         'note': 'against the fp32 FFMA peak the previous CUDA-core kernel was bound by'},
                     'avg_launch_ms': avg_ms, 'launches_timed': post_n, 'share_of_step': post_ms / t_extra
                     if world == 1 else None}
+            cap = ncu_traffic('tcp::attn_post_tc_kernel a2p')
+            if cap is not None:
+                roof2['traffic'] = cap['dram_bytes_read'] + cap['dram_bytes_write']
+                roof2['traffic_launch'] = cap['launch']
+                roof2['traffic_source'] = cap['source']
         cpu = None
         if not a.no_cpu_baseline and world == 1:
             ts, cores = time_oracle(a.cpu_baseline_scenes, A, M, RS, repeats=2, warmup=1)

@@ -141,5 +141,5 @@ def set_tensor_core(on):
 
 
 def set_stack_split(parts):
-    """Row-split chains of the fixed-source attention stacks (1 = single stream; default 2)."""
+    """Row-split chains of the fixed-source attention stacks (1 = single stream, the default)."""
     call('prosim_set_stack_split', int(parts))

@@ -167,6 +167,23 @@ def test_batch_invariance_tensor_core_kernel():
     assert worst < 1e-4
 
 
+def test_row_split_schedule_is_bit_identical():
+    """prosim_set_stack_split: the fixed-source stacks run as independent >= 1024-row chains on side streams; every
+    setting must give the same bits (rows never interact; chains are cut at multiples of 128 rows)."""
+    from prosim_b200 import lib
+    kw = dict(n_scenes=24, n_agents=100, n_map=80, steps=20)
+    try:
+        ref, _ = _run_gpu(kw, False)
+        for parts in (2, 3):
+            lib.set_stack_split(parts)
+            out, _ = _run_gpu(kw, False)
+            assert torch.equal(out['motion_pred'], ref['motion_pred'])
+            for name, r in ref['rollout_trajs'].items():
+                assert torch.equal(r['traj'], out['rollout_trajs'][name]['traj']), (parts, name)
+    finally:
+        lib.set_stack_split(1)
+
+
 def test_agent_permutation_equivariance():
     """Storing the observation slots in another order must not change any agent's trajectory beyond
     summation-order rounding (edges are visited in ascending slot index)."""
