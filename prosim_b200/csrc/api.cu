@@ -422,12 +422,12 @@ int prosim_build_knn_edges(const float* qpos, const int32_t* qscene, int n_q, co
   if (n_q == 0) return 0;
   if (!qpos || !qscene || !spos || !seg || !nbr || !deg) return ERR_ARG;
   if (int e = setup_attributes()) return e;
-  const size_t smem = (size_t)nmax * 8;
+  const size_t smem = (size_t)nmax * 8 * sizeof(unsigned);   // 8 query warps x nmax keys
   if (smem > 64 * 1024) return ERR_ARG;
   LaunchScope ls(PROSIM_K_KNN, S(stream));
-  knn_kernel<<<n_q, 128, smem, S(stream)>>>(reinterpret_cast<const float2*>(qpos), qscene, n_q,
-                                            reinterpret_cast<const float2*>(spos), reinterpret_cast<const int4*>(seg), k,
-                                            nmax, nbr, deg, stride);
+  knn_kernel<<<(n_q + 7) / 8, 256, smem, S(stream)>>>(reinterpret_cast<const float2*>(qpos), qscene, n_q,
+                                                      reinterpret_cast<const float2*>(spos), reinterpret_cast<const int4*>(seg), k,
+                                                      nmax, nbr, deg, stride);
   PROSIM_CHECK_LAUNCH();
   return 0;
 }
