@@ -241,7 +241,7 @@ int cached_map128(CUtensorMap* out, const float* base, size_t rows, int cols) {
 template <int ZD, int NW>
 int launch_edge4(const CUtensorMap& tm, const DstScratch& d, const prosim_graph_t& g, int n_dst, float* rbar, float* sk,
                  float* pw, float* ft, int ft_tiles, int* counter, cudaStream_t st) {
-  const int grid = (n_dst + NW - 1) / NW < 148 ? (n_dst + NW - 1) / NW : 148;
+  const int grid = (n_dst + NW - 1) / NW < 148 ? (n_dst + NW - 1) / NW : 148;   // one persistent CTA per SM
   attn_edge4_kernel<ZD, NW><<<grid, NW * 32, Edge4Cfg<ZD>::smem_bytes(NW), st>>>(tm, d.qhat, sk, g.deg, g.stride, n_dst, rbar,
                                                                               pw, ft, ft_tiles, counter);
   PROSIM_CHECK_LAUNCH();

@@ -42,7 +42,9 @@ namespace tcp {
 
 constexpr int NSTAGE = 3;            // weight ring stages
 constexpr int STAGE_BYTES = 32768;
-constexpr int NIN = 5;               // input tile ring stages
+constexpr int NIN_G = 2;             // input tile ring stages PER epilogue group (a slot is only ever consumed by one group,
+                                     // so that every waiter sees every phase of its barriers: parity waits alias otherwise)
+constexpr int NIN = 2 * NIN_G;
 constexpr int TILE_BYTES = 16384;    // [128 rows][32 floats], 128B-swizzled
 constexpr int THREADS = 352;           // 8 epilogue warps (two column groups) + weight producer + MMA issuer + input producer
 constexpr uint32_t ACC0 = 0, ACC1 = 128, AHI = 256, ALO = 384;
@@ -338,8 +340,9 @@ __global__ void __launch_bounds__(THREADS, 1)
           tm = &maps.out;
           col = k * 32;
         }
-        const int s = i % NIN;
-        if (i >= NIN) mbar_wait(&sm.in_empty[s], ((i / NIN) - 1) & 1);
+        const int kg = i >> 1;                              // tile i is the kg-th tile of group i & 1
+        const int s = (i & 1) * NIN_G + kg % NIN_G;
+        if (kg >= NIN_G) mbar_wait(&sm.in_empty[s], ((kg / NIN_G) - 1) & 1);
         const uint32_t fb = e4::smem_u32(&sm.in_full[s]);
         e4::mbar_expect_tx(fb, TILE_BYTES);
         tma_load_tile(e4::smem_u32(sm.in[s]), tm, col, row0, fb);
@@ -482,7 +485,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     const uint32_t a_ready = e4::smem_u32(&sm.a_ready);
     const float* vec = sm.vec;
     uint32_t ph_done0 = 0, ph_done1 = 0, ph_afree = 0, ph_up = 0, ph_hfree = 0;
-    int in_i = grp, xc = 0;
+    int in_k = 0, xc = 0;                               // tiles this group has consumed
     const bool issuer = r == 0;
     auto publish_a = [&]() {
       tmem_st_wait();
@@ -496,11 +499,11 @@ __global__ void __launch_bounds__(THREADS, 1)
     };
     // next input tile of this group -> this thread's 32 floats; the slot is handed back to the producer
     auto in_get = [&](float (&dst)[32]) {
-      const int s = in_i % NIN;
-      mbar_wait(&sm.in_full[s], (in_i / NIN) & 1);
+      const int s = grp * NIN_G + in_k % NIN_G;
+      mbar_wait(&sm.in_full[s], (in_k / NIN_G) & 1);
       tile_get32(sm.in[s], r, dst);
       mbar_arrive(e4::smem_u32(&sm.in_empty[s]));
-      in_i += 2;
+      ++in_k;
     };
     // this thread's 32 floats -> the group's staging tile -> TMA store of the [128 x 32] box at column col
     auto out_put = [&](const CUtensorMap* tm, int col, const float (&src)[32]) {
