@@ -47,6 +47,7 @@ def parse():
     ap.add_argument('--cpu-baseline-scenes', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-single-scene', action='store_true')
+    ap.add_argument('--large-batch-scenes', type=int, default=128, help='secondary figure: scenes per forward (0 = skip)')
     return ap.parse_args()
 
 
@@ -278,6 +279,26 @@ def run_b200(a):
                       'ms_per_forward': ms, 'value': A * RS / (ms * 1e-3), 'unit': UNIT,
                       'cuda_graph_e2e_ms': gms, 'cuda_graph_e2e_value': A * RS / (gms * 1e-3)}
 
+        large = None
+        if a.large_batch_scenes > 0 and rank == 0 and world == 1:
+            # secondary figure: the node kernel occupies one SM per 128 rows, so a 32-scene shard uses 32 of 148 SMs of it
+            LS = a.large_batch_scenes
+            big = synthetic.clone_batch(synthetic.make_batch(n_scenes=LS, n_agents=A, n_map=M, steps=RS, first_scene=1000), dev)[0]
+            lt = []
+            for i in range(5):
+                bb, _ = synthetic.clone_batch(big)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                model.forward(bb, 'val')
+                e1.record()
+                e1.synchronize()
+                lt.append(e0.elapsed_time(e1))
+            lms = statistics.median(lt[2:])
+            large = {'workload': f'{LS} scenes x {A} agents x {M} polylines x {RS} steps in one forward (device resident)',
+                     'ms_per_forward': lms, 'value': LS * A * RS / (lms * 1e-3), 'unit': UNIT}
+            del big
+
     total = torch.tensor([sum(times), sum(t for t, _, _ in e2e)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(total, op=dist.ReduceOp.MAX)
@@ -369,7 +390,7 @@ def run_b200(a):
                     'ms_per_step': e2e_ms / a.steps},
             'gpu_launches': launches, 'roofline': roof, 'roofline_dense_kernel': roof2, 'cpu_baseline': cpu,
             'clocks': clk.summary(),
-            'single_scene': single,
+            'single_scene': single, 'large_batch': large,
         }
         print(json.dumps(line))
     if world > 1:

@@ -167,6 +167,21 @@ def test_batch_invariance_tensor_core_kernel():
     assert worst < 1e-4
 
 
+def test_tensor_core_path_with_capped_generator_graph():
+    """>= 1024 policy rows with 450 map polylines per scene: the generator's scene->prompt graph hits its 512-neighbour
+    cap (16 z tiles per row in the edge kernel) on the tensor-core path; checked against the same scenes run one by one
+    (FFMA path, itself pinned to the reference goldens)."""
+    kw = dict(n_agents=100, n_map=450, steps=20)
+    out_a, _ = _run_gpu(dict(kw, n_scenes=11), False)
+    worst = 0.0
+    for s in (3, 10):
+        out_1, _ = _run_gpu(dict(kw, n_scenes=1, first_scene=s), False)
+        for name, r in out_1['rollout_trajs'].items():
+            other = out_a['rollout_trajs'][f'{s}-{name.split("-", 1)[1]}']
+            worst = max(worst, float((r['traj'] - other['traj']).abs().max()))
+    assert worst < 1e-4, worst
+
+
 def test_row_split_schedule_is_bit_identical():
     """prosim_set_stack_split: the fixed-source stacks run as independent >= 1024-row chains on side streams; every
     setting must give the same bits (rows never interact; chains are cut at multiples of 128 rows)."""
