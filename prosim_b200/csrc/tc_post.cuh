@@ -150,13 +150,19 @@ __device__ __forceinline__ void group_barrier(int grp) {   // the 4 warps of one
 }
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 3, 256;\n" ::: "memory"); }   // all 8 epilogue warps
 
+// round-to-nearest (ties away) to tf32 precision for finite values: what cvt.rna.tf32.f32 computes, in two integer
+// instructions -- the cvt expands to ~6 (inf / nan handling) and the split ran 3840 of them per row, a third of the
+// epilogue warps' instruction stream (profiles/r1_tcpost_sass_mix.txt)
+__device__ __forceinline__ float tf32_rna_finite(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
 // v (32 columns of this thread's row) -> tf32 hi / lo halves -> TMEM columns hi_col.. / lo_col.. of the thread's lane
 __device__ __forceinline__ void split_store(uint32_t lane_base, uint32_t hi_col, uint32_t lo_col, const float (&v)[32]) {
   float hi[32], lo[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
-    hi[i] = tc::to_tf32(v[i]);
-    lo[i] = tc::to_tf32(v[i] - hi[i]);
+    hi[i] = tf32_rna_finite(v[i]);
+    lo[i] = tf32_rna_finite(v[i] - hi[i]);
   }
   tmem_st32(lane_base + hi_col, hi);
   tmem_st32(lane_base + lo_col, lo);
