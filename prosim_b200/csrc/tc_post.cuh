@@ -520,6 +520,19 @@ __global__ void __launch_bounds__(THREADS, 1)
       group_barrier(grp);
       if (issuer) tma_store_tile(tm, col, row0, e4::smem_u32(sm.stage[grp]));
     };
+    // phase 5 only: every input tile has been consumed, so the group's two input slots join its staging tile and
+    // three stores can be in flight (a single tile serialises on the store's shared-memory read: 1.5 k cycles per chunk)
+    int rot = 0;
+    auto out_put3 = [&](auto issue, const float (&src)[32]) {
+      uint8_t* tile = rot == 2 ? sm.stage[grp] : sm.in[grp * NIN_G + rot];
+      rot = rot == 2 ? 0 : rot + 1;
+      if (issuer) tma_store_wait_read<2>();
+      group_barrier(grp);
+      tile_put32(tile, r, src);
+      e4::fence_proxy_async();
+      group_barrier(grp);
+      if (issuer) issue(e4::smem_u32(tile));
+    };
     // row total of a per-thread partial (this group's 64 columns + the other group's)
     auto row_sum = [&](float part) -> float {
       float* x = &sm.xchg[xc & 1][0][0];
@@ -770,7 +783,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] += t[i];
           if (to_a) split_store(lb, AHI + c0, ALO + c0, v);   // every MMA that read A = LN_dst'(out) has completed
-          out_put(tm, c0, v);
+          out_put3([&](uint32_t src) { tma_store_tile(tm, c0, row0, src); }, v);
         }
         tc::fence_before_sync();
         mbar_arrive(e4::smem_u32(&sm.acc_free[b]));
@@ -787,7 +800,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll 1
         for (int c0 = grp * 32; c0 < 128; c0 += 64) {
           tc::tmem_ld32(lb + (b ? ACC1 : ACC0) + c0, v);
-          out_put(&maps.qhat_n, h * D + c0, v);
+          out_put3([&](uint32_t src) { tma_store_tile(&maps.qhat_n, h * D + c0, row0, src); }, v);
         }
         tc::fence_before_sync();
         mbar_arrive(e4::smem_u32(&sm.acc_free[b]));
