@@ -239,10 +239,10 @@ int cached_map128(CUtensorMap* out, const float* base, size_t rows, int cols) {
 }
 
 template <int ZD, int NW>
-int launch_edge4(const CUtensorMap& tm, const DstScratch& d, const prosim_graph_t& g, int n_dst, float* rbar, float* sk,
+int launch_edge4(const CUtensorMap& tm, const CUtensorMap& tm32, const DstScratch& d, const prosim_graph_t& g, int n_dst, float* rbar, float* sk,
                  float* pw, float* ft, int ft_tiles, int* counter, cudaStream_t st) {
   const int grid = (n_dst + NW - 1) / NW < 148 ? (n_dst + NW - 1) / NW : 148;   // one persistent CTA per SM
-  attn_edge4_kernel<ZD, NW><<<grid, NW * 32, Edge4Cfg<ZD>::smem_bytes(NW), st>>>(tm, d.qhat, sk, g.deg, g.stride, n_dst, rbar,
+  attn_edge4_kernel<ZD, NW><<<grid, NW * 32, Edge4Cfg<ZD>::smem_bytes(NW), st>>>(tm, tm32, d.qhat, sk, g.deg, g.stride, n_dst, rbar,
                                                                               pw, ft, ft_tiles, counter);
   PROSIM_CHECK_LAUNCH();
   return 0;
@@ -254,8 +254,9 @@ int launch_edge(const DstScratch& d, const float* kv, const prosim_graph_t& g, i
   if ((g.zd != 96 && g.zd != 128) || g.stride > 32 * Edge4Cfg<96>::MT_TILES) return ERR_ARG;
   const size_t z_rows = (size_t)n_dst * g.stride;
   if (z_rows > 0x7fffffffull || (reinterpret_cast<uintptr_t>(g.z) & 15) != 0) return ERR_ARG;
-  alignas(64) CUtensorMap tm;
+  alignas(64) CUtensorMap tm, tm32;
   if (int e = make_z_map(&tm, g.z, z_rows, g.zd)) return e;
+  if (int e = make_map2d(&tm32, g.z, z_rows, g.zd, 32)) return e;
   const int ft_tiles = (g.stride + 31) / 32;
   {
     LaunchScope ls(PROSIM_K_EDGE_QK, st);
@@ -268,17 +269,17 @@ int launch_edge(const DstScratch& d, const float* kv, const prosim_graph_t& g, i
     const int per_sm = (n_dst + 147) / 148;
     int e = ERR_ARG;
     if (g.zd == 96) {
-      if (per_sm <= 1) e = launch_edge4<96, 1>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
-      else if (per_sm <= 2) e = launch_edge4<96, 2>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
-      else if (per_sm <= 4) e = launch_edge4<96, 4>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
-      else if (per_sm <= 8) e = launch_edge4<96, 8>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
-      else e = launch_edge4<96, 12>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
+      if (per_sm <= 1) e = launch_edge4<96, 1>(tm, tm32, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
+      else if (per_sm <= 2) e = launch_edge4<96, 2>(tm, tm32, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
+      else if (per_sm <= 4) e = launch_edge4<96, 4>(tm, tm32, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
+      else if (per_sm <= 8) e = launch_edge4<96, 8>(tm, tm32, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
+      else e = launch_edge4<96, 12>(tm, tm32, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
     } else {
-      if (per_sm <= 1) e = launch_edge4<128, 1>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
-      else if (per_sm <= 2) e = launch_edge4<128, 2>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
-      else if (per_sm <= 4) e = launch_edge4<128, 4>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
-      else if (per_sm <= 8) e = launch_edge4<128, 8>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
-      else e = launch_edge4<128, 10>(tm, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
+      if (per_sm <= 1) e = launch_edge4<128, 1>(tm, tm32, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
+      else if (per_sm <= 2) e = launch_edge4<128, 2>(tm, tm32, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
+      else if (per_sm <= 4) e = launch_edge4<128, 4>(tm, tm32, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
+      else if (per_sm <= 8) e = launch_edge4<128, 8>(tm, tm32, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
+      else e = launch_edge4<128, 10>(tm, tm32, d, g, n_dst, rbar, sk, pw, ft, ft_tiles, counter, st);
     }
     if (e) return e;
   }

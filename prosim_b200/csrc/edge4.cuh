@@ -83,7 +83,8 @@ struct Edge4Cfg {
 
 template <int ZD, int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
-    attn_edge4_kernel(const __grid_constant__ CUtensorMap tmZ, const float* __restrict__ Qhat, const float* __restrict__ Sk,
+    attn_edge4_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmZ32,
+                      const float* __restrict__ Qhat, const float* __restrict__ Sk,
                       const int* __restrict__ deg, int stride, int n_dst, float* __restrict__ Rbar, float* __restrict__ Pw,
                       float* __restrict__ Ft, int ft_tiles, int* __restrict__ row_counter) {
   using C = Edge4Cfg<ZD>;
@@ -138,14 +139,21 @@ __global__ void __launch_bounds__(NW * 32, 1)
     for (int t = 0; t < ntiles; ++t) {
       const int t0 = t << 5, nt = min(32, n_e - t0);
       // ---- fetch: z boxes of this tile (+ the row's Qhat with its first tile), all on one mbarrier phase
-      const int nbox = ((nt + 7) >> 3) * NSEG;
+      // a full tile is NSEG boxes of [32 edges x 32 floats] (tmZ32); a partial one is fetched in 8-edge boxes so that at
+      // most 7 rows beyond the list are read
+      const bool full_tile = nt == 32;
+      const int nbox = full_tile ? NSEG : ((nt + 7) >> 3) * NSEG;
       __syncwarp();                                   // every lane is done with the previous tile's buffers
-      if (lane == 0) e4::mbar_expect_tx(bar, nbox * 1024 + (t == 0 ? C::QBYTES : 0));
+      if (lane == 0) e4::mbar_expect_tx(bar, (full_tile ? NSEG * 4096 : nbox * 1024) + (t == 0 ? C::QBYTES : 0));
       __syncwarp();
       if (lane < nbox) {
         e4::fence_proxy_async();
-        const int g = lane / NSEG, sg = lane % NSEG;
-        e4::tma_box(zb_s + sg * 4096 + g * 1024, &tmZ, sg * 32, (int)(ebase + t0 + g * 8), bar, z_policy);
+        if (full_tile) {
+          e4::tma_box(zb_s + lane * 4096, &tmZ32, lane * 32, (int)(ebase + t0), bar, z_policy);
+        } else {
+          const int g = lane / NSEG, sg = lane % NSEG;
+          e4::tma_box(zb_s + sg * 4096 + g * 1024, &tmZ, sg * 32, (int)(ebase + t0 + g * 8), bar, z_policy);
+        }
       } else if (t == 0 && lane == 31) {
         e4::fence_proxy_async();
         e4::bulk_copy(qb_s, Qhat + (size_t)row * H * D, C::QBYTES, bar);
