@@ -221,8 +221,8 @@ struct MapEntry {
 };
 int cached_map128(CUtensorMap* out, const float* base, size_t rows, int cols) {
   constexpr int CAP = 64;
-  static MapEntry table[CAP];
-  static int used = 0, next = 0;
+  static thread_local MapEntry table[CAP];   // per host thread: the entry points stay re-entrant
+  static thread_local int used = 0, next = 0;
   for (int i = 0; i < used; ++i)
     if (table[i].base == base && table[i].rows == rows && table[i].cols == cols) {
       *out = table[i].tm;

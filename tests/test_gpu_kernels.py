@@ -178,6 +178,33 @@ def test_attention_layer_matches_oracle(ctx, bipartite, n_dst):
     assert (out - ref).abs().max() < 2e-5
 
 
+@pytest.mark.parametrize('stride,n_dst', [(768, 70), (37, 1300), (203, 1100)])
+def test_attention_layer_edge_tiling(ctx, stride, n_dst):
+    """Edge kernel tiling corners: the largest supported neighbour list (768 = 24 z tiles per row), strides that are not
+    a multiple of 8 (partial TMA boxes run past the row's list / the end of z), rows without edges; small launches
+    take the FFMA node kernel, >= 1024 rows the tensor-core one."""
+    ops, orc = ctx['ops'], ctx['oracle']
+    g = torch.Generator().manual_seed(100 + stride)
+    n_src = stride + 150
+    nbr, deg, j, ei = _random_graph(g, n_dst, n_src, stride)
+    deg_full = min(stride, n_src)
+    nbr[0, :deg_full] = torch.sort(torch.randperm(n_src, generator=g)[:deg_full])[0]   # one row with a full list
+    deg[0] = deg_full
+    j = torch.arange(stride)[None, :] < deg[:, None]
+    ei = torch.stack([nbr[j], torch.arange(n_dst)[:, None].expand(n_dst, stride)[j]])
+    x_src, x_dst = torch.randn(n_src, 128, generator=g), torch.randn(n_dst, 128, generator=g)
+    r = torch.randn(ei.shape[1], 128, generator=g)
+    r[:, 96:] = r[:, 64:96]                       # 96-wide z path: features 96..127 duplicate 64..95
+    ref = orc.attention_layer('policy.act_decoder.m2p_attn_layers.1', x_src, x_dst, r, ei, True)
+    z = torch.zeros(n_dst, stride, 96)
+    z[j] = F.layer_norm(r, (128,))[:, :96]
+    e = ops.EdgeList(nbr.reshape(-1).int().cuda(), deg.int().cuda(), stride, stride, z.reshape(-1, 96).cuda(), zd=96)
+    out = ops.attn_layer(x_src.cuda(), x_dst.cuda(), e, ctx['arena'],
+                         ctx['off']['pol_m2p'] + 1 * weights.ATTN_LAYER_FLOATS).cpu()
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max() < 2e-5
+
+
 @pytest.mark.parametrize('tensor_core', [True, False])
 def test_attention_stack_matches_oracle(ctx, tensor_core):
     """6 x (a2p, m2p) with fixed sources -- the policy tick's core -- and 3 x self-source layers; with the tcgen05 node
