@@ -106,6 +106,7 @@ class ProSimB200(nn.Module):
         self._arena = None
         self._off = None
         self._bufs = {}
+        self._plan_cache = []
         if state_dict is None:
             state_dict = weights.random_state_dict(0, self.use_condition)
         self.load_state_dict(state_dict)
@@ -171,6 +172,17 @@ class ProSimB200(nn.Module):
         # one device->host copy of every validity mask the bookkeeping needs
         ov = torch.stack([obs['mask'].all(-1).any(-1)] + [f['mask'].all(-1).any(-1) for f in futs])
         flat = torch.cat([ov.reshape(-1), mp['mask'].any(-1).reshape(-1), prm['prompt_mask'].reshape(-1)]).cpu().numpy()
+        # Plans are pure functions of (shapes, validity masks, id lists, ticks): batches that repeat them -- replicas of a
+        # scene, a fixed cast of agents re-simulated from new states -- reuse the device-resident index maps instead of
+        # rebuilding and re-uploading them (1.4 ms of host work during which the GPU idles at the start of a forward)
+        id_lists = [obs['agent_ids'], prm['agent_ids']] + [f['agent_ids'] for f in futs]
+        sig = (B, A, M, N, tuple(pl.all_t), str(self._device))
+        mask_bytes = flat.tobytes()
+        for ent in self._plan_cache:
+            if ent[0] == sig and ent[1] == mask_bytes and len(ent[2]) == len(id_lists) and \
+                    all(a is b or a == b for a, b in zip(ent[2], id_lists)):
+                batch._b200_plan = ent[3]
+                return ent[3]
         nt = len(pl.all_t)
         ov = flat[:nt * B * A].reshape(nt, B, A).copy()
         mv = flat[nt * B * A:nt * B * A + B * M].reshape(B, M)
@@ -253,6 +265,8 @@ class ProSimB200(nn.Module):
         pl.steps = len(pl.all_t) * STEP
         pl.T = HIST + pl.steps
         batch._b200_plan = pl
+        self._plan_cache.insert(0, (sig, mask_bytes, id_lists, pl))
+        del self._plan_cache[4:]
         return pl
 
     # ------------------------------------------------------------------ reference API

@@ -199,6 +199,23 @@ def test_row_split_schedule_is_bit_identical():
         lib.set_stack_split(1)
 
 
+def test_plan_cache_hits_only_on_identical_bookkeeping():
+    """The host index plan is reused when shapes, validity masks and id lists repeat, and only then."""
+    model = _model(False)
+    kw = dict(agents_per_scene=[9, 14], map_per_scene=[20, 31], steps=20)
+    b1 = synthetic.make_batch(**kw).to('cuda')
+    b2 = synthetic.make_batch(**kw).to('cuda')                     # same bookkeeping, different tensors
+    b3 = synthetic.make_batch(**kw, permute_obs=True).to('cuda')   # same shapes, other id order
+    b4 = synthetic.make_batch(agents_per_scene=[9, 13], map_per_scene=[20, 31], steps=20).to('cuda')
+    with torch.no_grad():
+        p1, p2, p3, p4 = (model._plan(b) for b in (b1, b2, b3, b4))
+        assert p1 is p2 and p3 is not p1 and p4 is not p1 and p4 is not p3
+        o1 = model.forward(b1, 'val')['motion_pred']
+        o3 = model.forward(b3, 'val')['motion_pred']
+    for name, r in o1['rollout_trajs'].items():
+        assert (r['traj'] - o3['rollout_trajs'][name]['traj']).abs().max() < 1e-4
+
+
 def test_agent_permutation_equivariance():
     """Storing the observation slots in another order must not change any agent's trajectory beyond
     summation-order rounding (edges are visited in ascending slot index)."""
