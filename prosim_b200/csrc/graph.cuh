@@ -119,51 +119,91 @@ __global__ void __launch_bounds__(256) knn_kernel(const float2* __restrict__ qpo
 // the packed weights).  Reference: policy/act_decoder.py:203-221 + layers/fourier_embedding.py:56-79.
 //   input = [|dp|, wrap(theta_src - theta_dst), phi, phi],  phi = atan2(c x dp, c . dp), c = (cos, sin)(theta_dst)
 //   feature[i*32 + 2m + {0,1}] = {sin, cos}( input_i * 2pi / dim_t[m] ),  dim_t[m] = 10000^(m/16)
-// One CTA (4 warps) per destination row, a warp per edge, lane l owns features 4l..4l+3.
+// One CTA (4 warps) per destination row; 8 lanes per edge (4 edges per warp and pass), lane sub-index s owns the
+// ZD/8 consecutive features [s*ZD/8, (s+1)*ZD/8) = ZD/16 (sin, cos) pairs: the per-edge geometry (atan2, sqrt, wrap)
+// and the LayerNorm reductions are paid once per 4 edges instead of once per edge (the first version ran a warp per
+// edge with 4 features per lane and a quarter of the lanes idle at ZD = 96).
 // extra (optional): per-edge [128] vector added to the PE before the normalisation (condition edges,
 // condition_transformer/condition_attns.py:211-216), indexed like Z.
 // ZD = 128 stores all features; ZD = 96 (only without `extra`) drops features 96..127, which are bit-identical
-// copies of 64..95 (the embedding gets phi twice); the statistics still run over all 128.
+// copies of 64..95 (the embedding gets phi twice); the statistics still run over all 128 (those features count twice).
 template <int ZD>
 __global__ void __launch_bounds__(128) edge_pe_kernel(const float2* __restrict__ dpos, const float* __restrict__ dori,
                                                       const float2* __restrict__ spos, const float* __restrict__ sori,
                                                       const int* __restrict__ nbr, const int* __restrict__ deg, int stride,
                                                       const float* __restrict__ dim_t, const float* __restrict__ extra,
                                                       float* __restrict__ Z) {
+  constexpr int NF = ZD / 8;          // features per lane: 12 or 16
+  constexpr int NP = NF / 2;          // (sin, cos) pairs per lane
+  __shared__ float s_dt[16];
+  if (threadIdx.x < 16) s_dt[threadIdx.x] = dim_t[threadIdx.x];
+  __syncthreads();
   const int row = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane >> 3, s = lane & 7;
   const int n_e = min(deg[row], stride);
   const float2 pd = dpos[row];
   const float od = dori[row];
   const float cx = cosf(od), cy = sinf(od);
-  const int inp = lane >> 3;
-  const int m0 = (lane & 7) * 2;
-  const float dt0 = dim_t[m0], dt1 = dim_t[m0 + 1];
   const float TWO_PI_F = 6.28318530717958647692f;
-  for (int e = warp; e < n_e; e += 4) {
-    const size_t ei = (size_t)row * stride + e;
+  for (int e0 = 0; e0 < n_e; e0 += 16) {
+    const int e = e0 + warp * 4 + sub;
+    const bool ok = e < n_e;                               // uniform over the 8 lanes of an edge
+    const size_t ei = (size_t)row * stride + (ok ? e : 0);
     const int j = nbr[ei];
     const float2 ps = spos[j];
     const float rx = ps.x - pd.x, ry = ps.y - pd.y;
-    float v;
     // torch.norm on the CPU reference reduces with acc = fma(v, v, acc): sqrt(fma(ry, ry, rx*rx)) bit for bit;
     // the dot product is a torch sum over two rounded products starting from +0 (so -0 + -0 becomes +0 and the
     // zero-offset self edge gets phi = atan2(+-0, +0) = 0, not pi).
-    if (inp == 0) v = sqrtf(fmaf(ry, ry, __fmul_rn(rx, rx)));
-    else if (inp == 1) v = wrap_angle(sori[j] - od);
-    else v = atan2f(__fsub_rn(__fmul_rn(cx, ry), __fmul_rn(cy, rx)),
-                    __fadd_rn(__fadd_rn(0.0f, __fmul_rn(cx, rx)), __fmul_rn(cy, ry)));
-    v = v * TWO_PI_F;
-    const float a0 = v / dt0, a1 = v / dt1;
-    float4 f;
-    sincosf(a0, &f.x, &f.y);     // one shared range reduction per argument (accurate path, no fast-math)
-    sincosf(a1, &f.z, &f.w);
-    if (extra != nullptr) {
-      const float4 x = *reinterpret_cast<const float4*>(extra + ei * D + 4 * lane);
-      f.x += x.x; f.y += x.y; f.z += x.z; f.w += x.w;
+    const float in0 = sqrtf(fmaf(ry, ry, __fmul_rn(rx, rx))) * TWO_PI_F;
+    const float in1 = wrap_angle(sori[j] - od) * TWO_PI_F;
+    const float in2 = atan2f(__fsub_rn(__fmul_rn(cx, ry), __fmul_rn(cy, rx)),
+                             __fadd_rn(__fadd_rn(0.0f, __fmul_rn(cx, rx)), __fmul_rn(cy, ry))) * TWO_PI_F;
+    float f[NF];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      const int p = s * NP + k;                            // pair index: scalar p / 16, frequency p % 16
+      const int i = p >> 4;
+      const float v = i == 0 ? in0 : i == 1 ? in1 : in2;
+      sincosf(v / s_dt[p & 15], &f[2 * k], &f[2 * k + 1]);   // accurate path, one shared range reduction per argument
     }
-    const float4 zn = ln_row_noaffine(f);
-    if (4 * lane < ZD) *reinterpret_cast<float4*>(Z + ei * ZD + 4 * lane) = zn;
+    if (extra != nullptr) {
+#pragma unroll
+      for (int k = 0; k < NF; k += 4) {
+        const float4 x = *reinterpret_cast<const float4*>(extra + ei * D + s * NF + k);
+        f[k] += x.x; f[k + 1] += x.y; f[k + 2] += x.z; f[k + 3] += x.w;
+      }
+    }
+    // LayerNorm over the 128 features (no affine); with ZD = 96 features 64..95 stand for 96..127 as well
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < NF; ++k) {
+      const float w = (ZD == 96 && s * NF + k >= 64) ? 2.0f : 1.0f;
+      sum = fmaf(w, f[k], sum);
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+    const float mean = sum * (1.0f / 128.0f);
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < NF; ++k) {
+      const float w = (ZD == 96 && s * NF + k >= 64) ? 2.0f : 1.0f;
+      const float d = f[k] - mean;
+      q = fmaf(w * d, d, q);
+    }
+    q += __shfl_xor_sync(0xffffffffu, q, 1);
+    q += __shfl_xor_sync(0xffffffffu, q, 2);
+    q += __shfl_xor_sync(0xffffffffu, q, 4);
+    const float rstd = 1.0f / sqrtf(q * (1.0f / 128.0f) + LN_EPS);
+    if (ok) {
+      float4* out = reinterpret_cast<float4*>(Z + ei * ZD + s * NF);
+#pragma unroll
+      for (int k = 0; k < NF; k += 4)
+        out[k >> 2] = make_float4((f[k] - mean) * rstd, (f[k + 1] - mean) * rstd, (f[k + 2] - mean) * rstd,
+                                  (f[k + 3] - mean) * rstd);
+    }
   }
 }
 
