@@ -118,6 +118,35 @@ __device__ __forceinline__ void gemm_tile_acc(float (&acc)[RPT], const float* __
   }
 }
 
+// Same contraction with packed fp32 FMAs: thread = (column pair cp = tid & 63, row group tid >> 6), RPT rows x 2
+// columns per thread, 256 threads cover 4*RPT rows x 128 columns.  One FFMA2 (scalar-broadcast x, a natural weight
+// pair, a natural accumulator pair) does the work of two FFMAs, and a k step costs RPT/4 LDS.128 + one LDG.64 per
+// thread instead of RPT/4... twice that per output column: half the issue slots per MAC.  Ascending k per output, so
+// results are bit-identical to gemm_tile_acc.
+template <int RPT>
+__device__ __forceinline__ void gemm_tile_acc2(float2 (&acc)[RPT], const float* __restrict__ Xs, int ldx, int K,
+                                               const float* __restrict__ Wt, int ldw) {
+  const int cp = threadIdx.x & 63;
+  const float* xrow = Xs + (threadIdx.x >> 6) * RPT * ldx;
+  const float2* w = reinterpret_cast<const float2*>(Wt) + cp;
+  const int ldw2 = ldw >> 1;
+#pragma unroll 2
+  for (int k = 0; k < K; k += 4) {
+    const float2 w0 = __ldg(w + (k + 0) * ldw2);
+    const float2 w1 = __ldg(w + (k + 1) * ldw2);
+    const float2 w2 = __ldg(w + (k + 2) * ldw2);
+    const float2 w3 = __ldg(w + (k + 3) * ldw2);
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const float4 x = *reinterpret_cast<const float4*>(xrow + r * ldx + k);
+      acc[r] = __ffma2_rn(make_float2(x.x, x.x), w0, acc[r]);
+      acc[r] = __ffma2_rn(make_float2(x.y, x.y), w1, acc[r]);
+      acc[r] = __ffma2_rn(make_float2(x.z, x.z), w2, acc[r]);
+      acc[r] = __ffma2_rn(make_float2(x.w, x.w), w3, acc[r]);
+    }
+  }
+}
+
 template <int RPT>
 __device__ __forceinline__ void acc_init(float (&acc)[RPT], float v) {
 #pragma unroll

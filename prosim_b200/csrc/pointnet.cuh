@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(256) pointnet_kernel(const float* __restrict__
                                                        int mask_inner, const int* __restrict__ rows, int n_poly,
                                                        const float* __restrict__ W, float* __restrict__ Out) {
   using C = PointNetCfg<P>;
-  constexpr int G = C::G, ROWS = C::ROWS, RPT = 32;
+  constexpr int G = C::G, ROWS = C::ROWS, RPT = 16;   // gemm_tile_acc2: 4 row groups x 16 rows, 64 column pairs
   extern __shared__ __align__(16) float smem[];
   float* bufA = smem;                         // [64][132]
   float* bufB = bufA + ROWS * LDS_PAD;        // [64][132]
@@ -35,7 +35,8 @@ __global__ void __launch_bounds__(256) pointnet_kernel(const float* __restrict__
   float* sPP = sPool + 8 * LDS_PAD;           // [8][132]
   int* sValid = reinterpret_cast<int*>(sPP + 8 * LDS_PAD);  // [64]
   const int poly0 = blockIdx.x * G;
-  const int n = threadIdx.x & 127, rg = threadIdx.x >> 7;
+  const int n = threadIdx.x & 127, rg = threadIdx.x >> 7;   // small pooled-row GEMMs (gemm_tile_acc<4>)
+  const int cp = threadIdx.x & 63, rg2 = threadIdx.x >> 6;  // per-point GEMMs (gemm_tile_acc2<16>)
 
   for (int r = threadIdx.x; r < ROWS; r += 256) {
     int g = r / P, p = r % P, v = 0;
@@ -56,34 +57,42 @@ __global__ void __launch_bounds__(256) pointnet_kernel(const float* __restrict__
   }
   __syncthreads();
 
-  float acc[RPT];
-  auto store_masked = [&](float* dst, bool relu) {
+  float2 acc[RPT];
+  auto init_bias = [&](const float* b) {
+    const float2 bb = __ldg(reinterpret_cast<const float2*>(b) + cp);
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) acc[r] = bb;
+  };
+  auto store = [&](float* dst, bool relu, bool masked) {
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
-      int row = rg * RPT + r;
-      float v = relu ? fmaxf(acc[r], 0.f) : acc[r];
-      dst[row * LDS_PAD + n] = sValid[row] ? v : 0.f;
+      const int row = rg2 * RPT + r;
+      float2 v = acc[r];
+      if (relu) v = make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f));
+      if (masked && !sValid[row]) v = make_float2(0.f, 0.f);
+      *reinterpret_cast<float2*>(dst + row * LDS_PAD + 2 * cp) = v;
     }
   };
+  auto store_masked = [&](float* dst, bool relu) { store(dst, relu, true); };
 
   // ---- pre_mlps
-  acc_init(acc, __ldg(W + pw::PRE0_B + n));
-  gemm_tile_acc<RPT>(acc, bufA, LDS_PAD, IN_PAD, W + pw::PRE0_W, D);
+  init_bias(W + pw::PRE0_B);
+  gemm_tile_acc2<RPT>(acc, bufA, LDS_PAD, IN_PAD, W + pw::PRE0_W, D);
   if (NPRE == 1) {
     store_masked(bufB, true);
   } else {
-    acc_store_smem<RPT>(acc, bufB, LDS_PAD, false);
+    store(bufB, false, false);
     __syncthreads();
     ln_tile_inplace<D>(bufB, LDS_PAD, ROWS, W + pw::PRE0_G, W + pw::PRE0_BB, true);
     __syncthreads();
-    acc_init(acc, __ldg(W + pw::PRE1_B + n));
-    gemm_tile_acc<RPT>(acc, bufB, LDS_PAD, D, W + pw::PRE1_W, D);
-    acc_store_smem<RPT>(acc, bufA, LDS_PAD, false);
+    init_bias(W + pw::PRE1_B);
+    gemm_tile_acc2<RPT>(acc, bufB, LDS_PAD, D, W + pw::PRE1_W, D);
+    store(bufA, false, false);
     __syncthreads();
     ln_tile_inplace<D>(bufA, LDS_PAD, ROWS, W + pw::PRE1_G, W + pw::PRE1_BB, true);
     __syncthreads();
-    acc_init(acc, __ldg(W + pw::PRE2_B + n));
-    gemm_tile_acc<RPT>(acc, bufA, LDS_PAD, D, W + pw::PRE2_W, D);
+    init_bias(W + pw::PRE2_B);
+    gemm_tile_acc2<RPT>(acc, bufA, LDS_PAD, D, W + pw::PRE2_W, D);
     store_masked(bufB, true);
   }
   __syncthreads();
@@ -106,20 +115,21 @@ __global__ void __launch_bounds__(256) pointnet_kernel(const float* __restrict__
 
   // ---- mlps.0 (point half + pooled half), LN, ReLU ; mlps.1, ReLU
   {
-    const float b = __ldg(W + pw::MLP0_B + n);
+    const float2 b = __ldg(reinterpret_cast<const float2*>(W + pw::MLP0_B) + cp);
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
-      int g = (rg * RPT + r) / P;
-      acc[r] = b + (g < G ? sPP[g * LDS_PAD + n] : 0.f);
+      const int g = (rg2 * RPT + r) / P;
+      const float2 pp = g < G ? *reinterpret_cast<const float2*>(sPP + g * LDS_PAD + 2 * cp) : make_float2(0.f, 0.f);
+      acc[r] = make_float2(b.x + pp.x, b.y + pp.y);
     }
   }
-  gemm_tile_acc<RPT>(acc, bufB, LDS_PAD, D, W + pw::MLP0_WA, D);
-  acc_store_smem<RPT>(acc, bufA, LDS_PAD, false);
+  gemm_tile_acc2<RPT>(acc, bufB, LDS_PAD, D, W + pw::MLP0_WA, D);
+  store(bufA, false, false);
   __syncthreads();
   ln_tile_inplace<D>(bufA, LDS_PAD, ROWS, W + pw::MLP0_G, W + pw::MLP0_BB, true);
   __syncthreads();
-  acc_init(acc, __ldg(W + pw::MLP1_B + n));
-  gemm_tile_acc<RPT>(acc, bufA, LDS_PAD, D, W + pw::MLP1_W, D);
+  init_bias(W + pw::MLP1_B);
+  gemm_tile_acc2<RPT>(acc, bufA, LDS_PAD, D, W + pw::MLP1_W, D);
   store_masked(bufB, true);
   __syncthreads();
   for (int i = threadIdx.x; i < G * D; i += 256) {
