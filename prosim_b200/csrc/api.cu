@@ -660,7 +660,7 @@ int prosim_step_env(const float* traj, const float* vel, const float* init_pos, 
   if (!traj || !vel || !init_pos || !init_heading || !p_row || !p_pos || !p_ori) return ERR_ARG;
   if (fut_in && (!fut_mask || !fut_pos || !fut_head || !p_slot)) return ERR_ARG;
   LaunchScope ls(PROSIM_K_STATE, S(stream));
-  step_env_kernel<<<(P + 127) / 128, 128, 0, S(stream)>>>(traj, vel, init_pos, init_heading, p_row, p_slot, P, T, tidx,
+  step_env_kernel<<<(P + 7) / 8, 128, 0, S(stream)>>>(traj, vel, init_pos, init_heading, p_row, p_slot, P, T, tidx,
                                                           p_pos, p_ori, fut_in, fut_mask, fut_pos, fut_head);
   PROSIM_CHECK_LAUNCH();
   return 0;

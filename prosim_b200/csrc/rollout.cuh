@@ -41,16 +41,17 @@ __global__ void init_traj_kernel(const float* __restrict__ obs_in, const float* 
   init_heading[row] = obs_head[slot];
 }
 
-// one thread per policy row.  tidx = number of valid steps in traj.  When fut_in != nullptr (every tick but
-// the first) the 11-step observation window of the agent is rebuilt in its current frame and written to
-// fut_obs (input cols 0-7, position, heading, mask), exactly like the reference does in place.
-__global__ void step_env_kernel(const float* __restrict__ traj, const float* __restrict__ vel,
+// 16 lanes per policy row (lane i < 11 owns step i of the observation window).  tidx = number of valid steps in traj.
+// When fut_in != nullptr (every tick but the first) the 11-step observation window of the agent is rebuilt in its
+// current frame and written to fut_obs (input cols 0-7, position, heading, mask), exactly like the reference does in
+// place.  (The first version ran one thread per row over the 11 steps: 4096 threads on the whole GPU, 45 us.)
+__global__ void __launch_bounds__(128) step_env_kernel(const float* __restrict__ traj, const float* __restrict__ vel,
                                 const float* __restrict__ init_pos, const float* __restrict__ init_heading,
                                 const int* __restrict__ p_row, const int* __restrict__ p_slot, int P, int T, int tidx,
                                 float* __restrict__ p_pos, float* __restrict__ p_ori, float* __restrict__ fut_in,
                                 uint8_t* __restrict__ fut_mask, float* __restrict__ fut_pos,
                                 float* __restrict__ fut_head) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = blockIdx.x * 8 + (threadIdx.x >> 4), i = threadIdx.x & 15;
   if (p >= P) return;
   const int row = p_row[p];
   const float4* tr = reinterpret_cast<const float4*>(traj) + (size_t)row * T;
@@ -60,41 +61,31 @@ __global__ void step_env_kernel(const float* __restrict__ traj, const float* __r
   const float px = init_pos[row * 2 + 0] + last.x, py = init_pos[row * 2 + 1] + last.y;
   const float th_last = atan2f(last.z, last.w);
   const float heading = wrap_angle(th_last + init_heading[row]);
-  p_pos[p * 2 + 0] = px;
-  p_pos[p * 2 + 1] = py;
-  p_ori[p] = heading;
-  if (fut_in == nullptr) return;
+  if (i == 0) {
+    p_pos[p * 2 + 0] = px;
+    p_pos[p * 2 + 1] = py;
+    p_ori[p] = heading;
+  }
+  if (fut_in == nullptr || i >= HIST) return;
   const int slot = p_slot[p];
-  float* dst = fut_in + (size_t)slot * HIST * 24;
   const float nth = -th_last;
   const float c = cosf(nth), s = sinf(nth);
-  float2 rv_prev;
-  {
-    float2 v = vl[tidx - HIST - 1];
-    rv_prev = make_float2(v.x * c - v.y * s, v.y * c + v.x * s);
+  const float2 vp = vl[tidx - HIST + i - 1], v = vl[tidx - HIST + i];
+  const float2 rv_prev = make_float2(vp.x * c - vp.y * s, vp.y * c + vp.x * s);
+  const float2 rv = make_float2(v.x * c - v.y * s, v.y * c + v.x * s);
+  const float4 w = tr[tidx - HIST + i];
+  const float ox = w.x - last.x, oy = w.y - last.y;
+  const float dth = wrap_angle(atan2f(w.z, w.w) - th_last);
+  float* o = fut_in + ((size_t)slot * HIST + i) * 24;
+  *reinterpret_cast<float4*>(o) = make_float4(ox * c - oy * s, oy * c + ox * s, sinf(dth), cosf(dth));
+  *reinterpret_cast<float4*>(o + 4) = make_float4(rv.x, rv.y, (rv.x - rv_prev.x) / 0.1f, (rv.y - rv_prev.y) / 0.1f);
+  unsigned long long* m = reinterpret_cast<unsigned long long*>(fut_mask + ((size_t)slot * HIST + i) * 24);
+  m[0] = m[1] = m[2] = 0x0101010101010101ull;
+  if (i == 0) {
+    fut_pos[slot * 2 + 0] = px;
+    fut_pos[slot * 2 + 1] = py;
+    fut_head[slot] = heading;
   }
-  for (int i = 0; i < HIST; ++i) {
-    const float4 w = tr[tidx - HIST + i];
-    const float ox = w.x - last.x, oy = w.y - last.y;
-    const float dth = wrap_angle(atan2f(w.z, w.w) - th_last);
-    const float2 v = vl[tidx - HIST + i];
-    const float2 rv = make_float2(v.x * c - v.y * s, v.y * c + v.x * s);
-    float* o = dst + i * 24;
-    o[0] = ox * c - oy * s;
-    o[1] = oy * c + ox * s;
-    o[2] = sinf(dth);
-    o[3] = cosf(dth);
-    o[4] = rv.x;
-    o[5] = rv.y;
-    o[6] = (rv.x - rv_prev.x) / 0.1f;
-    o[7] = (rv.y - rv_prev.y) / 0.1f;
-    rv_prev = rv;
-    uint8_t* m = fut_mask + ((size_t)slot * HIST + i) * 24;
-    for (int k = 0; k < 24; ++k) m[k] = 1;
-  }
-  fut_pos[slot * 2 + 0] = px;
-  fut_pos[slot * 2 + 1] = py;
-  fut_head[slot] = heading;
 }
 
 // compact gather of token poses: out_pos[i] = pos[rows[i]], out_ori[i] = head[rows[i]]
