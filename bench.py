@@ -333,7 +333,10 @@ def run_b200(a):
                     'algorithmic_bytes_per_launch': n_bytes / n_launch, 'edges_per_forward': n_edges,
                     'share_of_step': edge_ms / total_ms if world == 1 else None,
                     'fp32_ffma_frac': (n_edges * 3072.0 / n_launch) / (avg_ms * 1e-3) / 1e12 / ffma_peak,
-                    'note': 'one warp per row, z tiles by TMA; issue/latency bound at 12 warps per SM (profiles/), DESIGN.md section 5'}
+                    'note': 'one warp per row, z tiles by TMA; issue/latency bound at 12 warps per SM (profiles/), DESIGN.md '
+                            'section 5.  Reported as THE roofline kernel because the edge phase (edge_qk + attn_edge4 + edge_av) '
+                            'is the largest share of a step (45 %); the single largest kernel class by a hair is the tcgen05 '
+                            'node kernel, reported under roofline_dense_kernel'}
             cap = ncu_traffic('attn_edge4_kernel a2p')
             if cap is not None:
                 # the committed ncu --set full capture is ONE launch (first policy a2p layer); its algorithmic bytes are
