@@ -81,6 +81,8 @@ size_t prosim_attn_workspace_floats(int n_dst, int n_src, int max_stride);
 /* PointNet polyline encoder: prosim/models/scene_encoder/pointnet_encoder.py:24-62.
  * kind 0 = agent history (11 points x 24 features, mask uint8 [.,11,24]; obs_encoder.py:75-86)
  * kind 1 = map polyline  (19 vectors x 11 features, mask uint8 [.,19];   map_encoder.py:67-88)
+ * kind 2 / 3 = drag-point condition (16 / 8 points x 2 features; condition_transformer/condition_encoders.py:147-191);
+ *          mask may be NULL: a point is then valid when neither coordinate is NaN (:178)
  * rows[n_poly] selects the polylines to encode out of x; out is compact [n_poly][128]. */
 int prosim_pointnet_fwd(int kind, const float* x, const uint8_t* mask, const int32_t* rows, int n_poly,
                         const float* w, float* out, prosim_stream_t stream);
@@ -123,6 +125,15 @@ int prosim_reconst_fwd(const float* emd, int P, const float* w, float* out, pros
 /* PromptEncoder (prompt_encoder/base.py:30,37-50) / GoalConditionEncoder (condition_encoders.py:21-51) */
 int prosim_mlp2_fwd(const float* in, int ld_in, int k0, int n, int use_ln, const float* w, const float* tpe_t,
                     int tpe_ld, const float* dim_t128, float* out, prosim_stream_t stream);
+/* MotionTagEncoder for unary action tags (condition_transformer/condition_encoders.py:76-145): tags int64 [n][3] =
+ * (tag id, start step, end step); table [16][128] indexed by tag id; out [n][128] = tag vector + FourierEmbeddingFix(64)
+ * of start | end.  Rows with an id outside [0, n_tags) become zeros. */
+int prosim_tag_embed_fwd(const int64_t* tags, int n, int n_tags, const float* table, const float* dim_t64, float* out,
+                         prosim_stream_t stream);
+/* GNNConditionAttn edge matrix + mean pooling for unary conditions (condition_transformer/condition_attns.py:114-189):
+ * slot int32 [P][n_slots] = row of emb per (policy row, condition type) or -1; extra [P][128], has int32 [P]. */
+int prosim_cond_pool_fwd(const float* emb, const int32_t* slot, int P, int n_slots, float* extra, int32_t* has,
+                         prosim_stream_t stream);
 
 /* ProSim.init_agent_trajs (traj_sam.py:597-633) */
 int prosim_init_traj(const float* obs_in, const float* obs_pos, const float* obs_head, const int32_t* p_slot,

@@ -78,9 +78,11 @@ class ProSimOracle:
     def __init__(self, state_dict, goal_condition=None, dtype=torch.float32, faithful_bookkeeping=False):
         self.w = {k: v.detach().to(dtype).cpu() for k, v in state_dict.items()}
         self.dtype = dtype
-        if goal_condition is None:
-            goal_condition = any(k.startswith('condition_transformers.') for k in self.w)
-        self.goal_condition = goal_condition
+        ce = 'condition_transformers.policy_decoder.condition_encoders.'
+        if goal_condition is None or goal_condition is True:        # types in PROMPT.CONDITION.TYPES order
+            goal_condition = tuple(t for t in ('goal', 'v_action_tag', 'drag_point') if any(k.startswith(ce + t) for k in self.w))
+        self.cond_types = tuple(goal_condition or ())
+        self.goal_condition = bool(self.cond_types)
         self.faithful_bookkeeping = faithful_bookkeeping
         self.trace = None  # set to [] to record per-tick state for teacher-forced tests
         self.trace_states = []
@@ -225,37 +227,83 @@ class ProSimOracle:
         out = dict(emd=emd, agent_type=prompt['agent_type'])
         cond = batch.extras['condition']
         if self.goal_condition:
-            out['emd'] = self.goal_condition_attn(cond, emd, mask, prompt['position'].to(self.dtype),
+            out['emd'] = self.condition_attn(cond, emd, mask, prompt['position'].to(self.dtype),
                                                   prompt['heading'].to(self.dtype))
         return out
 
-    def goal_condition_attn(self, cond, emd, mask, position, heading):
-        """condition_transformer/base.py:38-60, condition_encoders.py:21-51, condition_attns.py:114-228.
-        A goal condition on agent n is a self edge n->n whose attribute is the goal embedding
-        (mean-pooled over one condition type = itself) plus the rel-PE of a zero offset."""
+    def encode_conditions(self, cond):
+        """condition_transformer/base.py:38-48 + condition_encoders.py: one {'emd','mask','prompt_idx'} dict per
+        condition type, in encoder (= PROMPT.CONDITION.TYPES) order; v_action_tag expands into one entry per used tag
+        that occurs in the batch (condition_encoders.py:107-143)."""
+        ct = 'condition_transformers.policy_decoder.condition_encoders'
+        out = {}
+        for t in self.cond_types:
+            if t not in cond.keys() or cond[t]['input'].shape[1] == 0:
+                continue
+            c = cond[t]
+            if t == 'goal':                                              # condition_encoders.py:21-51
+                gi = c['input'].to(self.dtype)
+                emd = self.mlp(f'{ct}.goal.goal_encoder', gi[..., :2], 2, ret_before_act=True, without_norm=True)
+                out['goal'] = dict(emd=emd + fourier_fix(gi[..., 2:], 128), mask=c['mask'], prompt_idx=c['prompt_idx'])
+            elif t == 'drag_point':                                      # condition_encoders.py:162-191
+                pts = c['input'].to(self.dtype)
+                emd = self.pointnet(f'{ct}.drag_point.pointnet_encoder', pts, ~(pts.isnan().any(-1)), 1, 2)
+                out['drag_point'] = dict(emd=emd, mask=c['mask'], prompt_idx=c['prompt_idx'])
+            elif t == 'v_action_tag':                                    # condition_encoders.py:76-145
+                from prosim_b200.weights import V_ACTION_TAGS, V_ACTION_TAG_ID
+                inp = c['input']
+                B, C = inp.shape[:2]
+                bi = torch.arange(B)[:, None].expand(-1, C)
+                ci = torch.arange(C)[None, :].expand(B, -1)
+                for tag in V_ACTION_TAGS:
+                    sel = inp[..., 0] == V_ACTION_TAG_ID[tag]
+                    if int(sel.sum()) == 0:
+                        continue
+                    cnt = sel.sum(1)
+                    T = int(cnt.max())
+                    tmask = torch.arange(T)[None, :].expand(B, -1) < cnt[:, None]
+                    emd = torch.zeros(B, T, 128, dtype=self.dtype)
+                    vmask = torch.zeros(B, T, dtype=torch.bool)
+                    pidx = -torch.ones(B, T, 1, dtype=torch.long)
+                    tb, tc = bi[sel], ci[sel]
+                    vmask[tmask] = c['mask'][tb, tc]
+                    pidx[tmask] = c['prompt_idx'][tb, tc]
+                    e = self.w[f'{ct}.v_action_tag.tag_encoder.{tag}'][None, :].expand(int(sel.sum()), -1)
+                    e = e + fourier_fix(inp[tb, tc, 1:3], 64).to(self.dtype)
+                    emd[tmask] = e
+                    out[tag] = dict(emd=emd, mask=vmask, prompt_idx=pidx)
+            else:
+                raise NotImplementedError(t)
+        return out
+
+    def condition_attn(self, cond, emd, mask, position, heading):
+        """condition_transformer/base.py:38-60, condition_attns.py:114-228.  A unary condition on agent n is a self
+        edge n->n; its attribute is the MEAN over the condition types present on that agent (COND_POOL_FUNC 'mean',
+        condition_attns.py:186-189) plus the rel-PE of a zero offset.  The 3-layer GNN output is added to every valid
+        prompt row (condition_attns.py:226)."""
         ct = 'condition_transformers.policy_decoder'
-        if 'goal' not in cond.keys() or cond['goal']['input'].shape[1] == 0:
+        emds = self.encode_conditions(cond)
+        if len(emds) == 0:
             return emd
-        gi = cond['goal']['input'].to(self.dtype)
-        g_emd = self.mlp(f'{ct}.condition_encoders.goal.goal_encoder', gi[..., :2], 2, ret_before_act=True,
-                         without_norm=True)
-        g_emd = g_emd + fourier_fix(gi[..., 2:], 128)
-        cmask = cond['goal']['mask']
         B, N = mask.shape
-        C = g_emd.shape[1]
-        edge_attr = torch.zeros(B, N, N, 1, 128, dtype=self.dtype)
-        edge_mask = torch.zeros(B, N, N, 1, dtype=torch.bool)
-        bidx = torch.arange(B).unsqueeze(-1).expand(B, C)[cmask]
-        nidx = cond['goal']['prompt_idx'][..., 0][cmask]
-        edge_attr[bidx, nidx, nidx, 0] = g_emd[cmask]
-        edge_mask[bidx, nidx, nidx, 0] = True
+        M = len(emds)
+        edge_attr = torch.zeros(B, N, M, 128, dtype=self.dtype)          # the [B,N,N,M,D] matrix is diagonal in (N,N)
+        edge_mask = torch.zeros(B, N, M, dtype=torch.bool)
+        for m, d in enumerate(emds.values()):
+            cmask = d['mask']
+            C = d['emd'].shape[1]
+            bidx = torch.arange(B).unsqueeze(-1).expand(B, C)[cmask]
+            nidx = d['prompt_idx'][..., 0][cmask]
+            edge_attr[bidx, nidx, m] = d['emd'][cmask]
+            edge_mask[bidx, nidx, m] = True
         edge_attr = edge_attr.sum(dim=-2) / edge_mask.sum(dim=-1).clamp(min=1)[..., None]
         edge_mask = edge_mask.any(dim=-1)
         node_idx = -torch.ones(B, N, dtype=torch.long)
         node_idx[mask] = torch.arange(int(mask.sum()))
         ve = edge_mask.nonzero()
-        e = torch.stack([node_idx[ve[:, 0], ve[:, 1]], node_idx[ve[:, 0], ve[:, 2]]], dim=0)
+        e = torch.stack([node_idx[ve[:, 0], ve[:, 1]], node_idx[ve[:, 0], ve[:, 1]]], dim=0)
         r = edge_attr[edge_mask] + self.rel_pe(e, heading[mask], position[mask], heading[mask], position[mask])
+        self._dbg_cond = dict(attr=edge_attr, has=edge_mask)
         x_p = emd[mask]
         for i in range(3):
             x_p = self.attention_layer(f'{ct}.condition_attn.attn_layers.{i}', x_p, x_p, r, e, False)

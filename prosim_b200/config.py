@@ -43,7 +43,10 @@ _DEFAULTS = {
     'TASK': {'TYPES': ['motion_pred'], 'MOTION_PRED': {'PROMPT': 'agent_status'}},
     'PROMPT': {
         'AGENT_STATUS': {'USE_VEL': True, 'USE_EXTEND': True, 'USE_AGENT_TYPE': True},
-        'CONDITION': {'TYPES': [], 'EVAL_COND_SETS': []},
+        'CONDITION': {'TYPES': [], 'EVAL_COND_SETS': [],
+                      'MOTION_TAG': {'USED_TAGS': ['Accelerate', 'Decelerate', 'KeepSpeed', 'Stopping', 'LeftLaneChange',
+                                                   'RightLaneChange', 'KeepLane', 'LeftTurn', 'RightTurn', 'Straight',
+                                                   'Parked']}},
     },
     'ROLLOUT': {
         'PARALLEL_NUM': 1,
@@ -82,7 +85,8 @@ _DEFAULTS = {
         'CONDITION_TRANSFORMER': {'USE_TEMPORAL_ENCODING': True, 'ATTN_TYPE': 'gnn', 'NLAYER': 3, 'NHEAD': 8,
                                   'FF_DIM': 16, 'DROPOUT': 0.1, 'COND_POOL_FUNC': 'mean',
                                   'CONDITION_LOCATIONS': ['policy_decoder'], 'USE_PLACEHOLDER': True,
-                                  'PE': {'ENABLE': True}},
+                                  'PE': {'ENABLE': True},
+                                  'CONDITION_ENCODER': {'DRAG_POINTS': {'NUM_PRE_LAYERS': 1, 'NUM_MLP_LAYERS': 3}}},
     },
 }
 
@@ -119,7 +123,11 @@ def check_supported(cfg):
         problems.append('MODEL.POLICY.ACT_DECODER.TRAJ must be K=1, anchor, PRED_VEL, no GMM')
     if m.DECODER.GOAL_PRED.ENABLE:
         problems.append('MODEL.DECODER.GOAL_PRED must be disabled')
-    if set(cfg.PROMPT.CONDITION.TYPES) - {'goal'}:
-        problems.append("PROMPT.CONDITION.TYPES may only contain 'goal'")
+    if set(cfg.PROMPT.CONDITION.TYPES) - {'goal', 'v_action_tag', 'drag_point'}:
+        problems.append("PROMPT.CONDITION.TYPES may only contain 'goal', 'v_action_tag', 'drag_point' (no v2v / text conditions)")
+    if len(set(cfg.PROMPT.CONDITION.TYPES)) != len(cfg.PROMPT.CONDITION.TYPES):
+        problems.append('PROMPT.CONDITION.TYPES has duplicates')
+    if cfg.PROMPT.CONDITION.TYPES and m.CONDITION_TRANSFORMER.COND_POOL_FUNC != 'mean':
+        problems.append("MODEL.CONDITION_TRANSFORMER.COND_POOL_FUNC must be 'mean'")
     if problems:
         raise NotImplementedError('; '.join(problems))

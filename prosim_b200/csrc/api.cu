@@ -95,6 +95,8 @@ int setup_attributes() {
   acc(allow_smem(attn_post_kernel<1>, PostSmem<1>::bytes));
   acc(allow_smem(pointnet_kernel<24, 24, 1, 11>, PointNetCfg<11>::smem_bytes));
   acc(allow_smem(pointnet_kernel<11, 12, 3, 19>, PointNetCfg<19>::smem_bytes));
+  acc(allow_smem(pointnet_kernel<2, 4, 1, 16>, PointNetCfg<16>::smem_bytes));
+  acc(allow_smem(pointnet_kernel<2, 4, 1, 8>, PointNetCfg<8>::smem_bytes));
   acc(allow_smem(knn_kernel, 64 * 1024));
   acc(allow_smem(attn_kv2_kernel<4, 8>, Kv2Smem<4, 8>::bytes));
   acc(allow_smem(attn_kv2_kernel<8, 8>, Kv2Smem<8, 8>::bytes));
@@ -323,7 +325,7 @@ int launch_post(const float* x, int n, int zd, const float* rbar, const float* a
 
 extern "C" {
 
-int prosim_abi_version(void) { return 5; }
+int prosim_abi_version(void) { return 6; }
 int prosim_tc_debug_read(long long* out32) {
   if (!out32) return ERR_ARG;
   return (int)cudaMemcpyFromSymbol(out32, tcp::g_tcp_dbg, 32 * sizeof(long long));
@@ -383,18 +385,26 @@ size_t prosim_attn_workspace_floats(int n_dst, int n_src, int max_stride) {
 
 int prosim_pointnet_fwd(int kind, const float* x, const uint8_t* mask, const int32_t* rows, int n_poly, const float* w,
                         float* out, prosim_stream_t stream) {
-  if (n_poly < 0 || (kind != 0 && kind != 1)) return ERR_ARG;
+  if (n_poly < 0 || kind < 0 || kind > 3) return ERR_ARG;
   if (n_poly == 0) return 0;
-  if (!x || !mask || !rows || !w || !out) return ERR_ARG;
+  if (!x || (!mask && kind < 2) || !rows || !w || !out) return ERR_ARG;
   if (int e = setup_attributes()) return e;
   LaunchScope ls(PROSIM_K_POINTNET, S(stream));
   if (kind == 0) {
     constexpr int G = PointNetCfg<11>::G;
     pointnet_kernel<24, 24, 1, 11><<<(n_poly + G - 1) / G, 256, PointNetCfg<11>::smem_bytes, S(stream)>>>(
         x, mask, 24, rows, n_poly, w, out);
-  } else {
+  } else if (kind == 1) {
     constexpr int G = PointNetCfg<19>::G;
     pointnet_kernel<11, 12, 3, 19><<<(n_poly + G - 1) / G, 256, PointNetCfg<19>::smem_bytes, S(stream)>>>(
+        x, mask, 1, rows, n_poly, w, out);
+  } else if (kind == 2) {
+    constexpr int G = PointNetCfg<16>::G;
+    pointnet_kernel<2, 4, 1, 16><<<(n_poly + G - 1) / G, 256, PointNetCfg<16>::smem_bytes, S(stream)>>>(
+        x, mask, 1, rows, n_poly, w, out);
+  } else {
+    constexpr int G = PointNetCfg<8>::G;
+    pointnet_kernel<2, 4, 1, 8><<<(n_poly + G - 1) / G, 256, PointNetCfg<8>::smem_bytes, S(stream)>>>(
         x, mask, 1, rows, n_poly, w, out);
   }
   PROSIM_CHECK_LAUNCH();
@@ -634,6 +644,29 @@ int prosim_mlp2_fwd(const float* in, int ld_in, int k0, int n, int use_ln, const
   const int rpt = pick_rpt(n);
   LaunchScope ls(PROSIM_K_MLP2, S(stream));
   DISPATCH_RPT(rpt, mlp2_kernel<RPT><<<(n + 2 * RPT - 1) / (2 * RPT), 256, 0, S(stream)>>>(in, ld_in, k0, n, use_ln, w, tpe_t, tpe_ld, dim_t128, out));
+  PROSIM_CHECK_LAUNCH();
+  return 0;
+}
+
+int prosim_tag_embed_fwd(const int64_t* tags, int n, int n_tags, const float* table, const float* dim_t64, float* out,
+                         prosim_stream_t stream) {
+  if (n < 0 || n_tags < 0 || n_tags > 16) return ERR_ARG;
+  if (n == 0) return 0;
+  if (!tags || !table || !dim_t64 || !out) return ERR_ARG;
+  LaunchScope ls(PROSIM_K_MLP2, S(stream));
+  tag_embed_kernel<<<(n * D + 255) / 256, 256, 0, S(stream)>>>(reinterpret_cast<const long long*>(tags), n, n_tags, table,
+                                                               dim_t64, out);
+  PROSIM_CHECK_LAUNCH();
+  return 0;
+}
+
+int prosim_cond_pool_fwd(const float* emb, const int32_t* slot, int P, int n_slots, float* extra, int32_t* has,
+                         prosim_stream_t stream) {
+  if (P < 0 || n_slots <= 0) return ERR_ARG;
+  if (P == 0) return 0;
+  if (!emb || !slot || !extra || !has) return ERR_ARG;
+  LaunchScope ls(PROSIM_K_MLP2, S(stream));
+  cond_pool_kernel<<<(P * D + 255) / 256, 256, 0, S(stream)>>>(emb, slot, P, n_slots, extra, has);
   PROSIM_CHECK_LAUNCH();
   return 0;
 }

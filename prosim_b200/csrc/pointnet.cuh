@@ -1,5 +1,6 @@
 // PointNet polyline encoder (reference: prosim/models/scene_encoder/pointnet_encoder.py:24-62 with the
-// obs / map configurations of obs_encoder.py:75-86 and map_encoder.py:67-88).
+// obs / map configurations of obs_encoder.py:75-86 and map_encoder.py:67-88, and the drag-point condition encoder
+// condition_transformer/condition_encoders.py:147-191).
 //   pre_mlps (per point) -> max-pool over the polyline -> [point | pooled] -> mlps -> max-pool -> out_mlps
 // Masked points contribute zeros to both max-pools (the reference scatters valid rows into a zero buffer);
 // since every pooled tensor is a ReLU output this equals a max over valid points clamped at 0.
@@ -20,7 +21,8 @@ struct PointNetCfg {
   static constexpr size_t smem_bytes = smem_floats * sizeof(float);
 };
 
-// X: [n_all][P][IN] raw inputs, mask: uint8 [n_all][P][mask_inner] (point valid = all mask_inner bytes != 0)
+// X: [n_all][P][IN] raw inputs, mask: uint8 [n_all][P][mask_inner] (point valid = all mask_inner bytes != 0);
+// mask == nullptr: validity is derived from the data (no NaN feature) -- the drag-point condition encoder
 // rows: [n_poly] indices into n_all (compaction list of valid polylines); Out: [n_poly][128]
 template <int IN, int IN_PAD, int NPRE, int P>
 __global__ void __launch_bounds__(256) pointnet_kernel(const float* __restrict__ X, const uint8_t* __restrict__ mask,
@@ -41,9 +43,14 @@ __global__ void __launch_bounds__(256) pointnet_kernel(const float* __restrict__
   for (int r = threadIdx.x; r < ROWS; r += 256) {
     int g = r / P, p = r % P, v = 0;
     if (g < G && poly0 + g < n_poly) {
-      const uint8_t* m = mask + ((size_t)rows[poly0 + g] * P + p) * mask_inner;
       v = 1;
-      for (int i = 0; i < mask_inner; ++i) v &= (m[i] != 0);
+      if (mask != nullptr) {
+        const uint8_t* m = mask + ((size_t)rows[poly0 + g] * P + p) * mask_inner;
+        for (int i = 0; i < mask_inner; ++i) v &= (m[i] != 0);
+      } else {   // no mask tensor: a point is valid when none of its features is NaN (condition_encoders.py:178)
+        const float* xp = X + ((size_t)rows[poly0 + g] * P + p) * IN;
+        for (int i = 0; i < IN; ++i) v &= !isnan(xp[i]);
+      }
     }
     sValid[r] = v;
   }

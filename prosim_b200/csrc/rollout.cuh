@@ -292,4 +292,47 @@ __global__ void __launch_bounds__(256) mlp2_kernel(const float* __restrict__ in,
   }
 }
 
+// MotionTagEncoder for the unary action tags (condition_transformer/condition_encoders.py:76-145): one learned
+// vector per tag plus FourierEmbeddingFix(64) of the start and of the end step, concatenated (:132-137).
+// tags: int64 [n][3] = (tag id, start, end) as the dataset stores them; table: [16][128], row = tag id.
+// Rows whose id is outside [0, n_tags) (the -1 padding) are written as zeros.  One thread per output float.
+__global__ void __launch_bounds__(256) tag_embed_kernel(const long long* __restrict__ tags, int n, int n_tags,
+                                                        const float* __restrict__ table,
+                                                        const float* __restrict__ dim_t64, float* __restrict__ out) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const int e = idx >> 7, c = idx & 127;
+  if (e >= n) return;
+  const long long id = tags[(size_t)e * 3];
+  float v = 0.f;
+  if (id >= 0 && id < n_tags) {
+    const float t = (float)tags[(size_t)e * 3 + 1 + (c >> 6)];
+    const float a = (t * 6.28318530717958647692f) / dim_t64[c & 63];
+    v = table[(int)id * D + c] + ((c & 1) ? cosf(a) : sinf(a));
+  }
+  out[(size_t)e * D + c] = v;
+}
+
+// GNNConditionAttn._construct_cond_edge_matrix + _pool_edges restricted to unary conditions (self edges)
+// (condition_transformer/condition_attns.py:114-189, COND_POOL_FUNC 'mean'): per policy row, the condition embeddings
+// of the condition types present on it are summed in type order and divided by their number.
+// slot: int32 [P][n_slots], row of emb for (policy row, condition type) or -1.  extra: [P][128]; has[p] = 1 if any.
+__global__ void __launch_bounds__(256) cond_pool_kernel(const float* __restrict__ emb, const int* __restrict__ slot,
+                                                        int P, int n_slots, float* __restrict__ extra,
+                                                        int* __restrict__ has) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  const int p = idx >> 7, c = idx & 127;
+  if (p >= P) return;
+  float s = 0.f;
+  int cnt = 0;
+  for (int m = 0; m < n_slots; ++m) {
+    const int e = slot[(size_t)p * n_slots + m];
+    if (e >= 0) {
+      s = __fadd_rn(s, emb[(size_t)e * D + c]);
+      ++cnt;
+    }
+  }
+  extra[(size_t)p * D + c] = cnt ? __fdiv_rn(s, (float)cnt) : 0.f;
+  if (c == 0) has[p] = cnt > 0;
+}
+
 }  // namespace prosim

@@ -8,7 +8,7 @@ from ctypes import POINTER, Structure, c_float, c_int, c_int32, c_size_t, c_void
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libprosim_b200.so')
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 SYMBOLS = (
     'prosim_abi_version', 'prosim_attn_layer_floats', 'prosim_pointnet_floats', 'prosim_head_floats',
@@ -16,7 +16,7 @@ SYMBOLS = (
     'prosim_build_knn_edges', 'prosim_edge_pe', 'prosim_attn_kv', 'prosim_attn_layer_fwd', 'prosim_attn_stack_fwd',
     'prosim_policy_head_fwd', 'prosim_reconst_fwd', 'prosim_mlp2_fwd', 'prosim_init_traj', 'prosim_step_env',
     'prosim_gather_pose', 'prosim_step_agent_traj', 'prosim_launch_count', 'prosim_profile_enable', 'prosim_profile_read',
-    'prosim_rollout_to_world', 'prosim_tc_gemm_test', 'prosim_set_tensor_core', 'prosim_tc_debug_read', 'prosim_set_stack_split',
+    'prosim_rollout_to_world', 'prosim_tc_gemm_test', 'prosim_set_tensor_core', 'prosim_tc_debug_read', 'prosim_set_stack_split', 'prosim_tag_embed_fwd', 'prosim_cond_pool_fwd',
 )
 
 KERNEL_CLASSES = {'pointnet': 0, 'radius': 1, 'knn': 2, 'edge_pe': 3, 'attn_kv': 4, 'attn_dstpre': 5, 'attn_edge': 6,
@@ -48,6 +48,8 @@ _SIGS = {
     'prosim_policy_head_fwd': [_P, _P, c_int, _P, _P, _P],
     'prosim_reconst_fwd': [_P, c_int, _P, _P, _P],
     'prosim_mlp2_fwd': [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P],
+    'prosim_tag_embed_fwd': [_P, c_int, c_int, _P, _P, _P, _P],
+    'prosim_cond_pool_fwd': [_P, _P, c_int, c_int, _P, _P, _P],
     'prosim_init_traj': [_P, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P],
     'prosim_step_env': [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P],
     'prosim_gather_pose': [_P, _P, _P, c_int, _P, _P, _P],

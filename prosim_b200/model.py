@@ -95,6 +95,7 @@ class ProSimB200(nn.Module):
         cfg = self.config
         self.tasks = list(cfg.TASK.TYPES)
         self.use_condition = len(cfg.PROMPT.CONDITION.TYPES) > 0
+        self.cond_types = tuple(cfg.PROMPT.CONDITION.TYPES)
         self.rollout_steps = cfg.ROLLOUT.POLICY.REPLAN_FREQ
         self.hist_step = cfg.DATASET.FORMAT.HISTORY.STEPS
         assert self.rollout_steps == STEP and self.hist_step == HIST and cfg.DATASET.FORMAT.TARGET.STEPS == STEP
@@ -107,8 +108,15 @@ class ProSimB200(nn.Module):
         self._off = None
         self._bufs = {}
         self._plan_cache = []
+        used = [t for t in cfg.PROMPT.CONDITION.MOTION_TAG.USED_TAGS if t in weights.V_ACTION_TAG_ID]   # condition_encoders.py:58
+        if 'v_action_tag' in self.cond_types and tuple(used) != weights.V_ACTION_TAGS:
+            raise NotImplementedError('PROMPT.CONDITION.MOTION_TAG.USED_TAGS differs from the released list')
+        lut = -torch.ones(16, dtype=torch.int64)        # tag id (motion_tag_utils.py:4-15) -> position in USED_TAGS
+        for pos, tag in enumerate(used):
+            lut[weights.V_ACTION_TAG_ID[tag]] = pos
+        self._tag_slot = lut
         if state_dict is None:
-            state_dict = weights.random_state_dict(0, self.use_condition)
+            state_dict = weights.random_state_dict(0, self.cond_types)
         self.load_state_dict(state_dict)
 
     # ------------------------------------------------------------------ weights
@@ -120,7 +128,7 @@ class ProSimB200(nn.Module):
         return dict(self._sd)
 
     def load_state_dict(self, state_dict, strict=True, assign=False):
-        want = [n for n, _, _ in weights.param_specs(self.use_condition, self.num_layers, self.cond_layers)]
+        want = [n for n, _, _ in weights.param_specs(self.cond_types, self.num_layers, self.cond_layers)]
         missing = [k for k in want if k not in state_dict]
         unexpected = [k for k in state_dict if k not in set(want)]
         if missing or (strict and unexpected):
@@ -377,7 +385,7 @@ class ProSimB200(nn.Module):
             self._note_edges('gen_p2p', e_pp, self.num_layers)
             self._note_edges('gen_s2p', e_sp, self.num_layers)
             if self.use_condition and 'policy_decoder' in self.config.MODEL.CONDITION_TRANSFORMER.CONDITION_LOCATIONS:
-                emd_flat = self._goal_condition(batch.extras['condition'], emd_flat, p_pos, p_ori, pl, ws)
+                emd_flat = self._conditions(batch.extras['condition'], emd_flat, p_pos, p_ori, pl, ws)
             emd = torch.zeros(pl.B * pl.N, D, device=self._device)
             emd[rows] = emd_flat
             result[task] = {'emd': emd.view(pl.B, pl.N, D), 'agent_type': enc['agent_type'], '_emd_flat': emd_flat}
@@ -385,31 +393,62 @@ class ProSimB200(nn.Module):
 
     decode_policy = generate_policy  # name used by the reference's rollout helpers (rollout/gpu_utils.py:200,216)
 
-    def _goal_condition(self, cond, emd_flat, p_pos, p_ori, pl, ws):
-        """condition_transformer/base.py:38-60: goal embedding on a self edge per conditioned agent, 3 GNN layers,
-        result added to the policy embedding of EVERY valid prompt row (condition_attns.py:226)."""
-        if 'goal' not in cond.keys() or cond['goal']['input'].shape[1] == 0:
-            return emd_flat
+    def _conditions(self, cond, emd_flat, p_pos, p_ori, pl, ws):
+        """condition_transformer/base.py:38-60.  Every condition entry is encoded by the encoder of its type (goal MLP +
+        time PE, tag vector + interval PE, drag-point PointNet: condition_encoders.py), the embeddings of the types present
+        on an agent are mean-pooled onto its self edge (condition_attns.py:114-189), 3 GNN layers run over those edges
+        and the result is added to the policy embedding of EVERY valid prompt row (condition_attns.py:226).
+        Two entries of the same type (same tag name) on one agent: the reference keeps whichever index_put wrote last;
+        here as well one of them wins (which one is unspecified)."""
         ar, off = self._arena, self._off
-        g = cond['goal']
+        dev = self._device
         P, B, N = pl.P, pl.B, pl.N
-        C = g['input'].shape[1]
-        bidx = torch.arange(B, device=self._device)[:, None].expand(B, C)
-        nidx = g['prompt_idx'][..., 0].clamp(min=0)
-        row = pl.i['prow_lut'].long()[(bidx * N + nidx).reshape(-1)]
-        valid = g['mask'].reshape(-1) & (row >= 0)
-        row = torch.where(valid, row, torch.full_like(row, P))
-        goal_in = torch.zeros(P + 1, 4, device=self._device)
-        goal_in[:, :3].index_put_((row,), g['input'].reshape(-1, 3).float())
-        has = torch.zeros(P + 1, device=self._device, dtype=torch.int32)
-        has.index_put_((row,), torch.ones_like(row, dtype=torch.int32))
-        goal_in, has = goal_in[:P].contiguous(), has[:P].contiguous()
         dim_t = ar[off['dim_t16']:off['dim_t16'] + 16]
-        dim_t128 = ar[off['dim_t128']:off['dim_t128'] + 128]
-        g_emd = ops.mlp2(goal_in, 2, False, ar, off['goal_mlp'], tpe_col=2, dim_t128=dim_t128)
-        nbr = torch.arange(P, device=self._device, dtype=torch.int32)
+        n_tags = len(weights.V_ACTION_TAGS)
+        embs, puts, n_emb, n_slots = [], [], 0, 0
+        for t in self.cond_types:
+            width = n_tags if t == 'v_action_tag' else 1
+            if t in cond.keys() and cond[t]['input'].shape[1] > 0:
+                c = cond[t]
+                C = c['input'].shape[1]
+                if t == 'goal':
+                    x = c['input'].reshape(-1, 3).float().contiguous()
+                    emb = ops.mlp2(x, 2, False, ar, off['goal_mlp'], tpe_col=2,
+                                   dim_t128=ar[off['dim_t128']:off['dim_t128'] + 128])
+                    col = torch.zeros(B * C, dtype=torch.int64, device=dev)
+                elif t == 'v_action_tag':
+                    tags = c['input'].reshape(-1, 3).contiguous()
+                    emb = ops.tag_embed(tags, ar[off['tag_vec']:off['tag_vec'] + 16 * D],
+                                        ar[off['dim_t64']:off['dim_t64'] + 64], n_tags)
+                    col = self._tag_slot.to(dev)[tags[:, 0].clamp(0, 15)]   # pooling order = USED_TAGS order
+                else:
+                    T = c['input'].shape[2]
+                    if T not in (16, 8):
+                        raise NotImplementedError(f'drag_point with {T} points per agent (16 or 8 are built)')
+                    x = c['input'].reshape(B * C, T, 2).float().contiguous()
+                    emb = ops.pointnet(2 if T == 16 else 3, x, None, torch.arange(B * C, device=dev, dtype=torch.int32),
+                                       ar, off['drag_enc'])
+                    col = torch.zeros(B * C, dtype=torch.int64, device=dev)
+                bidx = torch.arange(B, device=dev)[:, None].expand(B, C)
+                nidx = c['prompt_idx'][..., 0].clamp(min=0)
+                row = pl.i['prow_lut'].long()[(bidx * N + nidx).reshape(-1)]
+                valid = c['mask'].reshape(-1) & (row >= 0)
+                if t == 'v_action_tag':
+                    valid = valid & (tags[:, 0] >= 0) & (tags[:, 0] < 16) & (col >= 0)
+                row = torch.where(valid, row, torch.full_like(row, P))
+                puts.append((row, n_slots + col.clamp(min=0), n_emb + torch.arange(B * C, device=dev, dtype=torch.int32)))
+                embs.append(emb)
+                n_emb += B * C
+            n_slots += width
+        if not embs:
+            return emd_flat
+        slot = torch.full((P + 1, n_slots), -1, device=dev, dtype=torch.int32)
+        for row, col, ent in puts:
+            slot.index_put_((row, col), ent)
+        extra, has = ops.cond_pool(torch.cat(embs) if len(embs) > 1 else embs[0], slot[:P].contiguous())
+        nbr = torch.arange(P, device=dev, dtype=torch.int32)
         e = ops.EdgeList(nbr, has, 1, 1)
-        ops.edge_pe(e, p_pos, p_ori, p_pos, p_ori, dim_t, extra=g_emd)
+        ops.edge_pe(e, p_pos, p_ori, p_pos, p_ori, dim_t, extra=extra)
         x_c = ops.attn_stack(emd_flat, self.cond_layers, ops.stack_side(ar, off['cond_attn'], e), None, workspace=ws)
         return emd_flat + x_c
 

@@ -59,9 +59,11 @@ class EdgeList:
 
 
 def pointnet(kind, x, mask, rows, w_arena, w_off, out=None):
+    """kind 0 obs / 1 map / 2, 3 drag points (16 / 8 per agent; mask None = validity from NaN)."""
     _chk(x, torch.float32, 'x'), _chk(rows, torch.int32, 'rows')
-    mask = as_u8(mask)
-    _chk(mask, torch.uint8, 'mask')
+    if mask is not None or kind < 2:
+        mask = as_u8(mask)
+        _chk(mask, torch.uint8, 'mask')
     n = rows.shape[0]
     if out is None:
         out = torch.empty(n, D, device=x.device, dtype=torch.float32)
@@ -178,6 +180,25 @@ def mlp2(x, k0, use_ln, w_arena, w_off, tpe_col=None, dim_t128=None):
     lib.call('prosim_mlp2_fwd', ptr(x), ld, int(k0), n, int(bool(use_ln)), ptr(w_arena, w_off), tpe, ld,
              ptr(dim_t128) if tpe_col is not None else None, ptr(out), _stream())
     return out
+
+
+def tag_embed(tags, table, dim_t64, n_tags=11):
+    """tags: int64 [n, 3] (tag id, start, end) -> [n, 128] (condition_encoders.py:76-145)."""
+    _chk(tags, torch.int64, 'tags'), _chk(table, torch.float32, 'table'), _chk(dim_t64, torch.float32, 'dim_t64')
+    n = tags.shape[0]
+    out = torch.empty(n, D, device=tags.device, dtype=torch.float32)
+    lib.call('prosim_tag_embed_fwd', ptr(tags), n, int(n_tags), ptr(table), ptr(dim_t64), ptr(out), _stream())
+    return out
+
+
+def cond_pool(emb, slot):
+    """emb [n, 128], slot int32 [P, n_slots] -> (extra [P, 128], has int32 [P]) (condition_attns.py:114-189)."""
+    _chk(emb, torch.float32, 'emb'), _chk(slot, torch.int32, 'slot')
+    P, ns = slot.shape
+    extra = torch.empty(P, D, device=emb.device, dtype=torch.float32)
+    has = torch.empty(P, device=emb.device, dtype=torch.int32)
+    lib.call('prosim_cond_pool_fwd', ptr(emb), ptr(slot), P, ns, ptr(extra), ptr(has), _stream())
+    return extra, has
 
 
 def init_traj(obs_in, obs_pos, obs_head, p_slot, p_row, T, traj, vel, init_pos, init_heading):

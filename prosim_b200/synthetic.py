@@ -99,8 +99,12 @@ def _one_scene(g, n_agents, n_map):
 
 
 def make_batch(n_scenes=1, n_agents=128, n_map=512, steps=80, goal=False, first_scene=0,
-               agents_per_scene=None, map_per_scene=None, permute_obs=False, pin_memory=False):
+               agents_per_scene=None, map_per_scene=None, permute_obs=False, pin_memory=False, tags=False, drag=False):
     """Build a SceneBatch-like object on the host.
+
+    tags / drag: also attach 'v_action_tag' (dataset/condition_utils.py:177-222: long [B, C, 3] = tag id, start, end,
+    padded with -1) and 'drag_point' (:401-447: [B, A, 16, 2] with NaN at invalid points) conditions; with either of
+    them the goal condition covers a random ~70 % of the agents instead of all, so that agents carry 0..3 condition types.
 
     agents_per_scene / map_per_scene: optional per-scene counts (ragged batch, padded to the max).
     permute_obs: store observation slots in a different order than the prompt slots, so the
@@ -130,6 +134,12 @@ def make_batch(n_scenes=1, n_agents=128, n_map=512, steps=80, goal=False, first_
     goal_mask = torch.zeros(B, A, dtype=torch.bool)
     goal_pidx = -torch.ones(B, A, 1, dtype=torch.int64)
     prompt_ids, obs_ids = [], []
+    mixed = tags or drag
+    tag_rows, tag_pidx = [], []
+    DT = 16
+    drag_in = torch.full((B, A, DT, 2), nan, dtype=f32)
+    drag_mask = torch.zeros(B, A, dtype=torch.bool)
+    drag_pidx = -torch.ones(B, A, 1, dtype=torch.int64)
 
     for b in range(B):
         g = torch.Generator().manual_seed(1000 + first_scene + b)
@@ -159,6 +169,34 @@ def make_batch(n_scenes=1, n_agents=128, n_map=512, steps=80, goal=False, first_
             goal_in[b, :na, 2] = float(steps)
             goal_mask[b, :na] = True
             goal_pidx[b, :na, 0] = torch.arange(na)
+            if mixed:
+                drop = torch.rand(na, generator=g, dtype=f32) > 0.7
+                goal_mask[b, :na][drop] = False
+                goal_pidx[b, :na, 0][drop] = -1
+        if tags:      # up to two DIFFERENT action tags per agent (two of one kind on one agent race in the reference's index_put)
+            rows_b, idx_b = [], []
+            for lo, hi, prob in ((0, 4, 0.6), (7, 10, 0.3)):         # a speed tag and / or a turn tag
+                has = torch.rand(na, generator=g, dtype=f32) < prob
+                tid = torch.randint(lo, hi, (na,), generator=g)
+                t0 = torch.randint(0, 40, (na,), generator=g)
+                t1 = t0 + torch.randint(1, 40, (na,), generator=g)
+                sel = torch.nonzero(has).reshape(-1)
+                rows_b.append(torch.stack([tid[sel], t0[sel], t1[sel]], dim=1).to(torch.int64).view(-1, 3))
+                idx_b.append(sel.to(torch.int64).view(-1, 1))
+            rows_b, idx_b = torch.cat(rows_b), torch.cat(idx_b)
+            perm = torch.randperm(rows_b.shape[0], generator=g)          # conditions are not sorted by agent
+            tag_rows.append(rows_b[perm])
+            tag_pidx.append(idx_b[perm])
+        if drag:
+            has = torch.rand(na, generator=g, dtype=f32) < 0.5
+            for a in torch.nonzero(has).reshape(-1).tolist():
+                n_pts = int(torch.randint(5, DT + 1, (1,), generator=g))
+                start = int(torch.randint(0, DT - n_pts + 1, (1,), generator=g))
+                tt = (torch.arange(DT, dtype=f32) + 1.0) * 0.5
+                pts = torch.stack([sc['speed'][a] * tt, 0.02 * tt * tt], dim=1) + 0.1 * torch.randn(DT, 2, generator=g, dtype=f32)
+                drag_in[b, a, start:start + n_pts] = pts[start:start + n_pts]
+                drag_mask[b, a] = True
+                drag_pidx[b, a, 0] = a
 
     all_t = torch.arange(steps)[::10]
     fut = {}
@@ -170,14 +208,24 @@ def make_batch(n_scenes=1, n_agents=128, n_map=512, steps=80, goal=False, first_
         fut[int(t)] = InputMaskData(f_in, torch.zeros_like(obs_mask), torch.zeros_like(obs_pos),
                                     torch.zeros_like(obs_head), [list(x) for x in obs_ids])
 
+    conds = {}
+    if goal:
+        conds['goal'] = {'input': goal_in, 'mask': goal_mask, 'prompt_idx': goal_pidx, 'prompt_mask': prompt_mask.clone()}
+    if tags:
+        t_in = torch.nn.utils.rnn.pad_sequence(tag_rows, batch_first=True, padding_value=-1)
+        t_idx = torch.nn.utils.rnn.pad_sequence(tag_pidx, batch_first=True, padding_value=-1)
+        conds['v_action_tag'] = {'input': t_in, 'mask': (t_in != -1).all(dim=-1), 'prompt_idx': t_idx,
+                                 'prompt_mask': prompt_mask.clone()}
+    if drag:
+        conds['drag_point'] = {'input': drag_in, 'mask': drag_mask, 'prompt_idx': drag_pidx,
+                               'prompt_mask': prompt_mask.clone()}
     extras = {
         'init_obs': InputMaskData(obs_in, obs_mask, obs_pos, obs_head, obs_ids),
         'init_map': InputMaskData(map_in, map_mask, map_pos, map_head),
         'prompt': BatchPrompt({'motion_pred': {
             'prompt': prompt, 'prompt_mask': prompt_mask, 'position': p_pos, 'heading': p_head,
             'agent_type': p_type, 'agent_ids': prompt_ids}}),
-        'condition': BatchCondition({'goal': {'input': goal_in, 'mask': goal_mask, 'prompt_idx': goal_pidx,
-                                              'prompt_mask': prompt_mask.clone()}} if goal else {}),
+        'condition': BatchCondition(conds),
         'all_t_indices': all_t,
         'fut_obs': BatchDataDict(fut),
     }

@@ -73,7 +73,24 @@ SHARED_LN_STACKS = ('scene_encoder.a2a_attn_layers', 'scene_encoder.s2s_attn_lay
                     'condition_transformers.policy_decoder.condition_attn.attn_layers')
 
 
+V_ACTION_TAGS = ('Accelerate', 'Decelerate', 'KeepSpeed', 'Stopping', 'LeftLaneChange', 'RightLaneChange', 'KeepLane',
+                 'LeftTurn', 'RightTurn', 'Straight', 'Parked')      # PROMPT.CONDITION.MOTION_TAG.USED_TAGS order
+V_ACTION_TAG_ID = {'Stopping': 0, 'Accelerate': 1, 'Decelerate': 2, 'KeepSpeed': 3, 'LeftLaneChange': 4,
+                   'RightLaneChange': 5, 'KeepLane': 6, 'LeftTurn': 7, 'RightTurn': 8, 'Straight': 9,
+                   'Parked': 10}                                      # dataset/motion_tag_utils.py:4-15
+
+
+def cond_types(x):
+    """False / True / a sequence of PROMPT.CONDITION.TYPES -> tuple of types (True = the goal-only demo config)."""
+    if x is True:
+        return ('goal',)
+    if not x:
+        return ()
+    return tuple(x)
+
+
 def param_specs(goal_condition=False, num_layers=6, cond_layers=3):
+    types = cond_types(goal_condition)
     specs = []
     specs += _pointnet('scene_encoder.map_encoder', 11, 5, 3)
     specs += _pointnet('scene_encoder.obs_encoder', 24, 3, 1)
@@ -84,10 +101,19 @@ def param_specs(goal_condition=False, num_layers=6, cond_layers=3):
     for stack in ('p2p', 's2p'):
         for i in range(num_layers):
             specs += _attn_layer(f'decoder.{stack}_attn_layers.{i}')
-    if goal_condition:
+    if types:
+        # condition_transformer/base.py:22-35: one encoder per condition type in TYPES order, then the GNN attention
         ct = 'condition_transformers.policy_decoder'
-        specs += _mlp(f'{ct}.condition_encoders.goal.goal_encoder', [2, D, D], ret_before_act=True,
-                      without_norm=True)
+        for t in types:
+            if t == 'goal':
+                specs += _mlp(f'{ct}.condition_encoders.goal.goal_encoder', [2, D, D], ret_before_act=True,
+                              without_norm=True)
+            elif t == 'v_action_tag':   # condition_encoders.py:71-74: one learned vector per used tag
+                specs += [(f'{ct}.condition_encoders.v_action_tag.tag_encoder.{tag}', (D,), 'emb') for tag in V_ACTION_TAGS]
+            elif t == 'drag_point':     # condition_encoders.py:159-160, config DRAG_POINTS: 1 pre layer, 3 mlp layers
+                specs += _pointnet(f'{ct}.condition_encoders.drag_point.pointnet_encoder', 2, 3, 1)
+            else:
+                raise NotImplementedError(f'condition type {t}')
         for i in range(cond_layers):
             specs += _attn_layer(f'{ct}.condition_attn.attn_layers.{i}')
     pa = 'policy.act_decoder'
@@ -108,7 +134,9 @@ def param_specs(goal_condition=False, num_layers=6, cond_layers=3):
 def random_state_dict(seed=0, goal_condition=False, dtype=torch.float32):
     """Seeded random weights, torch-default-like scales; LayerNorm affine is NOT identity on purpose
     (so the gamma/beta folding in the kernels is exercised).  Non-bipartite layers share one LayerNorm
-    under two names (attention_layer.py:48-49): the dst copy is tied to the src one."""
+    under two names (attention_layer.py:48-49): the dst copy is tied to the src one.
+    goal_condition: False / True (= ('goal',)) / a tuple of PROMPT.CONDITION.TYPES."""
+    goal_condition = cond_types(goal_condition)
     sd = OrderedDict()
     for name, shape, kind in param_specs(goal_condition):
         g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(name.encode())) % (2 ** 63))
@@ -136,6 +164,7 @@ _SHAPES = {}
 
 
 def param_shapes_cache(goal_condition):
+    goal_condition = cond_types(goal_condition)
     if goal_condition not in _SHAPES:
         _SHAPES[goal_condition] = [(n, s) for n, s, _ in param_specs(goal_condition)]
     return _SHAPES[goal_condition]
@@ -328,9 +357,19 @@ def pack_model(sd, num_layers=6, cond_layers=3):
     for name, prefix, n in stacks:
         sections[name] = torch.cat([pack_attn_layer(sd, f'{prefix}.{i}') for i in range(n)])
     sections['prompt_mlp'] = pack_mlp2(sd, 'prompt_encoder.motion_pred.state_encoder', True)
-    if goal:
-        sections['goal_mlp'] = pack_mlp2(sd, 'condition_transformers.policy_decoder.condition_encoders.goal.goal_encoder',
-                                         False)
+    ce = 'condition_transformers.policy_decoder.condition_encoders'
+    if f'{ce}.goal.goal_encoder.mlp.0.weight' in sd:
+        sections['goal_mlp'] = pack_mlp2(sd, f'{ce}.goal.goal_encoder', False)
+    if f'{ce}.v_action_tag.tag_encoder.{V_ACTION_TAGS[0]}' in sd:
+        # row = V_Action_MotionTag value (the id found in the condition input), 11 rows padded to 16
+        table = torch.zeros(16, D)
+        for tag, tid in V_ACTION_TAG_ID.items():
+            table[tid] = sd[f'{ce}.v_action_tag.tag_encoder.{tag}'].float()
+        sections['tag_vec'] = table.reshape(-1)
+        dt = torch.arange(64, dtype=torch.float32)               # FourierEmbeddingFix(num_pos_feats=64): fourier_embedding.py:66-67
+        sections['dim_t64'] = (10000 ** (2 * (dt // 2) / 64)).contiguous()
+    if f'{ce}.drag_point.pointnet_encoder.pre_mlps.mlp.0.weight' in sd:
+        sections['drag_enc'] = pack_pointnet(sd, f'{ce}.drag_point.pointnet_encoder', 1)
     sections['head'] = pack_head(sd)
     # FourierEmbeddingFix denominators, evaluated by torch exactly as the reference does (fourier_embedding.py:66-67)
     dt = torch.arange(128 / 4, dtype=torch.float32)

@@ -3,7 +3,7 @@
 Run once in the authoring container (needs /root/reference):
     python tests/golden/make_golden.py
 Writes tests/golden/<case>.npz (+ state_dict_keys.json).  For every case of BASELINE.json's
-configs 1-4 and two ragged batches: the reference's fp32 rollout (traj, vel, motion_pred,
+configs 1-4, two ragged batches and two batches with mixed goal / action-tag / drag-point conditions: the reference's fp32 rollout (traj, vel, motion_pred,
 reconst_pred, init_pos/heading, pair_names) and the reference's own fp64 evaluation of the same
 inputs/weights (traj64), the arbiter for closed-loop rounding disputes.
 """
@@ -20,7 +20,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle import ref_shim  # noqa: E402
 from prosim_b200 import synthetic, weights  # noqa: E402
 
-from tests.helpers import CASES, to_double as _to_double  # noqa: E402
+from tests.helpers import CASES, cond_suffix, to_double as _to_double  # noqa: E402
 
 
 def _collect(out, ids):
@@ -39,19 +39,21 @@ def _collect(out, ids):
 
 def main():
     torch.set_num_threads(os.cpu_count())
+    only = sys.argv[1:]                      # optional: regenerate just the named cases
+    cases = {n: c for n, c in CASES.items() if not only or n in only}
     models = {}
-    for goal in (False, True):
+    for goal in dict.fromkeys(c[1] for c in cases.values()):
         sd = weights.random_state_dict(0, goal)
-        m32, _ = ref_shim.build_reference_model(('goal',) if goal else ())
+        m32, _ = ref_shim.build_reference_model(weights.cond_types(goal))
         m32.load_state_dict(sd)
-        m64, _ = ref_shim.build_reference_model(('goal',) if goal else (), dtype=torch.float64)
+        m64, _ = ref_shim.build_reference_model(weights.cond_types(goal), dtype=torch.float64)
         m64.load_state_dict({k: v.double() for k, v in sd.items()})
         models[goal] = (m32, m64)
-        with open(os.path.join(HERE, f'state_dict_keys{"_goal" if goal else ""}.json'), 'w') as f:
+        with open(os.path.join(HERE, f'state_dict_keys{cond_suffix(goal)}.json'), 'w') as f:
             json.dump({'keys': [[k, list(v.shape)] for k, v in m32.state_dict().items()],
                        'checksum': float(sum(v.double().sum() for v in sd.values())),
                        'abs_checksum': float(sum(v.double().abs().sum() for v in sd.values()))}, f)
-    for name, (kw, goal) in CASES.items():
+    for name, (kw, goal) in cases.items():
         m32, m64 = models[goal]
         b32 = synthetic.make_batch(**kw)
         ids = b32.extras['prompt']['motion_pred']['agent_ids']

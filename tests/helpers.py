@@ -6,6 +6,9 @@ import torch
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
+ALL_COND = ('goal', 'v_action_tag', 'drag_point')      # PROMPT.CONDITION.TYPES of the released prosim_demo/cfg/no_text.yaml
+
+# name -> (synthetic.make_batch kwargs, condition types of the model: False / True (= goal only) / tuple of types)
 CASES = {
     'cfg1_a16_m256_s20': (dict(n_scenes=1, n_agents=16, n_map=256, steps=20), False),
     'cfg2_a64_m256_s40': (dict(n_scenes=1, n_agents=64, n_map=256, steps=40), False),
@@ -15,7 +18,16 @@ CASES = {
                            permute_obs=True), False),
     'ragged_goal_b2_s20': (dict(agents_per_scene=[12, 20], map_per_scene=[48, 30], steps=20, goal=True,
                                 permute_obs=True), True),
+    'mixed_cond_a64_m256_s40': (dict(n_scenes=1, n_agents=64, n_map=256, steps=40, goal=True, tags=True, drag=True),
+                                ALL_COND),
+    'ragged_mixed_b2_s20': (dict(agents_per_scene=[12, 20], map_per_scene=[48, 30], steps=20, goal=True, tags=True,
+                                 drag=True, permute_obs=True), ALL_COND),
 }
+
+
+def cond_suffix(cond):
+    """File-name suffix of the per-model fixtures."""
+    return '' if not cond else '_goal' if cond is True else '_' + '_'.join(cond)
 
 
 def load_golden(name):
@@ -56,5 +68,6 @@ def to_double(batch):
     for k in ('prompt', 'position', 'heading'):
         p[k] = p[k].double()
     for c in ex['condition'].keys():
-        ex['condition'][c]['input'] = ex['condition'][c]['input'].double()
+        if ex['condition'][c]['input'].is_floating_point():       # action tags stay int64
+            ex['condition'][c]['input'] = ex['condition'][c]['input'].double()
     return batch

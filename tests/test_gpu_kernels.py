@@ -9,7 +9,7 @@ import torch.nn.functional as F
 from oracle import graph as ograph
 from oracle.prosim_oracle import ProSimOracle, fourier_fix, rel_pe_input
 from prosim_b200 import weights
-from tests.helpers import edge_set
+from tests.helpers import ALL_COND, edge_set
 
 pytestmark = pytest.mark.gpu
 
@@ -18,9 +18,9 @@ pytestmark = pytest.mark.gpu
 def ctx():
     from prosim_b200 import lib, ops
     lib.load()
-    sd = weights.random_state_dict(0, True)
+    sd = weights.random_state_dict(0, ALL_COND)
     arena, off = weights.pack_model(sd)
-    return dict(ops=ops, sd=sd, arena=arena.cuda(), off=off, oracle=ProSimOracle(sd, True))
+    return dict(ops=ops, sd=sd, arena=arena.cuda(), off=off, oracle=ProSimOracle(sd, ALL_COND))
 
 
 def _scene_points(g, counts, spread):
@@ -283,6 +283,85 @@ def test_prompt_and_goal_encoders_match_oracle(ctx):
     dim_t128 = ctx['arena'][ctx['off']['dim_t128']:ctx['off']['dim_t128'] + 128]
     out = ops.mlp2(gi.cuda(), 2, False, ctx['arena'], ctx['off']['goal_mlp'], tpe_col=2, dim_t128=dim_t128).cpu()
     assert (out - ref).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize('T', [16, 8])
+def test_condition_encoders_and_pooling_match_oracle(ctx, T):
+    """Action-tag / drag-point encoders and the per-agent mean pooling (condition_encoders.py:76-191,
+    condition_attns.py:114-189) against the oracle's encode_conditions / edge matrix."""
+    ops, orc, ar, off = ctx['ops'], ctx['oracle'], ctx['arena'], ctx['off']
+    g = torch.Generator().manual_seed(11)
+    B, N, C = 3, 9, 14
+    tags = torch.stack([torch.randint(-1, 11, (B, C), generator=g), torch.randint(0, 80, (B, C), generator=g),
+                        torch.randint(0, 200, (B, C), generator=g)], dim=-1)
+    tags[tags[..., 0] < 0] = -1
+    tmask = (tags != -1).all(-1)
+    # every (agent, tag name) pair at most once per scene, like the dataset
+    tidx = torch.zeros(B, C, 1, dtype=torch.long)
+    for b in range(B):
+        seen = set()
+        for c in range(C):
+            n = int(torch.randint(0, N, (1,), generator=g))
+            while (n, int(tags[b, c, 0])) in seen:
+                n = (n + 1) % N
+            seen.add((n, int(tags[b, c, 0])))
+            tidx[b, c, 0] = n if tmask[b, c] else -1
+    drag = torch.randn(B, N, T, 2, generator=g) * 20
+    drag[torch.rand(B, N, T, generator=g) < 0.4] = float('nan')
+    drag[0, 1] = float('nan')                                        # an agent without any drag point
+    dmask = ~drag.isnan().all(-1).all(-1)
+    didx = torch.arange(N).view(1, N, 1).expand(B, N, 1).clone()
+    didx[~dmask] = -1
+    goal = torch.cat([torch.randn(B, N, 2, generator=g) * 50, torch.full((B, N, 1), 80.0)], -1)
+    gmask = torch.rand(B, N, generator=g) < 0.6
+    gidx = torch.arange(N).view(1, N, 1).expand(B, N, 1).clone()
+    gidx[~gmask] = -1
+    pm = torch.ones(B, N, dtype=torch.bool)
+    cond = {'goal': dict(input=goal, mask=gmask, prompt_idx=gidx, prompt_mask=pm),
+            'v_action_tag': dict(input=tags, mask=tmask, prompt_idx=tidx, prompt_mask=pm),
+            'drag_point': dict(input=drag, mask=dmask, prompt_idx=didx, prompt_mask=pm)}
+    emds = orc.encode_conditions(cond)
+    # --- encoders, entry by entry
+    t_gpu = ops.tag_embed(tags.reshape(-1, 3).cuda(), ar[off['tag_vec']:off['tag_vec'] + 16 * 128],
+                          ar[off['dim_t64']:off['dim_t64'] + 64]).cpu().view(B, C, 128)
+    assert (t_gpu[tags[..., 0] < 0] == 0).all()
+    for tag, tid in weights.V_ACTION_TAG_ID.items():
+        sel = tags[..., 0] == tid
+        if tag in emds:
+            ref = emds[tag]['emd'][torch.arange(emds[tag]['emd'].shape[1])[None, :] < sel.sum(1)[:, None]]
+            assert (t_gpu[sel] - ref).abs().max() < 2e-5      # sin/cos of arguments up to 2 pi 200
+    d_gpu = ops.pointnet(2 if T == 16 else 3, drag.reshape(B * N, T, 2).cuda(), None,
+                         torch.arange(B * N, dtype=torch.int32).cuda(), ar, off['drag_enc']).cpu().view(B, N, 128)
+    assert torch.isfinite(d_gpu).all()
+    assert (d_gpu - emds['drag_point']['emd']).abs().max() < 2e-5
+    # --- pooling: build the slot table the way model._conditions does, compare with the oracle's pooled edge attribute
+    emd = torch.zeros(B, N, 128)
+    x_ref = orc.condition_attn(cond, emd, pm, torch.zeros(B, N, 2), torch.zeros(B, N, 1))
+    attr, has = orc._dbg_cond['attr'].view(B * N, 128), orc._dbg_cond['has'].view(B * N)
+    from prosim_b200.config import get_config
+    from prosim_b200.model import ProSimB200
+    from types import SimpleNamespace
+    model = ProSimB200(get_config(opts=['PROMPT.CONDITION.TYPES', list(ALL_COND)]), ctx['sd'], device='cuda')
+    P = B * N
+    pl = SimpleNamespace(P=P, B=B, N=N, i={'prow_lut': torch.arange(P, dtype=torch.int32).cuda()})
+    captured = {}
+    real_pool = ops.cond_pool
+
+    def spy(e, s):
+        captured['out'] = real_pool(e, s)
+        return captured['out']
+    ops.cond_pool = spy
+    try:
+        cc = {k: {kk: vv.cuda() for kk, vv in v.items()} for k, v in cond.items()}
+        p_pos, p_ori = torch.zeros(P, 2).cuda(), torch.zeros(P).cuda()
+        ws = ops.attn_workspace(P, P, 'cuda', 1)
+        x_gpu = model._conditions(cc, emd.view(P, 128).cuda(), p_pos, p_ori, pl, ws).cpu()
+    finally:
+        ops.cond_pool = real_pool
+    extra, has_gpu = captured['out']
+    assert torch.equal(has_gpu.cpu().bool(), has)
+    assert (extra.cpu() - attr).abs().max() < 2e-5
+    assert (x_gpu - x_ref.view(P, 128)).abs().max() < 5e-5
 
 
 def test_bad_arguments_raise(ctx):

@@ -22,7 +22,7 @@ def _model(goal):
     from prosim_b200.config import get_config
     from prosim_b200.model import ProSimB200
     if goal not in _models:
-        cfg = get_config(opts=['PROMPT.CONDITION.TYPES', ['goal']] if goal else None)
+        cfg = get_config(opts=['PROMPT.CONDITION.TYPES', list(weights.cond_types(goal))] if goal else None)
         _models[goal] = ProSimB200(cfg, weights.random_state_dict(0, goal), device='cuda')
     return _models[goal]
 
@@ -66,7 +66,7 @@ def test_closed_loop_matches_reference_golden(name):
     assert np.array_equal(init_pos, gold['init_pos'])
 
 
-@pytest.mark.parametrize('name', ['cfg2_a64_m256_s40', 'ragged_b3_s30', 'ragged_goal_b2_s20'])
+@pytest.mark.parametrize('name', ['cfg2_a64_m256_s40', 'ragged_b3_s30', 'ragged_goal_b2_s20', 'ragged_mixed_b2_s20'])
 def test_teacher_forced_ticks_and_edge_sets(name):
     """Feed the oracle's state at every tick to the GPU tick: motion_pred within 1e-5, neighbour sets identical,
     fut_obs written in place like the reference does."""

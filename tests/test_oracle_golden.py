@@ -9,12 +9,12 @@ import torch
 
 from oracle.prosim_oracle import ProSimOracle
 from prosim_b200 import synthetic, weights
-from tests.helpers import CASES, GOLDEN, load_golden, per_tick_max, stack_rollout, to_double
+from tests.helpers import ALL_COND, CASES, GOLDEN, cond_suffix, load_golden, per_tick_max, stack_rollout, to_double
 
 
-@pytest.mark.parametrize('goal', [False, True])
+@pytest.mark.parametrize('goal', [False, True, ALL_COND])
 def test_state_dict_table_matches_reference_keys(goal):
-    with open(os.path.join(GOLDEN, f'state_dict_keys{"_goal" if goal else ""}.json')) as f:
+    with open(os.path.join(GOLDEN, f'state_dict_keys{cond_suffix(goal)}.json')) as f:
         ref = json.load(f)
     mine = [[n, list(s)] for n, s, _ in weights.param_specs(goal)]
     assert mine == ref['keys']

@@ -10,20 +10,24 @@ from prosim_b200 import synthetic, weights
 pytestmark = pytest.mark.ref_tree
 
 
-@pytest.mark.parametrize('goal', [False, True])
+ALL = ('goal', 'v_action_tag', 'drag_point')      # PROMPT.CONDITION.TYPES of prosim_demo/cfg/no_text.yaml
+
+
+@pytest.mark.parametrize('goal', [False, True, ALL])
 def test_param_table_equals_live_reference(goal):
-    m, _ = ref_shim.build_reference_model(('goal',) if goal else ())
+    m, _ = ref_shim.build_reference_model(weights.cond_types(goal))
     ref = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
     assert ref == [(n, tuple(s)) for n, s, _ in weights.param_specs(goal)]
-    assert sum(p.numel() for p in m.parameters()) == (11314740 if goal else 10454196)
+    assert sum(p.numel() for p in m.parameters()) == {False: 10454196, True: 11314740, ALL: 11399220}[goal]
 
 
-@pytest.mark.parametrize('goal', [False, True])
+@pytest.mark.parametrize('goal', [False, True, ALL, ('drag_point', 'v_action_tag')])
 def test_oracle_bit_equal_to_reference(goal):
-    m, _ = ref_shim.build_reference_model(('goal',) if goal else ())
+    m, _ = ref_shim.build_reference_model(weights.cond_types(goal))
     sd = weights.random_state_dict(0, goal)
     m.load_state_dict(sd)
-    kw = dict(agents_per_scene=[20, 13], map_per_scene=[48, 37], steps=30, goal=goal, permute_obs=True)
+    kw = dict(agents_per_scene=[20, 13], map_per_scene=[48, 37], steps=30, goal=bool(goal), permute_obs=True,
+              tags='v_action_tag' in weights.cond_types(goal), drag='drag_point' in weights.cond_types(goal))
     b_ref, b_orc = synthetic.make_batch(**kw), synthetic.make_batch(**kw)
     with torch.no_grad():
         ref = m.forward(b_ref, 'val')['motion_pred']
