@@ -117,9 +117,11 @@ int prosim_attn_stack_fwd(const float* x, int n_dst, int n_layers, const prosim_
                           const prosim_stack_side_t* side_b, float* workspace, size_t workspace_floats, float* out,
                           prosim_stream_t stream);
 
-/* ActDecoder._compute_traj (policy/act_decoder.py:78-135): motion_pred [P][10][5] */
-int prosim_policy_head_fwd(const float* feat, const int32_t* agent_type, int P, const float* w, float* motion_pred,
-                           prosim_stream_t stream);
+/* ActDecoder._compute_traj (policy/act_decoder.py:78-135): motion_pred [P][10][5].
+ * noise (may be NULL): [P][10][2] standard-normal draws; noise * noise_std is added to the per-step (dx, dy) before the
+ * cumulative sum (RANDOM_NOISE_STD > 0, act_decoder.py:113-115).  The draws come from the caller's generator. */
+int prosim_policy_head_fwd(const float* feat, const int32_t* agent_type, int P, const float* w, const float* noise,
+                           float noise_std, float* motion_pred, prosim_stream_t stream);
 /* pred_mlp(policy emd) (act_decoder.py:129-131): out [P][2] */
 int prosim_reconst_fwd(const float* emd, int P, const float* w, float* out, prosim_stream_t stream);
 /* PromptEncoder (prompt_encoder/base.py:30,37-50) / GoalConditionEncoder (condition_encoders.py:21-51) */

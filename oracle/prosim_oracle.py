@@ -84,6 +84,8 @@ class ProSimOracle:
         self.cond_types = tuple(goal_condition or ())
         self.goal_condition = bool(self.cond_types)
         self.faithful_bookkeeping = faithful_bookkeeping
+        self.noise_std = 0.0      # MODEL.POLICY.ACT_DECODER.RANDOM_NOISE_STD (act_decoder.py:113-115)
+        self.noise_fn = torch.randn_like
         self.trace = None  # set to [] to record per-tick state for teacher-forced tests
         self.trace_states = []
 
@@ -431,6 +433,8 @@ class ProSimOracle:
             inp_ = (inp_ * i + inp) / (i + 1)
             ctx_ = (ctx_ * i + c) / (i + 1)
         motion = self.mlp(f'{pa}.motion_head', inp_, 3, ret_before_act=True).view(feat.shape[0], 1, STEP, 5)
+        if self.noise_std > 0:
+            motion[..., :2] += self.noise_fn(motion[..., :2]) * self.noise_std
         xy = motion[..., :2].cumsum(dim=-2)
         hd = wrap_angle(motion[..., 2:3].cumsum(dim=-2))
         pred = torch.cat([xy, hd, motion[..., 3:]], dim=-1)
@@ -444,6 +448,8 @@ class ProSimOracle:
             b += [bi] * len(ids)
             n += list(range(len(ids)))
         tidx = st['last_step']
+        if self.noise_std > 0:     # traj_sam.py:313: the degenerate mode draw still advances the generator
+            torch.randint(0, 1, (len(b),))
         cur = st['traj'][b, n, :tidx]
         pred = out['motion_pred'][:, 0, :STEP]
         last = torch.arctan2(cur[:, -1, 2], cur[:, -1, 3])[:, None]

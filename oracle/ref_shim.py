@@ -305,20 +305,21 @@ def install_shims():
     _INSTALLED = True
 
 
-def reference_config(cond_types=()):
-    """The released model shape (prosim_demo/cfg/no_text.yaml) with PROMPT.CONDITION.TYPES overridden."""
+def reference_config(cond_types=(), opts=()):
+    """The released model shape (prosim_demo/cfg/no_text.yaml) with PROMPT.CONDITION.TYPES (and further yacs
+    [key, value, ...] options) overridden."""
     install_shims()
     from prosim.config.default import get_config
     return get_config(os.path.join(REF_ROOT, 'prosim_demo/cfg/no_text.yaml'),
-                      ['PROMPT.CONDITION.TYPES', repr(list(cond_types))], 'local')
+                      ['PROMPT.CONDITION.TYPES', repr(list(cond_types))] + list(opts), 'local')
 
 
-def build_reference_model(cond_types=(), dtype=torch.float32):
+def build_reference_model(cond_types=(), dtype=torch.float32, opts=()):
     """registry.get_model(cfg.MODEL.TYPE)(cfg).eval() -- the reference's own class (traj_sam.py:13-14)."""
     install_shims()
     import prosim  # noqa: F401  (registers everything)
     from prosim.core.registry import registry
-    cfg = reference_config(cond_types)
+    cfg = reference_config(cond_types, opts)
     prev = torch.get_default_dtype()
     torch.set_default_dtype(dtype)
     try:

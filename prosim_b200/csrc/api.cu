@@ -613,14 +613,14 @@ int prosim_attn_stack_fwd(const float* x, int n_dst, int n_layers, const prosim_
   return err;
 }
 
-int prosim_policy_head_fwd(const float* feat, const int32_t* agent_type, int P, const float* w, float* motion_pred,
-                           prosim_stream_t stream) {
-  if (P < 0) return ERR_ARG;
+int prosim_policy_head_fwd(const float* feat, const int32_t* agent_type, int P, const float* w, const float* noise,
+                           float noise_std, float* motion_pred, prosim_stream_t stream) {
+  if (P < 0 || (noise && !(noise_std > 0.f))) return ERR_ARG;
   if (P == 0) return 0;
   if (!feat || !agent_type || !w || !motion_pred) return ERR_ARG;
   const int rpt = pick_rpt(P);
   LaunchScope ls(PROSIM_K_HEAD, S(stream));
-  DISPATCH_RPT(rpt, policy_head_kernel<RPT><<<(P + 2 * RPT - 1) / (2 * RPT), 256, 0, S(stream)>>>(feat, agent_type, P, w, motion_pred));
+  DISPATCH_RPT(rpt, policy_head_kernel<RPT><<<(P + 2 * RPT - 1) / (2 * RPT), 256, 0, S(stream)>>>(feat, agent_type, P, w, noise, noise_std, motion_pred));
   PROSIM_CHECK_LAUNCH();
   return 0;
 }

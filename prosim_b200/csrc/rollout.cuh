@@ -173,9 +173,11 @@ __device__ __forceinline__ void mlp3_tile(float* sIn, float* sTmp, float* sOut, 
 
 // feat: fused policy feature [P][128]; a_type: 1..3; motion_pred out [P][10][5] (xy cumsum, wrapped heading
 // cumsum, velocity passthrough).  K = 1 so max over modes is the identity and CG's context == input.
+// noise: optional [P][10][2] standard-normal draws (MODEL.POLICY.ACT_DECODER.RANDOM_NOISE_STD > 0).
 template <int RPT>
 __global__ void __launch_bounds__(256) policy_head_kernel(const float* __restrict__ feat, const int* __restrict__ a_type,
                                                           int P, const float* __restrict__ W,
+                                                          const float* __restrict__ noise, float noise_std,
                                                           float* __restrict__ motion_pred) {
   constexpr int R = 2 * RPT;
   __shared__ __align__(16) float sS[R * LDS_PAD];
@@ -219,10 +221,18 @@ __global__ void __launch_bounds__(256) policy_head_kernel(const float* __restric
   if (threadIdx.x < R && row0 + threadIdx.x < P) {
     const float* m = sB + threadIdx.x * LDS_PAD;
     float* o = motion_pred + (size_t)(row0 + threadIdx.x) * STEP * 5;
+    // RANDOM_NOISE_STD > 0 (act_decoder.py:113-115): standard-normal draws [P][10][2] scaled by std are added to the
+    // per-step displacements before the cumulative sum (a product then a sum in the reference: no fused multiply-add)
+    const float* nz = noise ? noise + (size_t)(row0 + threadIdx.x) * STEP * 2 : nullptr;
     float cx = 0.f, cy = 0.f, ch = 0.f;
     for (int i = 0; i < STEP; ++i) {
-      cx += m[i * 5 + 0];
-      cy += m[i * 5 + 1];
+      float dx = m[i * 5 + 0], dy = m[i * 5 + 1];
+      if (nz) {
+        dx = __fadd_rn(dx, __fmul_rn(nz[i * 2 + 0], noise_std));
+        dy = __fadd_rn(dy, __fmul_rn(nz[i * 2 + 1], noise_std));
+      }
+      cx += dx;
+      cy += dy;
       ch += m[i * 5 + 2];
       o[i * 5 + 0] = cx;
       o[i * 5 + 1] = cy;

@@ -45,7 +45,7 @@ _SIGS = {
     'prosim_attn_kv': [_P, c_int, _P, c_size_t, c_int, _P, c_size_t, _P],
     'prosim_attn_layer_fwd': [_P, c_int, _P, c_int, POINTER(Graph), _P, _P, c_size_t, _P, _P],
     'prosim_attn_stack_fwd': [_P, c_int, c_int, POINTER(StackSide), POINTER(StackSide), _P, c_size_t, _P, _P],
-    'prosim_policy_head_fwd': [_P, _P, c_int, _P, _P, _P],
+    'prosim_policy_head_fwd': [_P, _P, c_int, _P, _P, c_float, _P, _P],
     'prosim_reconst_fwd': [_P, c_int, _P, _P, _P],
     'prosim_mlp2_fwd': [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, _P],
     'prosim_tag_embed_fwd': [_P, c_int, c_int, _P, _P, _P, _P],

@@ -102,6 +102,10 @@ class ProSimB200(nn.Module):
         self.num_layers = cfg.MODEL.POLICY.ACT_DECODER.ATTN.NUM_LAYER
         self.cond_layers = cfg.MODEL.CONDITION_TRANSFORMER.NLAYER
         self.mode = 'val'
+        # act_decoder.py:113-115: Gaussian noise on the predicted per-step displacements; the draws come from torch's CUDA
+        # generator with the reference's shapes ([P, 1, 10, 2] per tick), noise_fn can be replaced to inject given draws
+        self.noise_std = float(cfg.MODEL.POLICY.ACT_DECODER.RANDOM_NOISE_STD)
+        self.noise_fn = lambda shape: torch.randn(shape, device=self._device, dtype=torch.float32)
         self._device = torch.device(device if device is not None else 'cuda')
         self._sd = None
         self._arena = None
@@ -535,7 +539,10 @@ class ProSimB200(nn.Module):
                            ops.stack_side(ar, off['pol_m2p'], e_m, kv_m), out=fuse, workspace=ws)
             self._note_edges('pol_a2p', e_a, L)
             self._note_edges('pol_m2p', e_m, L)
-            ops.policy_head(fuse, a_type, ar, off['head'], motion_pred=motion_pred[k])
+            noise = self.noise_fn((P, 1, STEP, 2)) if self.noise_std > 0 else None
+            ops.policy_head(fuse, a_type, ar, off['head'], motion_pred=motion_pred[k], noise=noise, noise_std=self.noise_std)
+            if self.noise_std > 0:       # traj_sam.py:313: the (degenerate, TOP_K = 1) mode draw still advances the generator
+                torch.randint(0, 1, (P,), device=self._device)
             ops.step_agent_traj(motion_pred[k], pl.i['p_row'], T, tidx, traj, vel)
             tidx += STEP
             if getattr(self, 'keep_tick_edges', False):

@@ -156,12 +156,16 @@ def attn_stack(x, n_layers, side_a, side_b=None, out=None, workspace=None):
     return out
 
 
-def policy_head(feat, agent_type, w_arena, w_off, motion_pred=None):
-    _chk(feat, torch.float32, 'feat'), _chk(agent_type, torch.int32, 'agent_type')
+def policy_head(feat, agent_type, w_arena, w_off, motion_pred=None, noise=None, noise_std=0.0):
+    """noise: optional standard-normal draws [P, 1, 10, 2] (RANDOM_NOISE_STD > 0, act_decoder.py:113-115)."""
+    _chk(feat, torch.float32, 'feat'), _chk(agent_type, torch.int32, 'agent_type'), _chk(noise, torch.float32, 'noise')
     P = feat.shape[0]
+    if noise is not None and noise.numel() != P * 20:
+        raise ValueError('noise must hold [P, 1, 10, 2] values')
     if motion_pred is None:
         motion_pred = torch.empty(P, 1, 10, 5, device=feat.device, dtype=torch.float32)
-    lib.call('prosim_policy_head_fwd', ptr(feat), ptr(agent_type), P, ptr(w_arena, w_off), ptr(motion_pred), _stream())
+    lib.call('prosim_policy_head_fwd', ptr(feat), ptr(agent_type), P, ptr(w_arena, w_off), ptr(noise), float(noise_std),
+             ptr(motion_pred), _stream())
     return motion_pred
 
 

@@ -231,6 +231,42 @@ def test_run_to_run_determinism_on_the_tensor_core_path():
             assert torch.equal(ref, traj)
 
 
+def test_action_noise_rollout_matches_oracle_with_injected_draws():
+    """MODEL.POLICY.ACT_DECODER.RANDOM_NOISE_STD > 0 (act_decoder.py:113-115): with the SAME standard-normal draws fed
+    to the GPU head kernel and to the oracle, the noisy closed loop agrees like the noise-free one does; with its own
+    CUDA generator the model is reproducible under torch.manual_seed and actually noisy."""
+    from prosim_b200.config import get_config
+    from prosim_b200.model import ProSimB200
+    kw = dict(agents_per_scene=[14, 9], map_per_scene=[40, 32], steps=20)
+    sd = weights.random_state_dict(0)
+    model = ProSimB200(get_config(opts=['MODEL.POLICY.ACT_DECODER.RANDOM_NOISE_STD', 0.05]), sd, device='cuda')
+    assert model.noise_std == pytest.approx(0.05)
+    g = torch.Generator().manual_seed(77)
+    draws = [torch.randn(23, 1, 10, 2, generator=g) for _ in range(2)]
+    it_gpu, it_cpu = iter(draws), iter(draws)
+    model.noise_fn = lambda shape: next(it_gpu).cuda().contiguous()
+    orc = ProSimOracle(sd)
+    orc.noise_std = 0.05
+    orc.noise_fn = lambda like: next(it_cpu).to(like.dtype)
+    ref = orc.forward(synthetic.make_batch(**kw))['motion_pred']
+    with torch.no_grad():
+        out = model.forward(synthetic.make_batch(**kw).to('cuda'), 'val')['motion_pred']
+    assert (out['motion_pred'][:23].cpu() - ref['motion_pred'][:23]).abs().max() < 1e-5       # open-loop tick
+    _, traj, _ = stack_rollout(out)
+    _, traj_ref, _ = stack_rollout(ref)
+    assert np.abs(traj - traj_ref).max() < 1e-4
+    quiet = ProSimOracle(sd).forward(synthetic.make_batch(**kw))['motion_pred']
+    assert np.abs(traj - stack_rollout(quiet)[1]).max() > 0.05                                  # the noise is really there
+    # own generator: seeded runs repeat, differently seeded runs differ
+    model.noise_fn = lambda shape: torch.randn(shape, device='cuda', dtype=torch.float32)
+    runs = []
+    for seed in (5, 5, 6):
+        torch.manual_seed(seed)
+        with torch.no_grad():
+            runs.append(model.forward(synthetic.make_batch(**kw).to('cuda'), 'val')['motion_pred']['motion_pred'].clone())
+    assert torch.equal(runs[0], runs[1]) and not torch.equal(runs[0], runs[2])
+
+
 def test_agent_permutation_equivariance():
     """Storing the observation slots in another order must not change any agent's trajectory beyond
     summation-order rounding (edges are visited in ascending slot index)."""

@@ -45,6 +45,28 @@ def test_oracle_bit_equal_to_reference(goal):
             assert torch.equal(torch.nan_to_num(a.float()), torch.nan_to_num(b.float())), (t, key)
 
 
+def test_oracle_bit_equal_to_reference_with_action_noise():
+    """MODEL.POLICY.ACT_DECODER.RANDOM_NOISE_STD > 0 (act_decoder.py:113-115): same torch generator state -> same draws
+    (the oracle also consumes the degenerate TOP_K = 1 draw of traj_sam.py:313) -> bit-equal noisy rollouts."""
+    m, _ = ref_shim.build_reference_model((), opts=['MODEL.POLICY.ACT_DECODER.RANDOM_NOISE_STD', '0.05'])
+    sd = weights.random_state_dict(0)
+    m.load_state_dict(sd)
+    kw = dict(agents_per_scene=[9, 6], map_per_scene=[30, 24], steps=30)
+    torch.manual_seed(123)
+    with torch.no_grad():
+        ref = m.forward(synthetic.make_batch(**kw), 'val')['motion_pred']
+    orc = ProSimOracle(sd)
+    orc.noise_std = 0.05
+    torch.manual_seed(123)
+    out = orc.forward(synthetic.make_batch(**kw))['motion_pred']
+    assert torch.equal(ref['motion_pred'], out['motion_pred'])
+    quiet = ProSimOracle(sd).forward(synthetic.make_batch(**kw))['motion_pred']
+    d = (out['motion_pred'][:15, 0, :, :2] - quiet['motion_pred'][:15, 0, :, :2])        # first tick: cumsum of N(0, 0.05^2)
+    assert 0.02 < float(d[:, 0].std()) < 0.1 and float(d[:, -1].std()) > float(d[:, 0].std())
+    for name, r in ref['rollout_trajs'].items():
+        assert torch.equal(r['traj'], out['rollout_trajs'][name]['traj']), name
+
+
 def test_world_transform_equals_reference():
     """oracle.rollout_trajs_in_world == the reference's obtain_rollout_trajs_in_world (rollout/gpu_utils.py:230-281)."""
     import math

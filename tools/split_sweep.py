@@ -10,7 +10,7 @@ model = ProSimB200(state_dict=weights.random_state_dict(0), device=dev)
 pristine = synthetic.clone_batch(synthetic.make_batch(n_scenes=32, n_agents=128, n_map=512, steps=80), dev)[0]
 ref = None
 with torch.no_grad():
-    for tc in (True, False):
+    for tc in (True,):
         lib.set_tensor_core(tc)
         for parts in (1, 2, 3, 4):
             lib.set_stack_split(parts)
