@@ -28,9 +28,10 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 __device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
+  // sm_100a: one CREDUX.MAX.F32 into a uniform register instead of five SHFL + FMNMX pairs (max is exact: same result)
+  float m;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
+  return m;
 }
 
 // torch.remainder semantics for a positive divisor: result in [0, b)

@@ -198,30 +198,26 @@ __global__ void __launch_bounds__(NW * 32, 1)
         }
       }
       // ---- online softmax bookkeeping (per head; max is warp uniform)
-      float p[H];
+      float p[H], corr[H];
 #pragma unroll
       for (int h = 0; h < H; ++h) {
         const float s = acc[h].x + acc[h].y;
         const float mx = warp_max(valid ? s : -INFINITY);
         const float mn = fmaxf(m[h], mx);                       // nt >= 1 => finite
-        const float corr = expf(m[h] - mn);                     // exp(-inf) = 0 on the first tile
-        p[h] = valid ? expf(s - mn) : 0.f;
-        lsum[h] = lsum[h] * corr + p[h];
+        // ex2.approx(x log2 e): arguments are <= 0, 2 ulp on the weights -- the accurate expf costs ~7 instructions, 16
+        // of them per tile were a quarter of the softmax bookkeeping
+        corr[h] = __expf(m[h] - mn);                            // exp(-inf) = 0 on the first tile
+        p[h] = valid ? __expf(s - mn) : 0.f;
+        lsum[h] = lsum[h] * corr[h] + p[h];
         m[h] = mn;
-        if (h < 2) {
-#pragma unroll
-          for (int c = 0; c < NSEG; ++c) { if (h == 0) r01[c].x *= corr; else r01[c].y *= corr; }
-        } else if (h < 4) {
-#pragma unroll
-          for (int c = 0; c < NSEG; ++c) { if (h == 2) r23[c].x *= corr; else r23[c].y *= corr; }
-        } else if (h < 6) {
-#pragma unroll
-          for (int c = 0; c < NSEG; ++c) { if (h == 4) r45[c].x *= corr; else r45[c].y *= corr; }
-        } else {
-#pragma unroll
-          for (int c = 0; c < NSEG; ++c) { if (h == 6) r67[c].x *= corr; else r67[c].y *= corr; }
-        }
         if (lane == h) mt[t * H + h] = mn;
+      }
+#pragma unroll
+      for (int c = 0; c < NSEG; ++c) {                          // head pairs: one packed multiply per accumulator
+        r01[c] = __fmul2_rn(r01[c], make_float2(corr[0], corr[1]));
+        r23[c] = __fmul2_rn(r23[c], make_float2(corr[2], corr[3]));
+        r45[c] = __fmul2_rn(r45[c], make_float2(corr[4], corr[5]));
+        r67[c] = __fmul2_rn(r67[c], make_float2(corr[6], corr[7]));
       }
       *reinterpret_cast<float4*>(pb + lane * 8) = make_float4(p[0], p[1], p[2], p[3]);
       *reinterpret_cast<float4*>(pb + lane * 8 + 4) = make_float4(p[4], p[5], p[6], p[7]);
