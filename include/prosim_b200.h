@@ -52,8 +52,12 @@ int prosim_abi_version(void);
 int prosim_set_tensor_core(int on);
 /* prosim_attn_stack_fwd with fixed sources on both sides runs as up to `parts` (1..4, default 1) independent row chains of
  * >= 1024 rows on internal side streams (forked from / joined to the caller's stream with events; capturable in a CUDA
- * graph).  Results are bit-identical for every setting.  Measured on B200 (bench workload): 38.4 ms at 1, 37.7 at 2, 37.3 at 3
- * parts -- the edge and node kernels are persistent one-CTA-per-SM designs, so there is little left to overlap. */
+ * graph).  Results are bit-identical for every setting.  Measured on B200 (bench workload): 31.4 ms per forward at 1 part,
+ * 30.9 at 2, 30.6 at 3, 31.4 at 4.  The chains drift into lockstep (both in their edge phase, then both in the node
+ * kernel: gpurun_out/split_timeline2.txt), so the gain is the node kernels of the chains sharing the chip, not an
+ * edge-phase / node-phase overlap; starting the chains half a layer apart and reserving SMs for the sibling's node kernel
+ * was tried and did not hold the stagger (the edge phase of half the rows is longer than a node kernel).  Off by default:
+ * 2.6 % is not worth per-launch timings that overlap (the roofline accounting of bench.py times single launches). */
 int prosim_set_stack_split(int parts);
 /* Measurement support: SM-clock timestamps of the phases of CTA 0 of the last tcgen05 node-kernel launch
  * ([0..15] epilogue thread, [16..31] MMA thread; csrc/tc_post.cuh TCP_MARK). */

@@ -19,7 +19,7 @@ using namespace prosim;
 
 namespace {
 
-int g_split = 1;        // row-split chains of prosim_attn_stack_fwd (prosim_set_stack_split); measured +2..3 % at 2-3 parts
+int g_split = 1;        // row-split chains of prosim_attn_stack_fwd (prosim_set_stack_split); measured 31.4 / 30.9 / 30.6 / 31.4 ms at 1..4 parts
 bool g_use_tc = true;   // node-side GEMMs on tcgen05 (tc_post.cuh); prosim_set_tensor_core(0) selects the FFMA kernels
 constexpr int ERR_ARG = -1;
 constexpr int ERR_WORKSPACE = -2;

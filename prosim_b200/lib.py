@@ -143,5 +143,5 @@ def set_tensor_core(on):
 
 
 def set_stack_split(parts):
-    """Row-split chains of the fixed-source attention stacks (1 = single stream, the default)."""
+    """Row-split chains of the fixed-source attention stacks (1 = single stream, the default; bit-identical results)."""
     call('prosim_set_stack_split', int(parts))

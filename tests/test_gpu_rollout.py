@@ -188,15 +188,16 @@ def test_row_split_schedule_is_bit_identical():
     from prosim_b200 import lib
     kw = dict(n_scenes=24, n_agents=100, n_map=80, steps=20)
     try:
+        lib.set_stack_split(1)
         ref, _ = _run_gpu(kw, False)
-        for parts in (2, 3):
+        for parts in (2, 3, 4):
             lib.set_stack_split(parts)
             out, _ = _run_gpu(kw, False)
             assert torch.equal(out['motion_pred'], ref['motion_pred'])
             for name, r in ref['rollout_trajs'].items():
                 assert torch.equal(r['traj'], out['rollout_trajs'][name]['traj']), (parts, name)
     finally:
-        lib.set_stack_split(1)
+        lib.set_stack_split(1)     # the library default
 
 
 def test_plan_cache_hits_only_on_identical_bookkeeping():
