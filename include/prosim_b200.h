@@ -102,7 +102,10 @@ int prosim_build_knn_edges(const float* qpos, const int32_t* qscene, int n_q, co
                            int k, int nmax, int32_t* nbr, int32_t* deg, int stride, prosim_stream_t stream);
 /* _get_rel_pe + FourierEmbeddingFix + attn_prenorm_r statistics (act_decoder.py:203-221,
  * layers/fourier_embedding.py:56-79, attention_layer.py:68). extra (nullable): per-edge vector added before
- * the normalisation (condition edges, condition_transformer/condition_attns.py:211-216). */
+ * the normalisation (condition edges, condition_transformer/condition_attns.py:211-216).
+ * Also zero-fills z up to the next multiple of 8 entries past each list (at least 8 entries per row, never past the
+ * row's stride): prosim_attn_layer_fwd / prosim_attn_stack_fwd read whole groups of 8 entries (with weight 0 beyond a
+ * list) and need finite values there -- a caller that fills z itself must guarantee the same. */
 int prosim_edge_pe(const float* dpos, const float* dori, int n_dst, const float* spos, const float* sori,
                    const int32_t* nbr, const int32_t* deg, int stride, const float* dim_t16, const float* extra,
                    int zd, float* z, prosim_stream_t stream);

@@ -242,14 +242,14 @@ __global__ void __launch_bounds__(NW * 32, 1)
           r67[c] = __ffma2_rn(zz, make_float2(pq.z, pq.w), r67[c]);
         }
       };
-      const int full = nt & ~7;
-      for (int e0 = 0; e0 < full; e0 += 8) {
+      // whole groups of 8 edges: the weights of the lanes beyond the list are exactly 0 and the rows they multiply were
+      // fetched with the tile's last 8-edge box (finite z of other rows, or TMA zero fill), so they add +-0 -- and the
+      // loop has no remainder blocks (seven predicated copies of the body cost 24 register moves per group)
+      const int n8 = (nt + 7) & ~7;
+      for (int e0 = 0; e0 < n8; e0 += 8) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) agg_edge(e0 + u, u);
       }
-#pragma unroll
-      for (int u = 0; u < 7; ++u)
-        if (full + u < nt) agg_edge(full + u, u);
     }
 
     // ---- row epilogue: 1 / (sum + 1e-16), Rbar, and the per-tile factors exp(m_tile - m_final) / (sum + 1e-16)

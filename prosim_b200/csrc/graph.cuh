@@ -146,6 +146,15 @@ __global__ void __launch_bounds__(128) edge_pe_kernel(const float2* __restrict__
   const float od = dori[row];
   const float cx = cosf(od), cy = sinf(od);
   const float TWO_PI_F = 6.28318530717958647692f;
+  // Zero padding: the edge kernel (edge4.cuh) aggregates whole groups of 8 edges with weight 0 on the entries beyond the
+  // list, so up to 7 entries past a list's end must hold finite values -- its own row's [n_e, round8(n_e)) and, when a
+  // list ends at the stride, the first 7 entries of the NEXT row (hence at least 8 initialised entries per row).
+  {
+    const int n8 = (n_e + 7) & ~7;
+    const int pad_end = min(stride, n8 > 8 ? n8 : 8);
+    for (int i = n_e * (ZD / 4) + threadIdx.x; i < pad_end * (ZD / 4); i += 128)
+      reinterpret_cast<float4*>(Z + (size_t)row * stride * ZD)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   for (int e0 = 0; e0 < n_e; e0 += 16) {
     const int e = e0 + warp * 4 + sub;
     const bool ok = e < n_e;                               // uniform over the 8 lanes of an edge
