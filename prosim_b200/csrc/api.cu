@@ -20,7 +20,6 @@ using namespace prosim;
 
 namespace {
 
-constexpr int PN_TR = 16;   // PointNet v2: 8 warps x 16 rows = 128 point rows per CTA
 int g_split = 1;        // row-split chains of prosim_attn_stack_fwd (prosim_set_stack_split); measured 31.4 / 30.9 / 30.6 / 31.4 ms at 1..4 parts
 bool g_use_tc = true;   // node-side GEMMs on tcgen05 (tc_post.cuh); prosim_set_tensor_core(0) selects the FFMA kernels
 constexpr int ERR_ARG = -1;
@@ -99,10 +98,6 @@ int setup_attributes() {
   acc(allow_smem(pointnet_kernel<11, 12, 3, 19>, PointNetCfg<19>::smem_bytes));
   acc(allow_smem(pointnet_kernel<2, 4, 1, 16>, PointNetCfg<16>::smem_bytes));
   acc(allow_smem(pointnet_kernel<2, 4, 1, 8>, PointNetCfg<8>::smem_bytes));
-  acc(allow_smem(pointnet2_kernel<24, 24, 1, 11, PN_TR>, PointNet2Cfg<11, PN_TR>::smem_bytes));
-  acc(allow_smem(pointnet2_kernel<11, 12, 3, 19, PN_TR>, PointNet2Cfg<19, PN_TR>::smem_bytes));
-  acc(allow_smem(pointnet2_kernel<2, 4, 1, 16, PN_TR>, PointNet2Cfg<16, PN_TR>::smem_bytes));
-  acc(allow_smem(pointnet2_kernel<2, 4, 1, 8, PN_TR>, PointNet2Cfg<8, PN_TR>::smem_bytes));
   acc(allow_smem(knn_kernel, 64 * 1024));
   acc(allow_smem(attn_kv2_kernel<4, 8>, Kv2Smem<4, 8>::bytes));
   acc(allow_smem(attn_kv2_kernel<8, 8>, Kv2Smem<8, 8>::bytes));
@@ -396,25 +391,23 @@ int prosim_pointnet_fwd(int kind, const float* x, const uint8_t* mask, const int
   if (!x || (!mask && kind < 2) || !rows || !w || !out) return ERR_ARG;
   if (int e = setup_attributes()) return e;
   LaunchScope ls(PROSIM_K_POINTNET, S(stream));
-  // PROSIM_POINTNET_V2=1 selects the v2 kernel (weights through the shared-memory stream, 128-row CTAs): bit-identical,
-  // measured 3.06 ms against 2.91 ms per forward for v1, so v1 stays the default (A/B switch only)
-  static const bool v1 = [] { const char* e = getenv("PROSIM_POINTNET_V2"); return !(e && atoi(e) != 0); }();
-  auto launch = [&](auto kern1, auto cfg1, auto kern2, auto cfg2, int inner) {
-    using C1 = decltype(cfg1);
-    using C2 = decltype(cfg2);
-    if (v1)
-      kern1<<<(n_poly + C1::G - 1) / C1::G, 256, C1::smem_bytes, S(stream)>>>(x, mask, inner, rows, n_poly, w, out);
-    else
-      kern2<<<(n_poly + C2::G - 1) / C2::G, 256, C2::smem_bytes, S(stream)>>>(x, mask, inner, rows, n_poly, w, out);
-  };
-  if (kind == 0)
-    launch(pointnet_kernel<24, 24, 1, 11>, PointNetCfg<11>{}, pointnet2_kernel<24, 24, 1, 11, PN_TR>, PointNet2Cfg<11, PN_TR>{}, 24);
-  else if (kind == 1)
-    launch(pointnet_kernel<11, 12, 3, 19>, PointNetCfg<19>{}, pointnet2_kernel<11, 12, 3, 19, PN_TR>, PointNet2Cfg<19, PN_TR>{}, 1);
-  else if (kind == 2)
-    launch(pointnet_kernel<2, 4, 1, 16>, PointNetCfg<16>{}, pointnet2_kernel<2, 4, 1, 16, PN_TR>, PointNet2Cfg<16, PN_TR>{}, 1);
-  else
-    launch(pointnet_kernel<2, 4, 1, 8>, PointNetCfg<8>{}, pointnet2_kernel<2, 4, 1, 8, PN_TR>, PointNet2Cfg<8, PN_TR>{}, 1);
+  if (kind == 0) {
+    constexpr int G = PointNetCfg<11>::G;
+    pointnet_kernel<24, 24, 1, 11><<<(n_poly + G - 1) / G, 256, PointNetCfg<11>::smem_bytes, S(stream)>>>(
+        x, mask, 24, rows, n_poly, w, out);
+  } else if (kind == 1) {
+    constexpr int G = PointNetCfg<19>::G;
+    pointnet_kernel<11, 12, 3, 19><<<(n_poly + G - 1) / G, 256, PointNetCfg<19>::smem_bytes, S(stream)>>>(
+        x, mask, 1, rows, n_poly, w, out);
+  } else if (kind == 2) {
+    constexpr int G = PointNetCfg<16>::G;
+    pointnet_kernel<2, 4, 1, 16><<<(n_poly + G - 1) / G, 256, PointNetCfg<16>::smem_bytes, S(stream)>>>(
+        x, mask, 1, rows, n_poly, w, out);
+  } else {
+    constexpr int G = PointNetCfg<8>::G;
+    pointnet_kernel<2, 4, 1, 8><<<(n_poly + G - 1) / G, 256, PointNetCfg<8>::smem_bytes, S(stream)>>>(
+        x, mask, 1, rows, n_poly, w, out);
+  }
   PROSIM_CHECK_LAUNCH();
   return 0;
 }

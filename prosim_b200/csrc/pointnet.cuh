@@ -9,7 +9,6 @@
 // One CTA = G polylines (G*P <= 64 point rows), all activations stay in shared memory.
 #pragma once
 #include "common.cuh"
-#include "gemm_tile.cuh"
 #include "weights_layout.h"
 
 namespace prosim {
@@ -169,185 +168,10 @@ __global__ void __launch_bounds__(256) pointnet_kernel(const float* __restrict__
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Version 2: same math and the same summation order as pointnet_kernel (bit-identical results), but every GEMM of the
-// chain goes through the shared-memory weight stream of gemm_tile.cuh (gemm2 / WPipe): a weight element is fetched once
-// per CTA by cp.async, 2 chunks ahead of the math and across GEMM boundaries, instead of by every thread with LDG.
-// (v1 ran 3 CTAs of 64 rows per SM at 23 % of the fp32 FMA rate, waiting on its own weight loads.)
-// One CTA = 8 warps, M = 8*TR point rows = G polylines of P points (TR = 16: 11 agent histories / 6 map polylines).
-// The per-polyline GEMMs (pooled half of mlps.0, out_mlps) run on 8*TRS >= G pooled rows with the same routine.
-// ---------------------------------------------------------------------------------------------------------------
-template <int P, int TR>
-struct PointNet2Cfg {
-  static constexpr int NW = 8;
-  static constexpr int ROWS = NW * TR;
-  static constexpr int G = ROWS / P;
-  static constexpr int TRS = (G + NW - 1) / NW;         // rows per thread of the pooled-row GEMMs
-  static constexpr int PROWS = NW * TRS;                // pooled rows held (>= G)
-  static constexpr size_t smem_floats = WPIPE_BYTES / sizeof(float) + 2 * (size_t)ROWS * LDS_PAD + 2 * (size_t)PROWS * LDS_PAD + ROWS;
-  static constexpr size_t smem_bytes = smem_floats * sizeof(float);
-};
-
-template <int IN, int IN_PAD, int NPRE, int P, int TR>
-__global__ void __launch_bounds__(256, 1) pointnet2_kernel(const float* __restrict__ X, const uint8_t* __restrict__ mask,
-                                                           int mask_inner, const int* __restrict__ rows, int n_poly,
-                                                           const float* __restrict__ W, float* __restrict__ Out) {
-  using C = PointNet2Cfg<P, TR>;
-  constexpr int NW = C::NW, ROWS = C::ROWS, G = C::G, TRS = C::TRS, PROWS = C::PROWS;
-  extern __shared__ __align__(16) float smem[];
-  WPipe pipe = wpipe_init<NW>(smem, [&](WSeg* sg) {
-    int n = 0;
-    sg[n++] = WSeg{W + pw::PRE0_W, D, IN_PAD};
-    if (NPRE == 3) {
-      sg[n++] = WSeg{W + pw::PRE1_W, D, D};
-      sg[n++] = WSeg{W + pw::PRE2_W, D, D};
-    }
-    sg[n++] = WSeg{W + pw::MLP0_WB, D, D};
-    sg[n++] = WSeg{W + pw::MLP0_WA, D, D};
-    sg[n++] = WSeg{W + pw::MLP1_W, D, D};
-    sg[n++] = WSeg{W + pw::OUT0_W, D, D};
-    sg[n++] = WSeg{W + pw::OUT1_W, D, D};
-    return n;
-  });
-  float* bufA = smem + WPIPE_BYTES / sizeof(float);   // [ROWS][132]
-  float* bufB = bufA + ROWS * LDS_PAD;                // [ROWS][132]
-  float* sPool = bufB + ROWS * LDS_PAD;               // [PROWS][132]
-  float* sPP = sPool + PROWS * LDS_PAD;               // [PROWS][132]
-  int* sValid = reinterpret_cast<int*>(sPP + PROWS * LDS_PAD);   // [ROWS]
-  const int poly0 = blockIdx.x * G;
-
-  for (int r = threadIdx.x; r < ROWS; r += 256) {
-    const int g = r / P, p = r % P;
-    int v = 0;
-    if (g < G && poly0 + g < n_poly) {
-      v = 1;
-      if (mask != nullptr) {
-        const uint8_t* m = mask + ((size_t)rows[poly0 + g] * P + p) * mask_inner;
-        for (int i = 0; i < mask_inner; ++i) v &= (m[i] != 0);
-      } else {
-        const float* xp = X + ((size_t)rows[poly0 + g] * P + p) * IN;
-        for (int i = 0; i < IN; ++i) v &= !isnan(xp[i]);
-      }
-    }
-    sValid[r] = v;
-  }
-  for (int i = threadIdx.x; i < PROWS * LDS_PAD; i += 256) sPool[i] = 0.f;
-  __syncthreads();
-  for (int i = threadIdx.x; i < ROWS * IN_PAD; i += 256) {
-    const int r = i / IN_PAD, c = i % IN_PAD;
-    float v = 0.f;
-    if (sValid[r] && c < IN) v = X[((size_t)rows[poly0 + r / P] * P + (r % P)) * IN + c];
-    bufA[r * LDS_PAD + c] = v;
-  }
-  __syncthreads();
-
-  const TileCoord tc = tile_coord<TR>();
-  float acc[TR][4];
-  auto store = [&](float* dst, bool relu, bool masked) {
-#pragma unroll
-    for (int r = 0; r < TR; ++r) {
-      const int row = tc.row + r;
-      float4 v = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-      if (relu) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
-      if (masked && !sValid[row]) v = make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(dst + row * LDS_PAD + tc.col) = v;
-    }
-  };
-  auto pool = [&](const float* src) {   // max over the P points of each polyline (zeros of masked points included)
-    for (int i = threadIdx.x; i < G * D; i += 256) {
-      const int g = i >> 7, c = i & 127;
-      float m = src[(g * P) * LDS_PAD + c];
-      for (int p = 1; p < P; ++p) m = fmaxf(m, src[(g * P + p) * LDS_PAD + c]);
-      sPool[g * LDS_PAD + c] = m;
-    }
-  };
-
-  // ---- pre_mlps
-  acc2_init_bias<TR>(acc, W + pw::PRE0_B);
-  gemm2<TR, NW>(acc, bufA, LDS_PAD, pipe);
-  if (NPRE == 1) {
-    store(bufB, true, true);
-  } else {
-    store(bufB, false, false);
-    __syncthreads();
-    ln_tile_inplace<D>(bufB, LDS_PAD, ROWS, W + pw::PRE0_G, W + pw::PRE0_BB, true);
-    __syncthreads();
-    acc2_init_bias<TR>(acc, W + pw::PRE1_B);
-    gemm2<TR, NW>(acc, bufB, LDS_PAD, pipe);
-    __syncthreads();                                   // every warp is done reading bufA's predecessor tile
-    store(bufA, false, false);
-    __syncthreads();
-    ln_tile_inplace<D>(bufA, LDS_PAD, ROWS, W + pw::PRE1_G, W + pw::PRE1_BB, true);
-    __syncthreads();
-    acc2_init_bias<TR>(acc, W + pw::PRE2_B);
-    gemm2<TR, NW>(acc, bufA, LDS_PAD, pipe);
-    __syncthreads();                                   // all reads of bufB (PRE1's input) are long over; keeps the pattern uniform
-    store(bufB, true, true);
-  }
-  __syncthreads();
-
-  // ---- max-pool per polyline and the pooled half of mlps.0 (per polyline, not per point)
-  pool(bufB);
-  __syncthreads();
-  {
-    const TileCoord ts = tile_coord<TRS>();
-    float a4[TRS][4];
-    acc2_init<TRS>(a4, 0.f);
-    gemm2<TRS, NW>(a4, sPool, LDS_PAD, pipe);
-#pragma unroll
-    for (int r = 0; r < TRS; ++r)
-      *reinterpret_cast<float4*>(sPP + (ts.row + r) * LDS_PAD + ts.col) = make_float4(a4[r][0], a4[r][1], a4[r][2], a4[r][3]);
-  }
-  __syncthreads();
-
-  // ---- mlps.0 (point half + pooled half), LN, ReLU ; mlps.1, ReLU
-  {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(W + pw::MLP0_B + tc.col));
-#pragma unroll
-    for (int r = 0; r < TR; ++r) {
-      const int g = (tc.row + r) / P;
-      float4 pp = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (g < G) pp = *reinterpret_cast<const float4*>(sPP + g * LDS_PAD + tc.col);
-      acc[r][0] = b.x + pp.x; acc[r][1] = b.y + pp.y; acc[r][2] = b.z + pp.z; acc[r][3] = b.w + pp.w;
-    }
-  }
-  gemm2<TR, NW>(acc, bufB, LDS_PAD, pipe);
-  store(bufA, false, false);
-  __syncthreads();
-  ln_tile_inplace<D>(bufA, LDS_PAD, ROWS, W + pw::MLP0_G, W + pw::MLP0_BB, true);
-  __syncthreads();
-  acc2_init_bias<TR>(acc, W + pw::MLP1_B);
-  gemm2<TR, NW>(acc, bufA, LDS_PAD, pipe);
-  __syncthreads();                                     // the pooled-half / point-half GEMMs have finished reading bufB
-  store(bufB, true, true);
-  __syncthreads();
-  pool(bufB);
-  __syncthreads();
-
-  // ---- out_mlps on the G pooled rows
-  {
-    const TileCoord ts = tile_coord<TRS>();
-    float a4[TRS][4];
-    acc2_init_bias<TRS>(a4, W + pw::OUT0_B);
-    gemm2<TRS, NW>(a4, sPool, LDS_PAD, pipe);
-#pragma unroll
-    for (int r = 0; r < TRS; ++r)
-      *reinterpret_cast<float4*>(sPP + (ts.row + r) * LDS_PAD + ts.col) =
-          make_float4(fmaxf(a4[r][0], 0.f), fmaxf(a4[r][1], 0.f), fmaxf(a4[r][2], 0.f), fmaxf(a4[r][3], 0.f));
-    __syncthreads();
-    acc2_init_bias<TRS>(a4, W + pw::OUT1_B);
-    gemm2<TRS, NW>(a4, sPP, LDS_PAD, pipe);
-#pragma unroll
-    for (int r = 0; r < TRS; ++r) {
-      const int g = ts.row + r;
-      if (g < G && poly0 + g < n_poly) {
-        int any = 0;
-        for (int p = 0; p < P; ++p) any |= sValid[g * P + p];
-        *reinterpret_cast<float4*>(Out + (size_t)(poly0 + g) * D + ts.col) =
-            any ? make_float4(a4[r][0], a4[r][1], a4[r][2], a4[r][3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-  }
-}
+// Tried and dropped (round 1): the same chain with every GEMM on gemm_tile.cuh's shared-memory weight stream (gemm2 /
+// WPipe, 128-row CTAs, 8 warps x 16 rows or 16 warps x 8 rows; bit-identical results).  ncu: 174 us against 187 us for the
+// agent histories but 1.67 ms against 1.40 ms for the map polylines (one CTA per SM at 218 KB, issue slots 34 % busy
+// against 48 %), 3.06 ms against 2.91 ms per forward in total.  This kernel already runs at 45 % (map) / 27 % (agent
+// histories) of the fp32 FMA peak; the next step for it is the tensor pipe, not another FFMA tiling.
 
 }  // namespace prosim
