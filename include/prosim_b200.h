@@ -87,9 +87,12 @@ size_t prosim_attn_workspace_floats(int n_dst, int n_src, int max_stride);
  * kind 1 = map polyline  (19 vectors x 11 features, mask uint8 [.,19];   map_encoder.py:67-88)
  * kind 2 / 3 = drag-point condition (16 / 8 points x 2 features; condition_transformer/condition_encoders.py:147-191);
  *          mask may be NULL: a point is then valid when neither coordinate is NaN (:178)
- * rows[n_poly] selects the polylines to encode out of x; out is compact [n_poly][128]. */
+ * rows[n_poly] selects the polylines to encode out of x; out is compact [n_poly][128].
+ * w = fp32 block (prosim_pointnet_floats), w_tc (nullable) = the same matrices as tcgen05 operands (K = 32 chunks
+ * pre-split into tf32 hi / lo, weights.py::pack_pointnet_tc): with w_tc and prosim_set_tensor_core(1) the GEMM chain runs
+ * on the tensor cores (csrc/pointnet_tc.cuh, 3xTF32), otherwise on fp32 FFMA (csrc/pointnet.cuh). */
 int prosim_pointnet_fwd(int kind, const float* x, const uint8_t* mask, const int32_t* rows, int n_poly,
-                        const float* w, float* out, prosim_stream_t stream);
+                        const float* w, const float* w_tc, float* out, prosim_stream_t stream);
 
 /* torch_cluster.radius / radius_graph (call sites decoder/sym_coord.py:86,94; policy/act_decoder.py:250,259).
  * seg[B][4] = {start0,len0,start1,len1}: source ranges of each scene.  drop_self=1 gives radius_graph(loop=False)

@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "graph.cuh"
 #include "pointnet.cuh"
+#include "pointnet_tc.cuh"
 #include <cstdlib>
 #include "rollout.cuh"
 #include "tc_gemm.cuh"
@@ -98,6 +99,10 @@ int setup_attributes() {
   acc(allow_smem(pointnet_kernel<11, 12, 3, 19>, PointNetCfg<19>::smem_bytes));
   acc(allow_smem(pointnet_kernel<2, 4, 1, 16>, PointNetCfg<16>::smem_bytes));
   acc(allow_smem(pointnet_kernel<2, 4, 1, 8>, PointNetCfg<8>::smem_bytes));
+  acc(allow_smem(pointnet_tc_kernel<24, 1, 11>, pntc::Cfg<11>::smem_bytes));
+  acc(allow_smem(pointnet_tc_kernel<11, 3, 19>, pntc::Cfg<19>::smem_bytes));
+  acc(allow_smem(pointnet_tc_kernel<2, 1, 16>, pntc::Cfg<16>::smem_bytes));
+  acc(allow_smem(pointnet_tc_kernel<2, 1, 8>, pntc::Cfg<8>::smem_bytes));
   acc(allow_smem(knn_kernel, 64 * 1024));
   acc(allow_smem(attn_kv2_kernel<4, 8>, Kv2Smem<4, 8>::bytes));
   acc(allow_smem(attn_kv2_kernel<8, 8>, Kv2Smem<8, 8>::bytes));
@@ -326,7 +331,7 @@ int launch_post(const float* x, int n, int zd, const float* rbar, const float* a
 
 extern "C" {
 
-int prosim_abi_version(void) { return 6; }
+int prosim_abi_version(void) { return 7; }
 int prosim_tc_debug_read(long long* out32) {
   if (!out32) return ERR_ARG;
   return (int)cudaMemcpyFromSymbol(out32, tcp::g_tcp_dbg, 32 * sizeof(long long));
@@ -385,12 +390,29 @@ size_t prosim_attn_workspace_floats(int n_dst, int n_src, int max_stride) {
 }
 
 int prosim_pointnet_fwd(int kind, const float* x, const uint8_t* mask, const int32_t* rows, int n_poly, const float* w,
-                        float* out, prosim_stream_t stream) {
+                        const float* w_tc, float* out, prosim_stream_t stream) {
   if (n_poly < 0 || kind < 0 || kind > 3) return ERR_ARG;
   if (n_poly == 0) return 0;
   if (!x || (!mask && kind < 2) || !rows || !w || !out) return ERR_ARG;
   if (int e = setup_attributes()) return e;
   LaunchScope ls(PROSIM_K_POINTNET, S(stream));
+  if (w_tc != nullptr && g_use_tc) {   // tcgen05 / TMEM 3xTF32 kernel (pointnet_tc.cuh)
+    if ((reinterpret_cast<uintptr_t>(w_tc) & 15) != 0) return ERR_ARG;
+    if (kind == 0)
+      pointnet_tc_kernel<24, 1, 11><<<(n_poly + pntc::Cfg<11>::G - 1) / pntc::Cfg<11>::G, 128, pntc::Cfg<11>::smem_bytes, S(stream)>>>(
+          x, mask, 24, rows, n_poly, w, w_tc, out);
+    else if (kind == 1)
+      pointnet_tc_kernel<11, 3, 19><<<(n_poly + pntc::Cfg<19>::G - 1) / pntc::Cfg<19>::G, 128, pntc::Cfg<19>::smem_bytes, S(stream)>>>(
+          x, mask, 1, rows, n_poly, w, w_tc, out);
+    else if (kind == 2)
+      pointnet_tc_kernel<2, 1, 16><<<(n_poly + pntc::Cfg<16>::G - 1) / pntc::Cfg<16>::G, 128, pntc::Cfg<16>::smem_bytes, S(stream)>>>(
+          x, mask, 1, rows, n_poly, w, w_tc, out);
+    else
+      pointnet_tc_kernel<2, 1, 8><<<(n_poly + pntc::Cfg<8>::G - 1) / pntc::Cfg<8>::G, 128, pntc::Cfg<8>::smem_bytes, S(stream)>>>(
+          x, mask, 1, rows, n_poly, w, w_tc, out);
+    PROSIM_CHECK_LAUNCH();
+    return 0;
+  }
   if (kind == 0) {
     constexpr int G = PointNetCfg<11>::G;
     pointnet_kernel<24, 24, 1, 11><<<(n_poly + G - 1) / G, 256, PointNetCfg<11>::smem_bytes, S(stream)>>>(

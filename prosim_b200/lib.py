@@ -8,7 +8,7 @@ from ctypes import POINTER, Structure, c_float, c_int, c_int32, c_size_t, c_void
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libprosim_b200.so')
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 SYMBOLS = (
     'prosim_abi_version', 'prosim_attn_layer_floats', 'prosim_pointnet_floats', 'prosim_head_floats',
@@ -38,7 +38,7 @@ class ProSimLibError(RuntimeError):
 
 _P = c_void_p
 _SIGS = {
-    'prosim_pointnet_fwd': [c_int, _P, _P, _P, c_int, _P, _P, _P],
+    'prosim_pointnet_fwd': [c_int, _P, _P, _P, c_int, _P, _P, _P, _P],
     'prosim_build_radius_edges': [_P, _P, c_int, _P, _P, c_float, c_int, c_int, _P, _P, c_int, _P],
     'prosim_build_knn_edges': [_P, _P, c_int, _P, _P, c_int, c_int, _P, _P, c_int, _P],
     'prosim_edge_pe': [_P, _P, c_int, _P, _P, _P, _P, c_int, _P, _P, c_int, _P, _P],

@@ -310,8 +310,8 @@ class ProSimB200(nn.Module):
         tok = self._buf('tok', (S, D))
         tok_pos = self._buf('tok_pos', (S, 2))
         tok_ori = self._buf('tok_ori', (S,))
-        ops.pointnet(1, mp['input'], mp['mask'], pl.i['map_rows'], ar, off['map_enc'], out=tok[:NM])
-        ops.pointnet(0, obs['input'], obs['mask'], pl.i['agent_rows0'], ar, off['obs_enc'], out=tok[NM:])
+        ops.pointnet(1, mp['input'], mp['mask'], pl.i['map_rows'], ar, off['map_enc'], out=tok[:NM], tc_off=off['map_enc_tc'])
+        ops.pointnet(0, obs['input'], obs['mask'], pl.i['agent_rows0'], ar, off['obs_enc'], out=tok[NM:], tc_off=off['obs_enc_tc'])
         ops.gather_pose(mp['position'], mp['heading'], pl.i['map_rows'], tok_pos[:NM], tok_ori[:NM])
         ops.gather_pose(obs['position'], obs['heading'], pl.i['agent_rows0'], tok_pos[NM:], tok_ori[NM:])
         dim_t = ar[off['dim_t16']:off['dim_t16'] + 16]
@@ -525,7 +525,7 @@ class ProSimB200(nn.Module):
                 ops.step_env(traj, vel, init_pos, init_heading, pl.i['p_row'], pl.i[f'p_slot{i}'], T, tidx, p_pos, p_ori,
                              fut=(fut['input'], fut['mask'], fut['position'], fut['heading']))
                 x_a, a_pos, a_ori = x_a_buf[:na], a_pos_buf[:na], a_ori_buf[:na]
-                ops.pointnet(0, fut['input'], fut['mask'], pl.i[f'agent_rows{i}'], ar, off['obs_enc'], out=x_a)
+                ops.pointnet(0, fut['input'], fut['mask'], pl.i[f'agent_rows{i}'], ar, off['obs_enc'], out=x_a, tc_off=off['obs_enc_tc'])
                 ops.gather_pose(fut['position'], fut['heading'], pl.i[f'agent_rows{i}'], a_pos, a_ori)
             e_a = ops.radius_edges(p_pos, pl.i['p_scene'], a_pos, pl.i[f'seg_agent{i}'].view(-1, 4), acfg.AGENT_RADIUS,
                                    acfg.MAX_NUM_NEIGH, stride_a, nbr=nbr_a, deg=deg_a)

@@ -58,8 +58,9 @@ class EdgeList:
         return torch.stack([nbr[j], dst], dim=0)
 
 
-def pointnet(kind, x, mask, rows, w_arena, w_off, out=None):
-    """kind 0 obs / 1 map / 2, 3 drag points (16 / 8 per agent; mask None = validity from NaN)."""
+def pointnet(kind, x, mask, rows, w_arena, w_off, out=None, tc_off=None):
+    """kind 0 obs / 1 map / 2, 3 drag points (16 / 8 per agent; mask None = validity from NaN).
+    tc_off: offset of the tensor-core operand block (weights.pack_pointnet_tc); None = fp32 FFMA kernel."""
     _chk(x, torch.float32, 'x'), _chk(rows, torch.int32, 'rows')
     if mask is not None or kind < 2:
         mask = as_u8(mask)
@@ -67,7 +68,8 @@ def pointnet(kind, x, mask, rows, w_arena, w_off, out=None):
     n = rows.shape[0]
     if out is None:
         out = torch.empty(n, D, device=x.device, dtype=torch.float32)
-    lib.call('prosim_pointnet_fwd', kind, ptr(x), ptr(mask), ptr(rows), n, ptr(w_arena, w_off), ptr(out), _stream())
+    lib.call('prosim_pointnet_fwd', kind, ptr(x), ptr(mask), ptr(rows), n, ptr(w_arena, w_off),
+             ptr(w_arena, tc_off) if tc_off is not None else None, ptr(out), _stream())
     return out
 
 

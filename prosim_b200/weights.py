@@ -307,6 +307,26 @@ def pack_pointnet(sd, p, n_pre):
     return out
 
 
+def pointnet_tc_floats(n_pre):
+    return (1 + (8 if n_pre == 3 else 0) + 8 + 4 + 4 + 4) * 8192
+
+
+def pack_pointnet_tc(sd, p, n_pre):
+    """Tensor-core operand block of one PointNet (csrc/pointnet_tc.cuh): every weight matrix [128 out][K in] cut into
+    K = 32 chunks, each pre-split into tf32 hi / lo in the tcgen05 core-matrix order, in the order the kernel consumes them:
+    pre_mlps.0 (input dim zero-padded to 32) [, pre_mlps.3, pre_mlps.6], mlps.0 (K = 256: point half, pooled half), mlps.3,
+    out_mlps.0, out_mlps.2."""
+    w = lambda n: _f64(sd[f'{p}.{n}']).float()
+    w0 = w('pre_mlps.mlp.0.weight')
+    mats = [torch.cat([w0, torch.zeros(D, 32 - w0.shape[1])], dim=1)]
+    if n_pre == 3:
+        mats += [w('pre_mlps.mlp.3.weight'), w('pre_mlps.mlp.6.weight')]
+    mats += [w('mlps.mlp.0.weight'), w('mlps.mlp.3.weight'), w('out_mlps.mlp.0.weight'), w('out_mlps.mlp.2.weight')]
+    out = torch.cat([_umma_chunk(m[:, 32 * c:32 * c + 32]) for m in mats for c in range(m.shape[1] // 32)])
+    assert out.numel() == pointnet_tc_floats(n_pre)
+    return out
+
+
 def _pack_mlp3(sd, p):
     w = lambda n: _f64(sd[f'{p}.{n}'])
     parts = [w('mlp.0.weight').t(), w('mlp.0.bias'), w('mlp.1.weight'), w('mlp.1.bias'),
@@ -346,6 +366,8 @@ def pack_model(sd, num_layers=6, cond_layers=3):
     sections = OrderedDict()
     sections['map_enc'] = pack_pointnet(sd, 'scene_encoder.map_encoder', 3)
     sections['obs_enc'] = pack_pointnet(sd, 'scene_encoder.obs_encoder', 1)
+    sections['map_enc_tc'] = pack_pointnet_tc(sd, 'scene_encoder.map_encoder', 3)
+    sections['obs_enc_tc'] = pack_pointnet_tc(sd, 'scene_encoder.obs_encoder', 1)
     stacks = [('enc_a2a', 'scene_encoder.a2a_attn_layers', num_layers),
               ('enc_s2s', 'scene_encoder.s2s_attn_layers', num_layers),
               ('dec_p2p', 'decoder.p2p_attn_layers', num_layers),
@@ -370,6 +392,7 @@ def pack_model(sd, num_layers=6, cond_layers=3):
         sections['dim_t64'] = (10000 ** (2 * (dt // 2) / 64)).contiguous()
     if f'{ce}.drag_point.pointnet_encoder.pre_mlps.mlp.0.weight' in sd:
         sections['drag_enc'] = pack_pointnet(sd, f'{ce}.drag_point.pointnet_encoder', 1)
+        sections['drag_enc_tc'] = pack_pointnet_tc(sd, f'{ce}.drag_point.pointnet_encoder', 1)
     sections['head'] = pack_head(sd)
     # FourierEmbeddingFix denominators, evaluated by torch exactly as the reference does (fourier_embedding.py:66-67)
     dt = torch.arange(128 / 4, dtype=torch.float32)
