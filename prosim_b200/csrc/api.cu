@@ -9,6 +9,7 @@
 #include "graph.cuh"
 #include "pointnet.cuh"
 #include "pointnet_tc.cuh"
+#include "kv_tc.cuh"
 #include <cstdlib>
 #include "rollout.cuh"
 #include "tc_gemm.cuh"
@@ -99,6 +100,7 @@ int setup_attributes() {
   acc(allow_smem(pointnet_kernel<11, 12, 3, 19>, PointNetCfg<19>::smem_bytes));
   acc(allow_smem(pointnet_kernel<2, 4, 1, 16>, PointNetCfg<16>::smem_bytes));
   acc(allow_smem(pointnet_kernel<2, 4, 1, 8>, PointNetCfg<8>::smem_bytes));
+  acc(allow_smem(attn_kv_tc_kernel, kvtc::SMEM_BYTES));
   acc(allow_smem(pointnet_tc_kernel<24, 1, 11>, pntc::Cfg<11>::smem_bytes));
   acc(allow_smem(pointnet_tc_kernel<11, 3, 19>, pntc::Cfg<19>::smem_bytes));
   acc(allow_smem(pointnet_tc_kernel<2, 1, 16>, pntc::Cfg<16>::smem_bytes));
@@ -153,6 +155,12 @@ int launch_kv(const float* x, int n, const float* w, size_t wstride, int layers,
   const int rpt = pick_rpt(n * layers);
   LaunchScope ls(PROSIM_K_ATTN_KV, st);
   const int rt = pick_rt(n);
+  if (g_use_tc) {   // tcgen05 / TMEM 3xTF32 (kv_tc.cuh) for every launch size: a row's K'|V' never depends on the batch it is in
+    if (int e = setup_attributes()) return e;
+    attn_kv_tc_kernel<<<dim3((n + 127) / 128, layers), 128, kvtc::SMEM_BYTES, st>>>(x, n, w, wstride, kv, kvstride);
+    PROSIM_CHECK_LAUNCH();
+    return 0;
+  }
   if (rt == 4) {
     attn_kv2_kernel<8, 8><<<dim3((n + 63) / 64, layers), 256, Kv2Smem<8, 8>::bytes, st>>>(x, n, w, wstride, kv, kvstride);
     PROSIM_CHECK_LAUNCH();

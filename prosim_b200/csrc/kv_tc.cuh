@@ -1,0 +1,119 @@
+// K' | V' of an attention layer's sources on the tensor cores (tcgen05 + TMEM, 3xTF32).
+//
+// Same math as attn_kv2_kernel (attn2.cuh; reference prosim/models/layers/attention_layer.py:67-72 with the folds of
+// weights_layout.h):  K' = Wk LN_src(x) + Wkr beta_r,  V' = Wv LN_src(x) + b_v + Wvr beta_r + b_vr.
+// One CTA (128 threads, thread = source row = TMEM lane) per 128 rows and layer, built on the chunk pipeline of
+// pointnet_tc.cuh: the row's LayerNorm is thread local, every K = 32 chunk of LN(x) is staged once per product and
+// multiplied into two accumulators (K' at TMEM columns 0..127, V' at 128..255) by weight chunks that arrive
+// interleaved [Wk c0, Wv c0, Wk c1, ...] (aw::TC_KV).  Rows enter and leave through a padded shared-memory tile so that
+// global accesses are whole 512-byte rows.
+#pragma once
+#include "pointnet_tc.cuh"
+
+namespace prosim {
+namespace kvtc {
+constexpr int TILE_LD = 132;
+constexpr size_t SMEM_BYTES = 1024 + 2 * pntc::A_BYTES + 2 * pntc::B_STAGE_BYTES + 64;
+static_assert(2 * pntc::A_BYTES + 2 * pntc::B_STAGE_BYTES >= 128 * TILE_LD * 4, "row tile aliases the operand buffers");
+}  // namespace kvtc
+
+__global__ void __launch_bounds__(128, 2) attn_kv_tc_kernel(const float* __restrict__ X, int N, const float* __restrict__ Wbase,
+                                                            size_t w_layer_stride, float* __restrict__ KV,
+                                                            size_t kv_layer_stride) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - (e4::smem_u32(smem_raw) & 1023u)) & 1023u);
+  const float* W = Wbase + (size_t)blockIdx.y * w_layer_stride;
+  float* kv = KV + (size_t)blockIdx.y * kv_layer_stride;
+  pntc::Pipe p;
+  p.sAhi = base;
+  p.sAlo = base + pntc::A_BYTES;
+  p.sB = base + 2 * pntc::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p.sB + 2 * pntc::B_STAGE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  p.bfull = bars;
+  p.bmma = bars + 2;
+  p.wtc = W + aw::TC_KV;
+  p.chunk = 0;
+  p.total = 8;
+  float* tile = reinterpret_cast<float*>(base);     // [128][132] fp32 over the (idle) operand buffers
+  const int m = threadIdx.x, warp = m >> 5;
+  const int row0 = blockIdx.x * 128;
+
+  if (warp == 0) tc::tmem_alloc(tmem_slot, 256);
+  if (m == 32) {
+    tc::mbar_init(&p.bfull[0], 1);
+    tc::mbar_init(&p.bfull[1], 1);
+    tc::mbar_init(p.bmma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  // rows -> tile (coalesced float4), then each thread takes its own row
+  for (int i = m; i < 128 * 32; i += 128) {
+    const int r = i >> 5, c4 = i & 31;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row0 + r < N) t = __ldg(reinterpret_cast<const float4*>(X + (size_t)(row0 + r) * D) + c4);
+    *reinterpret_cast<float4*>(tile + r * kvtc::TILE_LD + 4 * c4) = t;
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  p.tmem = *tmem_slot;
+  float v[128];
+#pragma unroll
+  for (int i = 0; i < 128; i += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(tile + m * kvtc::TILE_LD + i);
+    v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+  }
+  __syncthreads();                       // the tile is about to become operand buffers again
+  if (m == 0) pntc::load_b(p, 0);
+  {   // LN_src with affine, thread local
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 128; ++i) s += v[i];
+    const float mean = s * (1.0f / 128.0f);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 128; ++i) {
+      const float d = v[i] - mean;
+      q = fmaf(d, d, q);
+    }
+    const float rstd = 1.0f / sqrtf(q * (1.0f / 128.0f) + LN_EPS);
+#pragma unroll
+    for (int i = 0; i < 128; i += 4) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(W + aw::LN_SRC_G + i));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(W + aw::LN_SRC_B + i));
+      v[i] = (v[i] - mean) * rstd * g.x + b.x;
+      v[i + 1] = (v[i + 1] - mean) * rstd * g.y + b.y;
+      v[i + 2] = (v[i + 2] - mean) * rstd * g.z + b.z;
+      v[i + 3] = (v[i + 3] - mean) * rstd * g.w + b.w;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float a[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a[i] = v[c * 32 + i];
+    pntc::chunk_mma(p, a, c == 0, 0);      // K' += LN(x)[:, 32c..] . Wk chunk c
+    pntc::chunk_mma(p, a, c == 0, 128);    // V' += LN(x)[:, 32c..] . Wv chunk c
+  }
+  // accumulators -> tile -> global, one 128-column half at a time
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    pntc::read_acc(p, W + (half == 0 ? aw::KB : aw::VB), v, half * 128);
+    if (half == 1) __syncthreads();      // the first half has left the tile
+#pragma unroll
+    for (int i = 0; i < 128; i += 4)
+      *reinterpret_cast<float4*>(tile + m * kvtc::TILE_LD + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    __syncthreads();
+    for (int i = m; i < 128 * 32; i += 128) {
+      const int r = i >> 5, c4 = i & 31;
+      if (row0 + r < N)
+        *(reinterpret_cast<float4*>(kv + (size_t)(row0 + r) * 256 + half * 128) + c4) =
+            *reinterpret_cast<const float4*>(tile + r * kvtc::TILE_LD + 4 * c4);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(p.tmem, 256);
+}
+
+}  // namespace prosim

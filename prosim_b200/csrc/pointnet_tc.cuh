@@ -12,7 +12,12 @@
 // memory by the row's own thread; one thread issues 4 k-steps x 3 MMAs (a_lo*w_hi + a_hi*w_lo + a_hi*w_hi, fp32
 // accumulate in tensor memory) and commits to an mbarrier.  Epilogues (bias, LayerNorm, ReLU, mask) are thread local:
 // a thread reads its row's 128 accumulator columns with tcgen05.ld and keeps them in registers as the next A operand.
-// 128 TMEM columns and ~113 KB of shared memory per CTA: two CTAs per SM overlap each other's epilogues and MMAs.
+// 128 TMEM columns and ~106 KB of shared memory per CTA: two CTAs per SM overlap each other's epilogues and MMAs.
+// Measured alternatives (round 1, per forward: PointNet / K'V' launches): this version 1.77 / 0.91 ms; a 4-stage weight
+// ring with one CTA per SM 2.43 / 1.09 ms; 4 stages + two A buffers with deferred MMA waits 2.23 / 1.01 ms -- the chunk
+// loop is bound by the per-thread epilogue / staging instruction streams (one warp per scheduler), so the second
+// resident CTA is worth more than deeper pipelines inside one CTA.  (A policy-head variant on this pipeline was also
+// tried: 96 us against 84 us for the FFMA kernel at 32 CTAs, and its 3xTF32 rounding fed the closed loop directly.)
 #pragma once
 #include "common.cuh"
 #include "edge4.cuh"     // e4:: mbarrier / bulk-copy helpers
@@ -80,8 +85,9 @@ __device__ __forceinline__ void load_b(const Pipe& p, int c) {
 }
 
 // One K = 32 chunk of the current GEMM: a[] = this thread's 32 activations (row m = threadIdx.x).
-// first: the chunk starts a new accumulation.  All 128 threads call this in lockstep.
-__device__ __forceinline__ void chunk_mma(Pipe& p, const float (&a)[32], bool first) {
+// first: the chunk starts a new accumulation (in the 128 accumulator columns at acc_col).  All 128 threads call this in
+// lockstep.
+__device__ __forceinline__ void chunk_mma(Pipe& p, const float (&a)[32], bool first, uint32_t acc_col = 0) {
   const int m = threadIdx.x;
   // the previous chunk's MMAs have consumed the A buffers (and the stage the NEXT copy goes to)
   if (p.chunk > 0) wait_bar(p.bmma, (p.chunk - 1) & 1);
@@ -111,9 +117,9 @@ __device__ __forceinline__ void chunk_mma(Pipe& p, const float (&a)[32], bool fi
       const uint32_t adv = ks * 2 * LBO;
       const uint64_t ah = tc::make_smem_desc(ah0 + adv, LBO, SBO), al = tc::make_smem_desc(al0 + adv, LBO, SBO);
       const uint64_t bh = tc::make_smem_desc(bh0 + adv, LBO, SBO), bl = tc::make_smem_desc(bl0 + adv, LBO, SBO);
-      tc::mma_tf32(p.tmem, al, bh, idesc, !(first && ks == 0));
-      tc::mma_tf32(p.tmem, ah, bl, idesc, true);
-      tc::mma_tf32(p.tmem, ah, bh, idesc, true);
+      tc::mma_tf32(p.tmem + acc_col, al, bh, idesc, !(first && ks == 0));
+      tc::mma_tf32(p.tmem + acc_col, ah, bl, idesc, true);
+      tc::mma_tf32(p.tmem + acc_col, ah, bh, idesc, true);
     }
     tc::mma_commit(p.bmma);
   }
@@ -121,14 +127,14 @@ __device__ __forceinline__ void chunk_mma(Pipe& p, const float (&a)[32], bool fi
 }
 
 // wait for the last chunk's MMAs and read this thread's 128 accumulator columns (+ bias)
-__device__ __forceinline__ void read_acc(Pipe& p, const float* __restrict__ bias, float (&v)[128]) {
+__device__ __forceinline__ void read_acc(Pipe& p, const float* __restrict__ bias, float (&v)[128], uint32_t acc_col = 0) {
   wait_bar(p.bmma, (p.chunk - 1) & 1);
   tc::fence_after_sync();
   const uint32_t lane_base = p.tmem + ((uint32_t)((threadIdx.x >> 5) * 32) << 16);
 #pragma unroll
   for (int c0 = 0; c0 < 128; c0 += 32) {
     float t[32];
-    tc::tmem_ld32(lane_base + c0, t);
+    tc::tmem_ld32(lane_base + acc_col + c0, t);
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + i));

@@ -55,7 +55,8 @@ constexpr int TC_Q = TC_FF + 32 * 8192;        // 4 k-chunks each: to_q (pre-sca
 constexpr int TC_S = TC_Q + 4 * 8192;
 constexpr int TC_GX = TC_S + 4 * 8192;
 constexpr int TC_KRG = TC_GX + 4 * 8192;       // 8 heads x [128 d][16 c]  (WKRG rows of the head, transposed)
-constexpr int SIZE = TC_KRG + 8 * 4096;
+constexpr int TC_KV = TC_KRG + 8 * 4096;       // kv_tc.cuh: 4 k-chunks x ([128 n][32 k] of to_k, then of to_v), interleaved
+constexpr int SIZE = TC_KV + 8 * 8192;
 }  // namespace aw
 
 namespace pw {  // PointNet polyline encoder (scene_encoder/pointnet_encoder.py:13-62)

@@ -173,7 +173,7 @@ def param_shapes_cache(goal_condition):
 # ----------------------------------------------------------------------------- packing (mirror of csrc/weights_layout.h)
 ATTN_FP32_FLOATS = 512 + 3 * (16384 + 128) + 2 * 16384 + 12288 + (16384 + 128) + (2 * 16384 + 128) + (16384 + 128) + 512 \
     + (65536 + 512) + (65536 + 128) + 256
-ATTN_TC_FLOATS = 8 * 3072 + 8 * 4096 + 2 * 4 * 8192 + 32 * 8192 + 3 * 4 * 8192 + 8 * 4096
+ATTN_TC_FLOATS = 8 * 3072 + 8 * 4096 + 2 * 4 * 8192 + 32 * 8192 + 3 * 4 * 8192 + 8 * 4096 + 8 * 8192
 ATTN_LAYER_FLOATS = ATTN_FP32_FLOATS + ATTN_TC_FLOATS
 POINTNET_FLOATS = (24 * 128 + 384) + (16384 + 384) + (16384 + 128) + (2 * 16384 + 384) + (16384 + 128) + 2 * (16384 + 128)
 _MLP3_FLOATS = 2 * (16384 + 384) + (64 * 128 + 128)
@@ -210,11 +210,11 @@ def _umma_chunk(b):
     return torch.cat([lay(hi), lay(lo)])
 
 
-def _pack_attn_tc(wqt, wkrg, wvrgt, wvrg96t, wst, wgat, wgxt, wot, w1t, w2t):
+def _pack_attn_tc(wqt, wkrg, wvrgt, wvrg96t, wst, wgat, wgxt, wot, w1t, w2t, wkt, wvt):
     """Tensor-core operand block of one layer from the fp32-rounded K-major weights the FFMA kernels use."""
     f = lambda x: x.float()
-    wqt, wkrg, wvrgt, wvrg96t, wst, wgat, wgxt, wot, w1t, w2t = map(f, (wqt, wkrg, wvrgt, wvrg96t, wst, wgat, wgxt, wot,
-                                                                       w1t, w2t))
+    wqt, wkrg, wvrgt, wvrg96t, wst, wgat, wgxt, wot, w1t, w2t, wkt, wvt = map(f, (wqt, wkrg, wvrgt, wvrg96t, wst, wgat, wgxt,
+                                                                                 wot, w1t, w2t, wkt, wvt))
     out = []
     out += [_umma_chunk(wvrg96t[:, h * 16:(h + 1) * 16].t()) for h in range(HEADS)]
     out += [_umma_chunk(wvrgt[:, h * 16:(h + 1) * 16].t()) for h in range(HEADS)]
@@ -229,6 +229,8 @@ def _pack_attn_tc(wqt, wkrg, wvrgt, wvrg96t, wst, wgat, wgxt, wot, w1t, w2t):
     out += [down(14), down(15)]
     out += kchunks(wqt) + kchunks(wst) + kchunks(wgxt)
     out += [_umma_chunk(wkrg[h * 16:(h + 1) * 16, :].t()) for h in range(HEADS)]
+    for c in range(4):                                # kv_tc.cuh: to_k and to_v chunks interleaved
+        out += [_umma_chunk(wkt.t()[:, 32 * c:32 * c + 32]), _umma_chunk(wvt.t()[:, 32 * c:32 * c + 32])]
     out = torch.cat(out)
     assert out.numel() == ATTN_TC_FLOATS
     return out
@@ -260,7 +262,7 @@ def pack_attn_layer(sd, p):
         w('ff_postnorm.weight'), w('ff_postnorm.bias'),
     ]
     tc = _pack_attn_tc(wqt=parts[4], wkrg=parts[10], wvrgt=parts[11], wvrg96t=parts[12], wst=parts[13], wgat=parts[15],
-                       wgxt=parts[16], wot=parts[18], w1t=parts[24], w2t=parts[26])
+                       wgxt=parts[16], wot=parts[18], w1t=parts[24], w2t=parts[26], wkt=parts[6], wvt=parts[8])
     out = torch.cat([x.contiguous().reshape(-1) for x in parts]).float()
     assert out.numel() == ATTN_FP32_FLOATS
     return torch.cat([out, tc])
