@@ -13,3 +13,9 @@ ncu --profile-from-start off --set full --clock-control none --import-source on 
 ncu -i gpurun_out/r1_layer_$V.ncu-rep --page raw --csv > gpurun_out/r1_layer_${V}_raw.csv 2>> gpurun_out/prof_$V.log
 ncu -i gpurun_out/r1_layer_$V.ncu-rep --page source --csv -k regex:attn_edge4 -c 1 > gpurun_out/edge4_src_$V.csv 2>> gpurun_out/prof_$V.log
 ls -la gpurun_out/*$V*
+# the tensor-core PointNet / K'V' kernels (first launches of the forward: map polylines, agent histories, one K'V' launch)
+ncu --profile-from-start off --set full --clock-control none --import-source on \
+    -k regex:'pointnet_tc|attn_kv_tc' -c 4 -f -o gpurun_out/r1_pntc_$V \
+    python tools/profile_forward.py --ticks 1 >> gpurun_out/prof_$V.log 2>&1
+ncu -i gpurun_out/r1_pntc_$V.ncu-rep --page raw --csv > gpurun_out/r1_pntc_${V}_raw.csv 2>> gpurun_out/prof_$V.log
+ls -la gpurun_out/*pntc*$V*
