@@ -265,54 +265,60 @@ __global__ void __launch_bounds__(128, 2) pointnet_tc_kernel(const float* __rest
     for (int i = 0; i < 128; ++i) v[i] = valid ? fmaxf(v[i], 0.f) : 0.f;
   };
 
-  // ---- pre_mlps
+  // ---- the chain as a runtime loop over six stages (each: epilogue of the previous GEMM, then a K = 128 GEMM): one copy of
+  // the staging / MMA-issue / accumulator-read / LayerNorm / pooling code instead of one per GEMM.  Fully unrolled, the
+  // kernel was 11-16 k instructions (180-260 KB) that every warp walked through exactly once: the top stall was
+  // instruction fetch (ncu: 2.4-5.1 "no instruction" cycles per issued instruction).
+  //   stage 0, 1 (NPRE = 3 only): LN+ReLU -> pre_mlps.1 / pre_mlps.2
+  //   stage 2: ReLU+mask, max-pool -> mlps.0 on [point | pooled] (two K = 128 halves into one accumulator)
+  //   stage 3: LN+ReLU -> mlps.1
+  //   stage 4: ReLU+mask, max-pool, pooled rows to threads 0..G-1 -> out_mlps.0
+  //   stage 5: ReLU -> out_mlps.1
   pntc::chunk_mma(p, x, true);
   pntc::read_acc(p, W + pw::PRE0_B, v);
-  if (NPRE == 3) {
-    pntc::ln_relu(v, W + pw::PRE0_G, W + pw::PRE0_BB);
-    pntc::gemm_rows<128>(p, v);
-    pntc::read_acc(p, W + pw::PRE1_B, v);
-    pntc::ln_relu(v, W + pw::PRE1_G, W + pw::PRE1_BB);
-    pntc::gemm_rows<128>(p, v);
-    pntc::read_acc(p, W + pw::PRE2_B, v);
-  }
-  relu_mask();
-  pool();
-  // ---- mlps.0 on [point | pooled]  (K = 256), LN, ReLU ; mlps.1, ReLU
-  pntc::gemm_rows<128>(p, v);
-  {
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
-      float a[32];
+  for (int st = (NPRE == 3 ? 0 : 2); st < 6; ++st) {
+    if (st == 0 || st == 1 || st == 3) {
+      const int go = st == 0 ? pw::PRE0_G : st == 1 ? pw::PRE1_G : pw::MLP0_G;
+      pntc::ln_relu(v, W + go, W + go + 128);                  // gamma and beta are adjacent in the pw:: block
+    } else if (st == 5) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g < G) t = *reinterpret_cast<const float4*>(sPool + g * 128 + c * 32 + i);
-        a[i] = t.x; a[i + 1] = t.y; a[i + 2] = t.z; a[i + 3] = t.w;
+      for (int i = 0; i < 128; ++i) v[i] = m < G ? fmaxf(v[i], 0.f) : 0.f;
+    } else {
+      relu_mask();
+      if (st == 4) __syncthreads();                            // every thread has read its pooled row of the first pooling
+      pool();
+      if (st == 4) {                                           // out_mlps run on the G pooled rows (rows >= G are zero)
+#pragma unroll
+        for (int i = 0; i < 128; i += 4) {
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m < G) t = *reinterpret_cast<const float4*>(sPool + m * 128 + i);
+          v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+        }
       }
-      pntc::chunk_mma(p, a, false);
     }
-  }
-  pntc::read_acc(p, W + pw::MLP0_B, v);
-  pntc::ln_relu(v, W + pw::MLP0_G, W + pw::MLP0_BB);
-  pntc::gemm_rows<128>(p, v);
-  pntc::read_acc(p, W + pw::MLP1_B, v);
-  relu_mask();
-  __syncthreads();        // every thread has read its pooled row of the first pooling
-  pool();
-  // ---- out_mlps on the G pooled rows (rows >= G are zero)
+#pragma unroll 1
+    for (int half = 0; half < (st == 2 ? 2 : 1); ++half) {
+      if (half == 1) {                                         // the pooled half of mlps.0's input
 #pragma unroll
-  for (int i = 0; i < 128; i += 4) {
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (m < G) t = *reinterpret_cast<const float4*>(sPool + m * 128 + i);
-    v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
-  }
-  pntc::gemm_rows<128>(p, v);
-  pntc::read_acc(p, W + pw::OUT0_B, v);
+        for (int i = 0; i < 128; i += 4) {
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (g < G) t = *reinterpret_cast<const float4*>(sPool + g * 128 + i);
+          v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+        }
+      }
 #pragma unroll
-  for (int i = 0; i < 128; ++i) v[i] = m < G ? fmaxf(v[i], 0.f) : 0.f;
-  pntc::gemm_rows<128>(p, v);
-  pntc::read_acc(p, W + pw::OUT1_B, v);
+      for (int c = 0; c < 4; ++c) {
+        float a[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a[i] = v[c * 32 + i];
+        pntc::chunk_mma(p, a, half == 0 && c == 0);
+      }
+    }
+    const int bo = st == 0 ? pw::PRE1_B : st == 1 ? pw::PRE2_B : st == 2 ? pw::MLP0_B : st == 3 ? pw::MLP1_B
+                 : st == 4 ? pw::OUT0_B : pw::OUT1_B;
+    pntc::read_acc(p, W + bo, v);
+  }
   if (m < G && poly0 + m < n_poly) {
     int any = 0;
     for (int q = 0; q < P; ++q) any |= sValid[m * P + q];

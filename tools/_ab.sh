@@ -1,9 +1,8 @@
 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python tools/kernel_breakdown.py 2>&1 | tail -3 > gpurun_out/breakdown_sw.txt
+python tools/kernel_breakdown.py 2>&1 | tail -3 > gpurun_out/breakdown_loop.txt
 python - <<PY
 import json
-for l in open("gpurun_out/breakdown_sw.txt"):
+for l in open("gpurun_out/breakdown_loop.txt"):
     if l.startswith("{\"forward_ms\""):
-        d=json.loads(l); print(round(d["forward_ms"],2), "edge", d["attn_edge"], "post", d["attn_post"])
+        d=json.loads(l); print(round(d["forward_ms"],2), "pointnet", d["pointnet"], "kv", d["attn_kv"])
 PY
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
