@@ -47,8 +47,10 @@ typedef struct {
 } prosim_stack_side_t;
 
 int prosim_abi_version(void);
-/* Node-side GEMMs of the AttentionLayer: 1 (default) = tcgen05 / TMEM 3xTF32 kernel (csrc/tc_post.cuh) for launches
- * of >= 1024 rows, 0 = fp32 FFMA kernels everywhere (A/B measurement and parity cross-checks). */
+/* Tensor-core kernels: 1 (default) = tcgen05 / TMEM 3xTF32 for the node-side GEMMs of the AttentionLayer (csrc/tc_post.cuh,
+ * launches of >= 1024 rows), the K'|V' projections (csrc/kv_tc.cuh) and the PointNet encoders (csrc/pointnet_tc.cuh);
+ * 0 = fp32 FFMA kernels everywhere (A/B measurement and parity cross-checks).  Other values select kernels by bit
+ * (1 node kernel, 2 K'|V', 4 PointNet) for fault isolation. */
 int prosim_set_tensor_core(int on);
 /* prosim_attn_stack_fwd with fixed sources on both sides runs as up to `parts` (1..4, default 1) independent row chains of
  * >= 1024 rows on internal side streams (forked from / joined to the caller's stream with events; capturable in a CUDA

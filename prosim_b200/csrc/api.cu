@@ -24,6 +24,7 @@ namespace {
 
 int g_split = 1;        // row-split chains of prosim_attn_stack_fwd (prosim_set_stack_split); measured 31.4 / 30.9 / 30.6 / 31.4 ms at 1..4 parts
 bool g_use_tc = true;   // node-side GEMMs on tcgen05 (tc_post.cuh); prosim_set_tensor_core(0) selects the FFMA kernels
+int g_tc_mask = 7;      // bit 0: node kernel, bit 1: K'|V', bit 2: PointNet (prosim_set_tensor_core(mask), A/B and fault isolation)
 constexpr int ERR_ARG = -1;
 constexpr int ERR_WORKSPACE = -2;
 
@@ -155,7 +156,7 @@ int launch_kv(const float* x, int n, const float* w, size_t wstride, int layers,
   const int rpt = pick_rpt(n * layers);
   LaunchScope ls(PROSIM_K_ATTN_KV, st);
   const int rt = pick_rt(n);
-  if (g_use_tc) {   // tcgen05 / TMEM 3xTF32 (kv_tc.cuh) for every launch size: a row's K'|V' never depends on the batch it is in
+  if (g_tc_mask & 2) {   // tcgen05 / TMEM 3xTF32 (kv_tc.cuh) for every launch size: a row's K'|V' never depends on the batch it is in
     if (int e = setup_attributes()) return e;
     attn_kv_tc_kernel<<<dim3((n + 127) / 128, layers), 128, kvtc::SMEM_BYTES, st>>>(x, n, w, wstride, kv, kvstride);
     PROSIM_CHECK_LAUNCH();
@@ -310,7 +311,7 @@ int launch_post(const float* x, int n, int zd, const float* rbar, const float* a
   if (n <= 0) return 0;
   const int rpt = pick_rpt(n);
   LaunchScope ls(PROSIM_K_ATTN_POST, st);
-  if (pick_rt(n) != 0 && g_use_tc) {
+  if (pick_rt(n) != 0 && (g_tc_mask & 1)) {
     alignas(64) tcp::Maps m;
     const bool nx = w_next != nullptr;
     int e = 0;
@@ -351,6 +352,7 @@ int prosim_set_stack_split(int parts) {
 }
 int prosim_set_tensor_core(int on) {
   g_use_tc = on != 0;
+  g_tc_mask = on == 1 ? 7 : (on & 7);    // 1 = everything (the default); other values select kernels by bit
   return 0;
 }
 
@@ -404,7 +406,7 @@ int prosim_pointnet_fwd(int kind, const float* x, const uint8_t* mask, const int
   if (!x || (!mask && kind < 2) || !rows || !w || !out) return ERR_ARG;
   if (int e = setup_attributes()) return e;
   LaunchScope ls(PROSIM_K_POINTNET, S(stream));
-  if (w_tc != nullptr && g_use_tc) {   // tcgen05 / TMEM 3xTF32 kernel (pointnet_tc.cuh)
+  if (w_tc != nullptr && (g_tc_mask & 4)) {   // tcgen05 / TMEM 3xTF32 kernel (pointnet_tc.cuh)
     if ((reinterpret_cast<uintptr_t>(w_tc) & 15) != 0) return ERR_ARG;
     if (kind == 0)
       pointnet_tc_kernel<24, 1, 11><<<(n_poly + pntc::Cfg<11>::G - 1) / pntc::Cfg<11>::G, 128, pntc::Cfg<11>::smem_bytes, S(stream)>>>(

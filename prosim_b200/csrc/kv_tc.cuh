@@ -63,8 +63,6 @@ __global__ void __launch_bounds__(128, 2) attn_kv_tc_kernel(const float* __restr
     const float4 t = *reinterpret_cast<const float4*>(tile + m * kvtc::TILE_LD + i);
     v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
   }
-  __syncthreads();                       // the tile is about to become operand buffers again
-  if (m == 0) pntc::load_b(p, 0);
   {   // LN_src with affine, thread local
     float s = 0.f;
 #pragma unroll
@@ -87,6 +85,14 @@ __global__ void __launch_bounds__(128, 2) attn_kv_tc_kernel(const float* __restr
       v[i + 3] = (v[i + 3] - mean) * rstd * g.w + b.w;
     }
   }
+  // The tile is about to become operand buffers again, and the first weight chunk is written into it by the bulk-copy
+  // engine (async proxy).  A barrier alone does not order another thread's still-pending shared-memory LOADS before that
+  // write: with the copy issued right after the row reads, ~1 % of the launches returned a few corrupted rows 62..127 (the
+  // part of the tile under weight stage 0).  The LayerNorm above has consumed every loaded value; the proxy fence orders
+  // this thread's generic accesses before the async ones that follow the barrier.
+  tc::fence_async_smem();
+  __syncthreads();
+  if (m == 0) pntc::load_b(p, 0);
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     float a[32];

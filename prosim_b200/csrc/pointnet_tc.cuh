@@ -30,13 +30,14 @@ namespace pntc {
 constexpr int KC = 32;                         // K per chunk
 constexpr int A_BYTES = 128 * KC * 4;          // one of hi / lo: 16 KB
 constexpr int B_STAGE_BYTES = 2 * 128 * KC * 4;   // hi | lo: 32 KB
+constexpr int N_VEC = 13;                      // per-column vectors (biases, LayerNorm affine) staged in shared memory
 constexpr int POOL_LD = 33;                    // pooling scratch [128 rows][32 + 1] floats inside the A buffers
 
 template <int P>
 struct Cfg {
   static constexpr int G = 128 / P;
   static constexpr int GP = (G + 3) & ~3;
-  static constexpr size_t smem_bytes = 1024 + 2 * A_BYTES + 2 * B_STAGE_BYTES + (size_t)GP * 128 * 4 + 128 * 4 + 64;
+  static constexpr size_t smem_bytes = 1024 + 2 * A_BYTES + 2 * B_STAGE_BYTES + (size_t)GP * 128 * 4 + 128 * 4 + 64 + N_VEC * 512;
 };
 
 // chunks of the packed tensor-core weight block (weights.py::pack_pointnet_tc), in consumption order
@@ -137,7 +138,7 @@ __device__ __forceinline__ void read_acc(Pipe& p, const float* __restrict__ bias
     tc::tmem_ld32(lane_base + acc_col + c0, t);
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + i));
+      const float4 b = *reinterpret_cast<const float4*>(bias + c0 + i);    // global or shared
       v[c0 + i] = t[i] + b.x; v[c0 + i + 1] = t[i + 1] + b.y; v[c0 + i + 2] = t[i + 2] + b.z; v[c0 + i + 3] = t[i + 3] + b.w;
     }
   }
@@ -158,7 +159,7 @@ __device__ __forceinline__ void ln_relu(float (&v)[128], const float* __restrict
   const float rstd = 1.0f / sqrtf(q * (1.0f / 128.0f) + LN_EPS);
 #pragma unroll
   for (int i = 0; i < 128; i += 4) {
-    const float4 gg = __ldg(reinterpret_cast<const float4*>(g + i)), bb = __ldg(reinterpret_cast<const float4*>(b + i));
+    const float4 gg = *reinterpret_cast<const float4*>(g + i), bb = *reinterpret_cast<const float4*>(b + i);
     v[i] = fmaxf((v[i] - mean) * rstd * gg.x + bb.x, 0.f);
     v[i + 1] = fmaxf((v[i + 1] - mean) * rstd * gg.y + bb.y, 0.f);
     v[i + 2] = fmaxf((v[i + 2] - mean) * rstd * gg.z + bb.z, 0.f);
@@ -198,6 +199,7 @@ __global__ void __launch_bounds__(128, 2) pointnet_tc_kernel(const float* __rest
   int* sValid = reinterpret_cast<int*>(sPool + C::GP * 128);                 // [128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sValid + 128);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  float* sVec = reinterpret_cast<float*>(bars + 8);                         // [N_VEC][128]
   p.bfull = bars;
   p.bmma = bars + 2;
   p.wtc = Wtc;
@@ -236,6 +238,12 @@ __global__ void __launch_bounds__(128, 2) pointnet_tc_kernel(const float* __rest
     }
   }
   sValid[m] = valid;
+  {   // per-column vectors -> shared memory (every thread reads all of them, many times)
+    constexpr int src[pntc::N_VEC] = {pw::PRE0_B, pw::PRE0_G, pw::PRE0_BB, pw::PRE1_B, pw::PRE1_G, pw::PRE1_BB, pw::PRE2_B,
+                                      pw::MLP0_B, pw::MLP0_G, pw::MLP0_BB, pw::MLP1_B, pw::OUT0_B, pw::OUT1_B};
+#pragma unroll
+    for (int k = 0; k < pntc::N_VEC; ++k) sVec[k * 128 + m] = __ldg(W + src[k] + m);
+  }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -275,12 +283,12 @@ __global__ void __launch_bounds__(128, 2) pointnet_tc_kernel(const float* __rest
   //   stage 4: ReLU+mask, max-pool, pooled rows to threads 0..G-1 -> out_mlps.0
   //   stage 5: ReLU -> out_mlps.1
   pntc::chunk_mma(p, x, true);
-  pntc::read_acc(p, W + pw::PRE0_B, v);
+  pntc::read_acc(p, sVec, v);
 #pragma unroll 1
   for (int st = (NPRE == 3 ? 0 : 2); st < 6; ++st) {
     if (st == 0 || st == 1 || st == 3) {
-      const int go = st == 0 ? pw::PRE0_G : st == 1 ? pw::PRE1_G : pw::MLP0_G;
-      pntc::ln_relu(v, W + go, W + go + 128);                  // gamma and beta are adjacent in the pw:: block
+      const int go = st == 0 ? 1 : st == 1 ? 4 : 8;            // sVec rows: gamma, then beta
+      pntc::ln_relu(v, sVec + go * 128, sVec + (go + 1) * 128);
     } else if (st == 5) {
 #pragma unroll
       for (int i = 0; i < 128; ++i) v[i] = m < G ? fmaxf(v[i], 0.f) : 0.f;
@@ -315,9 +323,8 @@ __global__ void __launch_bounds__(128, 2) pointnet_tc_kernel(const float* __rest
         pntc::chunk_mma(p, a, half == 0 && c == 0);
       }
     }
-    const int bo = st == 0 ? pw::PRE1_B : st == 1 ? pw::PRE2_B : st == 2 ? pw::MLP0_B : st == 3 ? pw::MLP1_B
-                 : st == 4 ? pw::OUT0_B : pw::OUT1_B;
-    pntc::read_acc(p, W + bo, v);
+    const int bo = st == 0 ? 3 : st == 1 ? 6 : st == 2 ? 7 : st == 3 ? 10 : st == 4 ? 11 : 12;   // sVec row of the bias
+    pntc::read_acc(p, sVec + bo * 128, v);
   }
   if (m < G && poly0 + m < n_poly) {
     int any = 0;

@@ -259,6 +259,33 @@ def _attention_stack_case(ctx, tol12, tol3):
     assert (out - ref).abs().max() < tol3
 
 
+def test_tensor_core_chunk_pipeline_is_race_free(ctx):
+    """The tcgen05 PointNet / K'|V' kernels reuse shared memory between generic-proxy tiles and async-proxy (bulk copy,
+    MMA) operands.  A first version of attn_kv_tc_kernel issued a weight copy over rows other threads were still loading:
+    ~1 % of the launches returned a few corrupted rows.  Repeat both kernels a few hundred times: every result must be
+    bit-identical to the first."""
+    ops, ar, off = ctx['ops'], ctx['arena'], ctx['off']
+    g = torch.Generator().manual_seed(29)
+    x_m = torch.randn(8150, 128, generator=g).cuda()
+    ref = None
+    for _ in range(400):
+        kv = ops.attn_kv(x_m, ar, off['pol_m2p'], 6, weights.ATTN_LAYER_FLOATS)
+        if ref is None:
+            ref = kv.clone()
+        else:
+            assert torch.equal(kv, ref)
+    x = torch.randn(1200, 11, 24, generator=g).cuda()
+    mask = (torch.rand(1200, 11, 1, generator=g) > 0.2).expand(1200, 11, 24).contiguous().cuda()
+    rows = torch.arange(1200, dtype=torch.int32).cuda()
+    ref = None
+    for _ in range(200):
+        out = ops.pointnet(0, x, mask, rows, ar, off['obs_enc'], tc_off=off['obs_enc_tc'])
+        if ref is None:
+            ref = out.clone()
+        else:
+            assert torch.equal(out, ref)
+
+
 # ------------------------------------------------------------------------------------ heads
 def test_policy_head_and_reconst_match_oracle(ctx):
     ops, orc = ctx['ops'], ctx['oracle']
