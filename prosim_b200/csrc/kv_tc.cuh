@@ -13,7 +13,7 @@
 namespace prosim {
 namespace kvtc {
 constexpr int TILE_LD = 132;
-constexpr size_t SMEM_BYTES = 1024 + 2 * pntc::A_BYTES + 2 * pntc::B_STAGE_BYTES + 64;
+constexpr size_t SMEM_BYTES = 1024 + 2 * pntc::A_BYTES + 2 * pntc::B_STAGE_BYTES + 64 + 4 * 512;
 static_assert(2 * pntc::A_BYTES + 2 * pntc::B_STAGE_BYTES >= 128 * TILE_LD * 4, "row tile aliases the operand buffers");
 }  // namespace kvtc
 
@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(128, 2) attn_kv_tc_kernel(const float* __restr
   p.sB = base + 2 * pntc::A_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(p.sB + 2 * pntc::B_STAGE_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  float* sVec = reinterpret_cast<float*>(bars + 8);    // LN_src gamma, beta, K' bias, V' bias: read by every thread
   p.bfull = bars;
   p.bmma = bars + 2;
   p.wtc = W + aw::TC_KV;
@@ -46,6 +47,10 @@ __global__ void __launch_bounds__(128, 2) attn_kv_tc_kernel(const float* __restr
     tc::mbar_init(p.bmma, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
+  sVec[m] = __ldg(W + aw::LN_SRC_G + m);
+  sVec[128 + m] = __ldg(W + aw::LN_SRC_B + m);
+  sVec[256 + m] = __ldg(W + aw::KB + m);
+  sVec[384 + m] = __ldg(W + aw::VB + m);
   // rows -> tile (coalesced float4), then each thread takes its own row
   for (int i = m; i < 128 * 32; i += 128) {
     const int r = i >> 5, c4 = i & 31;
@@ -77,8 +82,8 @@ __global__ void __launch_bounds__(128, 2) attn_kv_tc_kernel(const float* __restr
     const float rstd = 1.0f / sqrtf(q * (1.0f / 128.0f) + LN_EPS);
 #pragma unroll
     for (int i = 0; i < 128; i += 4) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(W + aw::LN_SRC_G + i));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(W + aw::LN_SRC_B + i));
+      const float4 g = *reinterpret_cast<const float4*>(sVec + i);
+      const float4 b = *reinterpret_cast<const float4*>(sVec + 128 + i);
       v[i] = (v[i] - mean) * rstd * g.x + b.x;
       v[i + 1] = (v[i + 1] - mean) * rstd * g.y + b.y;
       v[i + 2] = (v[i + 2] - mean) * rstd * g.z + b.z;
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(128, 2) attn_kv_tc_kernel(const float* __restr
   // accumulators -> tile -> global, one 128-column half at a time
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
-    pntc::read_acc(p, W + (half == 0 ? aw::KB : aw::VB), v, half * 128);
+    pntc::read_acc(p, sVec + 256 + half * 128, v, half * 128);
     if (half == 1) __syncthreads();      // the first half has left the tile
 #pragma unroll
     for (int i = 0; i < 128; i += 4)
