@@ -158,7 +158,7 @@ int launch_kv(const float* x, int n, const float* w, size_t wstride, int layers,
   const int rt = pick_rt(n);
   if (g_tc_mask & 2) {   // tcgen05 / TMEM 3xTF32 (kv_tc.cuh) for every launch size: a row's K'|V' never depends on the batch it is in
     if (int e = setup_attributes()) return e;
-    attn_kv_tc_kernel<<<dim3((n + 127) / 128, layers), 128, kvtc::SMEM_BYTES, st>>>(x, n, w, wstride, kv, kvstride);
+    attn_kv_tc_kernel<<<dim3((n + 127) / 128, layers, 2), 128, kvtc::SMEM_BYTES, st>>>(x, n, w, wstride, kv, kvstride);
     PROSIM_CHECK_LAUNCH();
     return 0;
   }

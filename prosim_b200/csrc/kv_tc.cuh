@@ -3,9 +3,8 @@
 // Same math as attn_kv2_kernel (attn2.cuh; reference prosim/models/layers/attention_layer.py:67-72 with the folds of
 // weights_layout.h):  K' = Wk LN_src(x) + Wkr beta_r,  V' = Wv LN_src(x) + b_v + Wvr beta_r + b_vr.
 // One CTA (128 threads, thread = source row = TMEM lane) per 128 rows and layer, built on the chunk pipeline of
-// pointnet_tc.cuh: the row's LayerNorm is thread local, every K = 32 chunk of LN(x) is staged once per product and
-// multiplied into two accumulators (K' at TMEM columns 0..127, V' at 128..255) by weight chunks that arrive
-// interleaved [Wk c0, Wv c0, Wk c1, ...] (aw::TC_KV).  Rows enter and leave through a padded shared-memory tile so that
+// pointnet_tc.cuh: the row's LayerNorm is thread local; K' and V' are separate CTAs (blockIdx.z) that take every second
+// chunk of the interleaved weight block [Wk c0, Wv c0, Wk c1, ...] (aw::TC_KV).  Rows enter and leave through a padded shared-memory tile so that
 // global accesses are whole 512-byte rows.
 #pragma once
 #include "pointnet_tc.cuh"
@@ -33,14 +32,18 @@ __global__ void __launch_bounds__(128, 2) attn_kv_tc_kernel(const float* __restr
   float* sVec = reinterpret_cast<float*>(bars + 8);    // LN_src gamma, beta, K' bias, V' bias: read by every thread
   p.bfull = bars;
   p.bmma = bars + 2;
+  const int half = blockIdx.z;            // 0: K' (kv columns 0..127), 1: V' (128..255) -- one CTA each: twice the CTAs,
+                                          // half the serial chain (a 4096-row x 6-layer launch is 192 tiles on 296 CTA slots)
   p.wtc = W + aw::TC_KV;
+  p.wmul = 2;
+  p.woff = half;
   p.chunk = 0;
-  p.total = 8;
+  p.total = 4;
   float* tile = reinterpret_cast<float*>(base);     // [128][132] fp32 over the (idle) operand buffers
   const int m = threadIdx.x, warp = m >> 5;
   const int row0 = blockIdx.x * 128;
 
-  if (warp == 0) tc::tmem_alloc(tmem_slot, 256);
+  if (warp == 0) tc::tmem_alloc(tmem_slot, 128);
   if (m == 32) {
     tc::mbar_init(&p.bfull[0], 1);
     tc::mbar_init(&p.bfull[1], 1);
@@ -103,28 +106,23 @@ __global__ void __launch_bounds__(128, 2) attn_kv_tc_kernel(const float* __restr
     float a[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) a[i] = v[c * 32 + i];
-    pntc::chunk_mma(p, a, c == 0, 0);      // K' += LN(x)[:, 32c..] . Wk chunk c
-    pntc::chunk_mma(p, a, c == 0, 128);    // V' += LN(x)[:, 32c..] . Wv chunk c
+    pntc::chunk_mma(p, a, c == 0);
   }
-  // accumulators -> tile -> global, one 128-column half at a time
-#pragma unroll 1
-  for (int half = 0; half < 2; ++half) {
-    pntc::read_acc(p, sVec + 256 + half * 128, v, half * 128);
-    if (half == 1) __syncthreads();      // the first half has left the tile
+  // accumulator -> tile -> global
+  pntc::read_acc(p, sVec + 256 + half * 128, v);
 #pragma unroll
-    for (int i = 0; i < 128; i += 4)
-      *reinterpret_cast<float4*>(tile + m * kvtc::TILE_LD + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-    __syncthreads();
-    for (int i = m; i < 128 * 32; i += 128) {
-      const int r = i >> 5, c4 = i & 31;
-      if (row0 + r < N)
-        *(reinterpret_cast<float4*>(kv + (size_t)(row0 + r) * 256 + half * 128) + c4) =
-            *reinterpret_cast<const float4*>(tile + r * kvtc::TILE_LD + 4 * c4);
-    }
+  for (int i = 0; i < 128; i += 4)
+    *reinterpret_cast<float4*>(tile + m * kvtc::TILE_LD + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  __syncthreads();
+  for (int i = m; i < 128 * 32; i += 128) {
+    const int r = i >> 5, c4 = i & 31;
+    if (row0 + r < N)
+      *(reinterpret_cast<float4*>(kv + (size_t)(row0 + r) * 256 + half * 128) + c4) =
+          *reinterpret_cast<const float4*>(tile + r * kvtc::TILE_LD + 4 * c4);
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(p.tmem, 256);
+  if (warp == 0) tc::tmem_dealloc(p.tmem, 128);
 }
 
 }  // namespace prosim

@@ -71,6 +71,7 @@ struct Pipe {
   uint64_t* bfull;        // [2]
   uint64_t* bmma;         // [1]
   const float* wtc;       // packed chunks
+  int wmul, woff;         // chunk c of this CTA is packed chunk c * wmul + woff (kv_tc.cuh: K' and V' chunks interleaved)
   uint32_t tmem;
   int chunk;              // chunks consumed so far (stage = chunk & 1, B parity = (chunk >> 1) & 1, MMA parity = chunk & 1)
   int total;
@@ -81,7 +82,8 @@ __device__ __forceinline__ void load_b(const Pipe& p, int c) {
   if (c < p.total) {
     const uint32_t fb = e4::smem_u32(&p.bfull[c & 1]);
     e4::mbar_expect_tx(fb, B_STAGE_BYTES);
-    e4::bulk_copy(e4::smem_u32(p.sB + (c & 1) * B_STAGE_BYTES), p.wtc + (size_t)c * (B_STAGE_BYTES / 4), B_STAGE_BYTES, fb);
+    e4::bulk_copy(e4::smem_u32(p.sB + (c & 1) * B_STAGE_BYTES), p.wtc + (size_t)(c * p.wmul + p.woff) * (B_STAGE_BYTES / 4),
+                  B_STAGE_BYTES, fb);
   }
 }
 
@@ -203,6 +205,8 @@ __global__ void __launch_bounds__(128, 2) pointnet_tc_kernel(const float* __rest
   p.bfull = bars;
   p.bmma = bars + 2;
   p.wtc = Wtc;
+  p.wmul = 1;
+  p.woff = 0;
   p.chunk = 0;
   p.total = pntc::n_chunks<NPRE>();
   float* sScr = reinterpret_cast<float*>(base);       // pooling scratch [128][33] floats = 16.9 KB over the (idle) A buffers
