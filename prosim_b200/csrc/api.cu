@@ -102,6 +102,7 @@ int setup_attributes() {
   acc(allow_smem(pointnet_kernel<2, 4, 1, 16>, PointNetCfg<16>::smem_bytes));
   acc(allow_smem(pointnet_kernel<2, 4, 1, 8>, PointNetCfg<8>::smem_bytes));
   acc(allow_smem(attn_kv_tc_kernel, kvtc::SMEM_BYTES));
+  acc(allow_smem(policy_head2_kernel<2>, Head2Smem<2>::bytes));
   acc(allow_smem(pointnet_tc_kernel<24, 1, 11>, pntc::Cfg<11>::smem_bytes));
   acc(allow_smem(pointnet_tc_kernel<11, 3, 19>, pntc::Cfg<19>::smem_bytes));
   acc(allow_smem(pointnet_tc_kernel<2, 1, 16>, pntc::Cfg<16>::smem_bytes));
@@ -653,6 +654,13 @@ int prosim_policy_head_fwd(const float* feat, const int32_t* agent_type, int P, 
   if (!feat || !agent_type || !w || !motion_pred) return ERR_ARG;
   const int rpt = pick_rpt(P);
   LaunchScope ls(PROSIM_K_HEAD, S(stream));
+  if (pick_rt(P) != 0) {   // >= 1024 rows: weights through the shared-memory stream (bit-identical to the kernel below)
+    if (int e = setup_attributes()) return e;
+    policy_head2_kernel<2><<<(P + 15) / 16, 256, Head2Smem<2>::bytes, S(stream)>>>(feat, agent_type, P, w, noise, noise_std,
+                                                                             motion_pred);
+    PROSIM_CHECK_LAUNCH();
+    return 0;
+  }
   DISPATCH_RPT(rpt, policy_head_kernel<RPT><<<(P + 2 * RPT - 1) / (2 * RPT), 256, 0, S(stream)>>>(feat, agent_type, P, w, noise, noise_std, motion_pred));
   PROSIM_CHECK_LAUNCH();
   return 0;

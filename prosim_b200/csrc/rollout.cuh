@@ -8,6 +8,7 @@
 // T = 11 + rollout steps, preallocated once (the reference grows them with torch.cat every tick).
 #pragma once
 #include "common.cuh"
+#include "gemm_tile.cuh"
 #include "weights_layout.h"
 
 namespace prosim {
@@ -223,6 +224,110 @@ __global__ void __launch_bounds__(256) policy_head_kernel(const float* __restric
     float* o = motion_pred + (size_t)(row0 + threadIdx.x) * STEP * 5;
     // RANDOM_NOISE_STD > 0 (act_decoder.py:113-115): standard-normal draws [P][10][2] scaled by std are added to the
     // per-step displacements before the cumulative sum (a product then a sum in the reference: no fused multiply-add)
+    const float* nz = noise ? noise + (size_t)(row0 + threadIdx.x) * STEP * 2 : nullptr;
+    float cx = 0.f, cy = 0.f, ch = 0.f;
+    for (int i = 0; i < STEP; ++i) {
+      float dx = m[i * 5 + 0], dy = m[i * 5 + 1];
+      if (nz) {
+        dx = __fadd_rn(dx, __fmul_rn(nz[i * 2 + 0], noise_std));
+        dy = __fadd_rn(dy, __fmul_rn(nz[i * 2 + 1], noise_std));
+      }
+      cx += dx;
+      cy += dy;
+      ch += m[i * 5 + 2];
+      o[i * 5 + 0] = cx;
+      o[i * 5 + 1] = cy;
+      o[i * 5 + 2] = wrap_angle(ch);
+      o[i * 5 + 3] = m[i * 5 + 3];
+      o[i * 5 + 4] = m[i * 5 + 4];
+    }
+  }
+}
+
+// Throughput variant of policy_head_kernel for launches of >= 1024 rows: the six GEMMs go through the shared-memory weight
+// stream of gemm_tile.cuh (gemm2 / WPipe: a weight element is fetched once per CTA, two chunks ahead, across GEMM
+// boundaries) instead of per-thread LDG.  Same summation order per output (ascending k): bit-identical to policy_head_kernel.
+template <int TR>
+struct Head2Smem {
+  static constexpr int M = 8 * TR;
+  static constexpr size_t bytes = WPIPE_BYTES + 3 * (size_t)M * LDS_PAD * sizeof(float);
+};
+
+template <int TR>
+__global__ void __launch_bounds__(256) policy_head2_kernel(const float* __restrict__ feat, const int* __restrict__ a_type,
+                                                           int P, const float* __restrict__ W,
+                                                           const float* __restrict__ noise, float noise_std,
+                                                           float* __restrict__ motion_pred) {
+  constexpr int NW = 8, M = NW * TR;
+  extern __shared__ __align__(16) float smem[];
+  WPipe p = wpipe_init<NW>(smem, [&](WSeg* sg) {
+    for (int i = 0; i < 3; ++i) sg[i] = WSeg{W + hw::CG_W + i * hw::CG_STRIDE, D, D};
+    sg[3] = WSeg{W + hw::MH0_W, D, D};
+    sg[4] = WSeg{W + hw::MH1_W, D, D};
+    sg[5] = WSeg{W + hw::MH2_W, D, 64};
+    return 6;
+  });
+  float* sS = smem + WPIPE_BYTES / sizeof(float);
+  float* sA = sS + M * LDS_PAD;
+  float* sB = sA + M * LDS_PAD;
+  const int row0 = blockIdx.x * M;
+  for (int i = threadIdx.x; i < M * D; i += 256) {
+    const int r = i >> 7, c = i & 127;
+    int t = row0 + r < P ? a_type[row0 + r] - 1 : 0;
+    t = min(max(t, 0), 2);
+    sA[r * LDS_PAD + c] = __ldg(W + hw::ANCHOR + t * D + c);
+  }
+  __syncthreads();
+  const TileCoord tc = tile_coord<TR>();
+  float acc[TR][4];
+#pragma unroll 1
+  for (int i = 0; i < 3; ++i) {
+    const float* Wc = W + hw::CG_W + i * hw::CG_STRIDE;
+    acc2_init_bias<TR>(acc, Wc + 16384);
+    gemm2<TR, NW>(acc, i == 0 ? sA : sS, LDS_PAD, p);
+    acc2_store_smem<TR>(acc, sB, LDS_PAD, false);
+    __syncthreads();
+    ln_tile_inplace<D>(sB, LDS_PAD, M, Wc + 16384 + 128, Wc + 16384 + 256, true);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < TR; ++r) {
+      const int lr = tc.row + r, row = row0 + lr;
+      const float4 y = *reinterpret_cast<const float4*>(sB + lr * LDS_PAD + tc.col);
+      float4 sv;
+      if (i == 0) {
+        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < P) f = *reinterpret_cast<const float4*>(feat + (size_t)row * D + tc.col);
+        sv = make_float4(y.x * f.x, y.y * f.y, y.z * f.z, y.w * f.w);
+      } else {
+        const float4 so = *reinterpret_cast<const float4*>(sS + lr * LDS_PAD + tc.col);
+        const float fi = (float)i, fd = (float)(i + 1);
+        sv = make_float4((so.x * fi + y.x * so.x) / fd, (so.y * fi + y.y * so.y) / fd, (so.z * fi + y.z * so.z) / fd,
+                         (so.w * fi + y.w * so.w) / fd);
+      }
+      *reinterpret_cast<float4*>(sS + lr * LDS_PAD + tc.col) = sv;
+    }
+    __syncthreads();
+  }
+  // motion_head: Linear+LN+ReLU (128), Linear+LN+ReLU (64 real columns), Linear (50 real columns)
+  acc2_init_bias<TR>(acc, W + hw::MH0_B);
+  gemm2<TR, NW>(acc, sS, LDS_PAD, p);
+  acc2_store_smem<TR>(acc, sA, LDS_PAD, false);
+  __syncthreads();
+  ln_tile_inplace<D>(sA, LDS_PAD, M, W + hw::MH0_G, W + hw::MH0_BB, true);
+  __syncthreads();
+  acc2_init_bias<TR>(acc, W + hw::MH1_B);
+  gemm2<TR, NW>(acc, sA, LDS_PAD, p);
+  acc2_store_smem<TR>(acc, sS, LDS_PAD, false);
+  __syncthreads();
+  ln_tile_inplace<64>(sS, LDS_PAD, M, W + hw::MH1_G, W + hw::MH1_BB, true);
+  __syncthreads();
+  acc2_init_bias<TR>(acc, W + hw::MH2_B);
+  gemm2<TR, NW>(acc, sS, LDS_PAD, p);
+  acc2_store_smem<TR>(acc, sB, LDS_PAD, false);
+  __syncthreads();
+  if (threadIdx.x < M && row0 + threadIdx.x < P) {
+    const float* m = sB + threadIdx.x * LDS_PAD;
+    float* o = motion_pred + (size_t)(row0 + threadIdx.x) * STEP * 5;
     const float* nz = noise ? noise + (size_t)(row0 + threadIdx.x) * STEP * 2 : nullptr;
     float cx = 0.f, cy = 0.f, ch = 0.f;
     for (int i = 0; i < STEP; ++i) {
