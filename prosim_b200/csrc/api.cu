@@ -14,6 +14,7 @@
 #include "rollout.cuh"
 #include "tc_gemm.cuh"
 #include "tc_post.cuh"
+#include "post_sw.cuh"
 #include "weights_layout.h"
 
 #include <cudaTypedefs.h>
@@ -24,7 +25,9 @@ namespace {
 
 int g_split = 1;        // row-split chains of prosim_attn_stack_fwd (prosim_set_stack_split); measured 31.4 / 30.9 / 30.6 / 31.4 ms at 1..4 parts
 bool g_use_tc = true;   // node-side GEMMs on tcgen05 (tc_post.cuh); prosim_set_tensor_core(0) selects the FFMA kernels
-int g_tc_mask = 7;      // bit 0: node kernel, bit 1: K'|V', bit 2: PointNet (prosim_set_tensor_core(mask), A/B and fault isolation)
+int g_tc_mask = 15;     // bit 0: node kernel, bit 1: K'|V', bit 2: PointNet, bit 3: the 32-row "swapped" node kernel (post_sw.cuh) for
+                        // launches it fills the chip with (prosim_set_tensor_core(mask), A/B and fault isolation)
+constexpr int SW_MAX_ROWS = 148 * 32 * 2;   // above two waves of 32-row CTAs the 128-row kernel streams 4x less weight per row
 constexpr int ERR_ARG = -1;
 constexpr int ERR_WORKSPACE = -2;
 
@@ -114,6 +117,8 @@ int setup_attributes() {
   acc(allow_smem(attn_dstpre2_kernel<8, 8>, Pre2Smem<8, 8>::bytes));
   acc(allow_smem(attn_post2_kernel<4, 8>, Post2Smem<4, 8>::bytes));
   acc(allow_smem(tcp::attn_post_tc_kernel, tcp::SMEM_BYTES));
+  acc(allow_smem(psw::attn_post_sw_kernel<96>, psw::SMEM_BYTES));
+  acc(allow_smem(psw::attn_post_sw_kernel<128>, psw::SMEM_BYTES));
   state = e == cudaSuccess ? 1 : (int)e + 1000;
   return e == cudaSuccess ? 0 : (int)e;
 }
@@ -312,6 +317,17 @@ int launch_post(const float* x, int n, int zd, const float* rbar, const float* a
   if (n <= 0) return 0;
   const int rpt = pick_rpt(n);
   LaunchScope ls(PROSIM_K_ATTN_POST, st);
+  if (pick_rt(n) != 0 && (g_tc_mask & 1) && (g_tc_mask & 8) && n <= SW_MAX_ROWS && (zd == 96 || zd == 128)) {
+    psw::Args a;
+    a.x = x; a.rbar = rbar; a.aggv = aggv; a.s = cur.s; a.gx = cur.gx; a.out = out;
+    a.q_n = nxt.q; a.qhat_n = nxt.qhat; a.s_n = nxt.s; a.gx_n = nxt.gx;
+    a.W = w; a.Wn = w_next; a.n = n;
+    const int grid = (n + psw::NR - 1) / psw::NR;
+    if (zd == 96) psw::attn_post_sw_kernel<96><<<grid, psw::THREADS, psw::SMEM_BYTES, st>>>(a);
+    else psw::attn_post_sw_kernel<128><<<grid, psw::THREADS, psw::SMEM_BYTES, st>>>(a);
+    PROSIM_CHECK_LAUNCH();
+    return 0;
+  }
   if (pick_rt(n) != 0 && (g_tc_mask & 1)) {
     alignas(64) tcp::Maps m;
     const bool nx = w_next != nullptr;
@@ -353,7 +369,7 @@ int prosim_set_stack_split(int parts) {
 }
 int prosim_set_tensor_core(int on) {
   g_use_tc = on != 0;
-  g_tc_mask = on == 1 ? 7 : (on & 7);    // 1 = everything (the default); other values select kernels by bit
+  g_tc_mask = on == 1 ? 15 : (on & 15);  // 1 = everything (the default); other values select kernels by bit
   return 0;
 }
 

@@ -56,7 +56,10 @@ constexpr int TC_S = TC_Q + 4 * 8192;
 constexpr int TC_GX = TC_S + 4 * 8192;
 constexpr int TC_KRG = TC_GX + 4 * 8192;       // 8 heads x [128 d][16 c]  (WKRG rows of the head, transposed)
 constexpr int TC_KV = TC_KRG + 8 * 4096;       // kv_tc.cuh: 4 k-chunks x ([128 n][32 k] of to_k, then of to_v), interleaved
-constexpr int SIZE = TC_KV + 8 * 8192;
+constexpr int TC_FF2 = TC_KV + 8 * 8192;       // post_sw.cuh (weights on the M side): FFN in hidden tiles of 128, 4 k-chunks [128 m][32 k] each,
+                                               //   in consumption order up_0, up_1, down_0, up_2, down_1, up_3, down_2, down_3
+                                               //   up_t = W1 rows 128t..128t+127, down_t = W2[:, 128t..128t+127]
+constexpr int SIZE = TC_FF2 + 32 * 8192;
 }  // namespace aw
 
 namespace pw {  // PointNet polyline encoder (scene_encoder/pointnet_encoder.py:13-62)

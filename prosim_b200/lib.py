@@ -138,8 +138,10 @@ def profile_read():
 
 
 def set_tensor_core(on):
-    """Node-side GEMMs of launches with >= 1024 rows: True = tcgen05 / TMEM 3xTF32 kernel (default), False = fp32 FFMA kernels."""
-    call('prosim_set_tensor_core', 1 if on else 0)
+    """Tensor-core (tcgen05 / TMEM, 3xTF32) kernels: True = all of them (the default), False = fp32 FFMA kernels, an int
+    mask selects by bit -- 1 node kernel (launches >= 1024 rows), 2 K'|V', 4 PointNet, 8 the 32-row "swapped" node kernel
+    (post_sw.cuh) where it applies (7 = the 128-row node kernel of tc_post.cuh everywhere).  PROCESS-WIDE switch."""
+    call('prosim_set_tensor_core', int(on) if not isinstance(on, bool) else (1 if on else 0))
 
 
 def set_stack_split(parts):

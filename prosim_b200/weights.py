@@ -173,7 +173,7 @@ def param_shapes_cache(goal_condition):
 # ----------------------------------------------------------------------------- packing (mirror of csrc/weights_layout.h)
 ATTN_FP32_FLOATS = 512 + 3 * (16384 + 128) + 2 * 16384 + 12288 + (16384 + 128) + (2 * 16384 + 128) + (16384 + 128) + 512 \
     + (65536 + 512) + (65536 + 128) + 256
-ATTN_TC_FLOATS = 8 * 3072 + 8 * 4096 + 2 * 4 * 8192 + 32 * 8192 + 3 * 4 * 8192 + 8 * 4096 + 8 * 8192
+ATTN_TC_FLOATS = 8 * 3072 + 8 * 4096 + 2 * 4 * 8192 + 32 * 8192 + 3 * 4 * 8192 + 8 * 4096 + 8 * 8192 + 32 * 8192
 ATTN_LAYER_FLOATS = ATTN_FP32_FLOATS + ATTN_TC_FLOATS
 POINTNET_FLOATS = (24 * 128 + 384) + (16384 + 384) + (16384 + 128) + (2 * 16384 + 384) + (16384 + 128) + 2 * (16384 + 128)
 _MLP3_FLOATS = 2 * (16384 + 384) + (64 * 128 + 128)
@@ -231,6 +231,10 @@ def _pack_attn_tc(wqt, wkrg, wvrgt, wvrg96t, wst, wgat, wgxt, wot, w1t, w2t, wkt
     out += [_umma_chunk(wkrg[h * 16:(h + 1) * 16, :].t()) for h in range(HEADS)]
     for c in range(4):                                # kv_tc.cuh: to_k and to_v chunks interleaved
         out += [_umma_chunk(wkt.t()[:, 32 * c:32 * c + 32]), _umma_chunk(wvt.t()[:, 32 * c:32 * c + 32])]
+    # post_sw.cuh: the FFN with the weights as the M-side operand, hidden tiles of 128 features, 4 k-chunks each
+    up2 = lambda t: [_umma_chunk(w1[128 * t:128 * t + 128, 32 * c:32 * c + 32]) for c in range(4)]
+    down2 = lambda t: [_umma_chunk(w2[:, 128 * t + 32 * c:128 * t + 32 * c + 32]) for c in range(4)]
+    out += up2(0) + up2(1) + down2(0) + up2(2) + down2(1) + up2(3) + down2(2) + down2(3)
     out = torch.cat(out)
     assert out.numel() == ATTN_TC_FLOATS
     return out

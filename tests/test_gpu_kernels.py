@@ -209,13 +209,14 @@ def test_attention_layer_edge_tiling(ctx, stride, n_dst):
     assert (out - ref).abs().max() < 2e-5
 
 
-@pytest.mark.parametrize('tensor_core', [True, False])
+@pytest.mark.parametrize('tensor_core', [True, 7, False])
 def test_attention_stack_matches_oracle(ctx, tensor_core):
     """6 x (a2p, m2p) with fixed sources -- the policy tick's core -- and 3 x self-source layers; with the tcgen05 node
     kernel (3xTF32, activations in TMEM) and with the FFMA node kernels."""
     from prosim_b200 import lib
     lib.set_tensor_core(tensor_core)
     try:
+        # True: the 32-row swapped tcgen05 node kernel (post_sw.cuh); 7: the 128-row one (tc_post.cuh); False: FFMA
         _attention_stack_case(ctx, 1e-4 if tensor_core else 5e-5, 4e-5 if tensor_core else 2e-5)
     finally:
         lib.set_tensor_core(True)
