@@ -70,7 +70,8 @@ int prosim_tc_debug_read(long long* out32);
 enum {
   PROSIM_K_POINTNET = 0, PROSIM_K_RADIUS = 1, PROSIM_K_KNN = 2, PROSIM_K_EDGE_PE = 3, PROSIM_K_ATTN_KV = 4,
   PROSIM_K_ATTN_DSTPRE = 5, PROSIM_K_ATTN_EDGE = 6, PROSIM_K_ATTN_POST = 7, PROSIM_K_HEAD = 8, PROSIM_K_MLP2 = 9,
-  PROSIM_K_STATE = 10, PROSIM_K_EDGE_QK = 11, PROSIM_K_EDGE_AV = 12
+  PROSIM_K_STATE = 10, PROSIM_K_EDGE_QK = 11, PROSIM_K_EDGE_AV = 12,
+  PROSIM_K_ATTN_POST_SW = 13 /* the launches of PROSIM_K_ATTN_POST that took the 32-row tcgen05 kernel (csrc/post_sw.cuh) */
 };
 long long prosim_launch_count(int kernel_class);
 int prosim_profile_enable(int kernel_class);

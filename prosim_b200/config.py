@@ -129,5 +129,19 @@ def check_supported(cfg):
         problems.append('PROMPT.CONDITION.TYPES has duplicates')
     if cfg.PROMPT.CONDITION.TYPES and m.CONDITION_TRANSFORMER.COND_POOL_FUNC != 'mean':
         problems.append("MODEL.CONDITION_TRANSFORMER.COND_POOL_FUNC must be 'mean'")
+    # the kernels hard-code the released data format: 11 history steps x 24 features per agent (8 motion elements + extent
+    # + type one-hot + time one-hot), 10-step targets (x, y, h, xd, yd), dt = 0.1 s, 19 vectors x 11 features per polyline
+    f = cfg.DATASET.FORMAT
+    if f.HISTORY.ELEMENTS != 'x,y,s,c,xd,yd,xdd,ydd' or f.HISTORY.STEPS != 11 or not (f.HISTORY.WITH_EXTEND and
+                                                                                  f.HISTORY.WITH_AGENT_TYPE and f.HISTORY.WITH_TIME_EMB):
+        problems.append('DATASET.FORMAT.HISTORY must be the released layout (x,y,s,c,xd,yd,xdd,ydd + extent + type + time, 11 steps)')
+    if f.TARGET.STEPS != 10 or f.TARGET.SAMPLE_RATE != 10 or not f.TARGET.ELEMENTS.startswith('x,y,h'):
+        problems.append('DATASET.FORMAT.TARGET must be 10 steps of x,y,h(,xd,yd) at SAMPLE_RATE 10')
+    if not (f.MAP.WITH_TYPE_EMB and f.MAP.WITH_DIR):
+        problems.append('DATASET.FORMAT.MAP must carry the type embedding and direction (11 features per vector)')
+    if abs(float(cfg.DATASET.MOTION.DT) - 0.1) > 1e-12:
+        problems.append('DATASET.MOTION.DT must be 0.1')
+    if cfg.ROLLOUT.POLICY.REPLAN_FREQ != 10:
+        problems.append('ROLLOUT.POLICY.REPLAN_FREQ must be 10')
     if problems:
         raise NotImplementedError('; '.join(problems))

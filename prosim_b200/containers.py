@@ -108,11 +108,19 @@ class BatchPrompt(_DictOfDicts):
     def all_prompts(self):
         return self._data
 
+    @all_prompts.setter
+    def all_prompts(self, value):       # a plain attribute in the reference: callers assign to it
+        self._data = value
+
 
 class BatchCondition(_DictOfDicts):
     @property
     def all_cond(self):
         return self._data
+
+    @all_cond.setter
+    def all_cond(self, value):          # rollout/gpu_utils.py:175 replaces the whole condition set
+        self._data = value
 
 
 class SceneBatch:

@@ -88,8 +88,12 @@ inline cudaError_t allow_smem(K kernel, size_t bytes) {
 }
 
 int setup_attributes() {
-  static int state = 0;  // 0 = not done, 1 = ok, <0/>1 = error
-  if (state != 0) return state == 1 ? 0 : state;
+  // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device: one state per device
+  static int states[64] = {0};   // 0 = not done, 1 = ok, > 1 = error + 1000
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return ERR_ARG;
+  int& state = states[dev];
+  if (state != 0) return state == 1 ? 0 : state - 1000;
   cudaError_t e = cudaSuccess;
   auto acc = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
 #define E4_ATTR(ZD, NW) acc(allow_smem(attn_edge4_kernel<ZD, NW>, Edge4Cfg<ZD>::smem_bytes(NW)))
@@ -318,6 +322,7 @@ int launch_post(const float* x, int n, int zd, const float* rbar, const float* a
   const int rpt = pick_rpt(n);
   LaunchScope ls(PROSIM_K_ATTN_POST, st);
   if (pick_rt(n) != 0 && (g_tc_mask & 1) && (g_tc_mask & 8) && n <= SW_MAX_ROWS && (zd == 96 || zd == 128)) {
+    LaunchScope ls_sw(PROSIM_K_ATTN_POST_SW, st);   // counted (and timed) under both classes
     psw::Args a;
     a.x = x; a.rbar = rbar; a.aggv = aggv; a.s = cur.s; a.gx = cur.gx; a.out = out;
     a.q_n = nxt.q; a.qhat_n = nxt.qhat; a.s_n = nxt.s; a.gx_n = nxt.gx;
@@ -376,7 +381,8 @@ int prosim_set_tensor_core(int on) {
 long long prosim_launch_count(int kernel_class) {
   if (kernel_class >= 0 && kernel_class < N_CLASSES) return g_launches[kernel_class];
   long long t = 0;
-  for (int i = 0; i < N_CLASSES; ++i) t += g_launches[i];
+  for (int i = 0; i < N_CLASSES; ++i)
+    if (i != PROSIM_K_ATTN_POST_SW) t += g_launches[i];   // a sub-class of PROSIM_K_ATTN_POST: not a launch of its own
   return t;
 }
 

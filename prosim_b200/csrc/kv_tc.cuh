@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(128, 2) attn_kv_tc_kernel(const float* __restr
   const int m = threadIdx.x, warp = m >> 5;
   const int row0 = blockIdx.x * 128;
 
-  if (warp == 0) tc::tmem_alloc(tmem_slot, 128);
+  if (warp == 0) tc::tmem_alloc(tmem_slot, 256);
   if (m == 32) {
     tc::mbar_init(&p.bfull[0], 1);
     tc::mbar_init(&p.bfull[1], 1);
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(128, 2) attn_kv_tc_kernel(const float* __restr
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(p.tmem, 128);
+  if (warp == 0) tc::tmem_dealloc(p.tmem, 256);
 }
 
 }  // namespace prosim

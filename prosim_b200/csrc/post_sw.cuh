@@ -5,29 +5,41 @@
 // time.  Here the GEMMs are transposed: D^T[feature][row] = W[feature][k] . X[row][k]^T -- the WEIGHTS are the M-side
 // operand (128 output features = 128 TMEM lanes, pre-split tf32 hi / lo chunks streamed from L2 by cp.async.bulk, the
 // same packed chunks tc_post.cuh consumes as its N side) and the ACTIVATIONS of NR = 32 destination rows are the N-side
-// operand (K-major in shared memory, written by the epilogue threads).  A CTA owns 32 rows: 128 CTAs per 4096 rows,
-// the tensor work per CTA drops 4x (N = 32: 16 cycles per MMA), the per-thread epilogue work 4x (16 values per phase).
+// operand (K-major, 128B-swizzled, written by the epilogue threads).  A CTA owns 32 rows: 128 CTAs per 4096 rows.
 //
 // Same math as tc_post.cuh / attn_post2_kernel (reference prosim/models/layers/attention_layer.py:102-118, :38-43 and
 // the next layer's destination-side projections :56-66):
-//   agg = AggV + Rbar_h . Wvr'_h           (normal orientation: rows on lanes 0..31 of an M = 128 MMA, N = 16 per head)
+//   agg = AggV + Rbar_h . Wvr'_h           (fp32 FFMA: thread = (row, head), ZD x 16 MACs, the row's Rbar_h in registers)
 //   g = sigmoid(Wga agg + Gx) ; u = agg + g (S - agg) ; x1 = x + LN(Wo u + bo)
 //   y = W2 relu(W1 LN(x1) + b1) + b2 ; out = x1 + LN(y) ; next layer: s | gx | q = {Ws, Wgx, Wq} LN_dst'(out), Qhat_h
-// every product as three tf32 MMAs (a_lo w_hi + a_hi w_lo + a_hi w_hi, fp32 accumulation in TMEM).
+// every tensor-core product a w ~ a_hi w_hi + a_lo w_hi + a_hi w_lo (tf32 hi / lo splits, fp32 accumulation in TMEM) in
+// TWO MMAs per k-step: the activation operand holds its 32 hi rows and its 32 lo rows as one 64-row operand, so
+// W_hi . [X_hi ; X_lo]^T is one N = 64 instruction (columns 0..31 = hi hi, 32..63 = hi lo) and W_lo . X_hi^T accumulates
+// onto columns 32..63; the epilogue adds the two column halves.
+//
+// What was measured on the way (B200, 4096 rows, profiles/r2_*): SS-mode MMAs re-read their operands from shared memory
+// per instruction, so at N = 32 the 4 KB weight operand -- not the math -- paces the tensor pipe (65 cycles per MMA with
+// three MMAs per k-step); activation operands whose 128-byte core matrices were placed 144 bytes apart (to make the
+// epilogue's stores conflict free) doubled that operand's fetch cost -> SWIZZLE_128B operands, conflict free for both
+// store patterns AND aligned.  The weight stream is NOT the bound: multicasting it inside clusters of 2 / 4 CTAs changed
+// nothing (60.8 / 60.7 / 59.9 us per launch), neither did skipping the copies altogether.  Rbar_h . Wvr'_h as eight
+// M = 128 MMAs (96 of 128 operand rows unused) with hi / lo staging cost 13 k cycles per CTA; as fp32 FFMA it is exact
+// and shorter.
 //
 // Thread roles (320 threads, 1 CTA / SM):
-//   warps 0-7  epilogue.  Two index maps over the CTA's [32 rows x 128 features] tile, 16 values per thread:
+//   warps 0-7  epilogue.  Index maps over the CTA's [32 rows x 128 features] tile, 16 values per thread:
 //                T-map (TMEM native): thread = feature f = 32 (warp % 4) + lane, rows 16 (warp / 4) .. + 15.  Biases are
-//                  per-thread scalars; global rows [r][f] are read / written as coalesced 128-byte lines; the next
-//                  operand is written with conflict-free 4-byte stores (operand core matrices are 144 bytes apart).
+//                  per-thread scalars; global rows [r][f] are read / written as coalesced 128-byte lines.
 //                R-map (row major): thread = (row 4 warp + lane / 8, feature groups s + 8 i of 4 floats, s = lane % 8):
 //                  LayerNorm statistics are three xor-shuffles inside 8 lanes.  T-map -> R-map goes through a padded
 //                  [32][132] fp32 scratch tile and one named barrier.
+//                H-map (agg only): thread = (row lane, head warp): weight reads are warp-wide broadcasts.
 //   warp 8     weight producer (one thread, 4 x 32 KB ring on full / empty mbarriers)
 //   warp 9     MMA issuer (one thread)
-// TMEM: twelve [128 lanes x 32 columns] accumulator slots + the [32 lanes x 128 columns] agg accumulator; every slot is
-// written by one GEMM and read by one epilogue, so there are no accumulator-free barriers; every accumulator has its own
-// single-use "done" mbarrier.
+// TMEM: eight [128 lanes x 64 columns] accumulator slots; every accumulator has its own single-use "done" mbarrier, and
+// a slot is rewritten only after every epilogue thread has read its previous contents AND arrived on a barrier the MMA
+// thread waits on before that GEMM, so there are no "free" barriers:
+//   gate 0, out 1, up_0 2, up_1 3, up_2 2, up_3 3, down 4, q 2, s 0, gx 1, Qhat_h: 3 4 5 6 7 2 0 1
 #pragma once
 #include <cuda.h>
 
@@ -45,30 +57,27 @@ namespace psw {
 constexpr int NR = 32;                     // destination rows per CTA
 constexpr int NST = 4;                     // weight ring stages
 constexpr int STAGE_BYTES = 32768;
-constexpr int LBO_A = 144;                 // activation operands: K-adjacent core matrices 144 B apart (bank spread)
-constexpr int SBO_A = 32 * LBO_A;          // 8-row groups of a [32 x 128] operand
-constexpr int OPND_HALF = 4 * SBO_A;       // hi (or lo) part
-constexpr int OPND_BYTES = 2 * OPND_HALF;
+constexpr int SLAB_BYTES = 8192;           // one 32-wide k block of an activation operand: 64 rows (32 hi + 32 lo) x 128 B
+constexpr int LO_OFF = 4096;               // lo rows follow the hi rows inside a slab
+constexpr int OPND_BYTES = 4 * SLAB_BYTES;
 constexpr int SCR_LD = 132;                // scratch row pitch (floats)
-constexpr int EPI_THREADS = 256;
+constexpr int EPI_THREADS = 256, EPI_WARPS = 8;
 constexpr int THREADS = EPI_THREADS + 64;
-constexpr uint32_t AGG_COL = 384;          // agg accumulator [lanes 0..31][128]
-constexpr int A_AGG = 0, A_GATE = 1, A_OUT = 2, A_UP = 3, A_DOWN = 7, A_S = 8, A_GX = 9, A_Q = 10, A_QH = 11, NACC = 19;
-// accumulator slots (x 32 columns): gate 0, out 1, up_t 2..5, down 6, s 7, gx 8, q 9, Qhat_h: 0..5, 10, 11
-__host__ __device__ constexpr uint32_t slot_col(int s) { return 32u * (uint32_t)s; }
-__host__ __device__ constexpr int qh_slot(int h) { return h < 6 ? h : 4 + h; }
+constexpr int A_GATE = 0, A_OUT = 1, A_UP = 2, A_DOWN = 6, A_S = 7, A_GX = 8, A_Q = 9, A_QH = 10, NACC = 18;
+__host__ __device__ constexpr uint32_t slot_col(int s) { return 64u * (uint32_t)s; }
+__host__ __device__ constexpr int qh_slot(int h) { return h < 5 ? 3 + h : h == 5 ? 2 : h - 6; }
 
 struct Smem {
-  uint8_t actA[OPND_BYTES];                // activation operand (agg / u / LN(x1) / LN_dst(out)); Rbar head buffer 0
-  uint8_t actH[OPND_BYTES];                // FFN hidden operand, q operand; Rbar head buffer 1
-  uint8_t ring[NST][STAGE_BYTES];          // (the agg MMAs read 96 unused operand rows past the Rbar buffers: into here)
+  uint8_t actA[OPND_BYTES];                // activation operand: agg / u / LN(x1) / LN_dst(out)
+  uint8_t actH[OPND_BYTES];                // FFN hidden operand, q operand
+  uint8_t ring[NST][STAGE_BYTES];
   float scratch[NR * SCR_LD];
   float vec[tcp::V_SIZE];
   uint64_t full[NST], empty[NST];
-  uint64_t rb_ready[2], rb_free[2], opnd_ready, h_ready, h_free, acc_done[NACC];
+  uint64_t opnd_ready, sgx_read, h_ready, h_free, acc_done[NACC];
   uint32_t tmem_base;
 };
-constexpr size_t SMEM_BYTES = sizeof(Smem) + 128;
+constexpr size_t SMEM_BYTES = sizeof(Smem) + 1024;
 
 struct Args {
   const float *x, *rbar, *aggv, *s, *gx;   // [n][128], [n][8 zd], [n][128] ...
@@ -78,8 +87,19 @@ struct Args {
   int n;
 };
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
+// K-major SWIZZLE_128B shared-memory matrix descriptor (8-row groups 1024 B apart; cute/arch/mma_sm100_desc.hpp)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                        // leading byte offset: unused for swizzled K-major operands
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset
+  d |= (uint64_t)1 << 46;                        // descriptor version 1 (Blackwell)
+  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  return d;
+}
+// 16 accumulator values = hi.hi half (columns taddr ..) + cross-term half (columns taddr + 32 ..), one wait for both loads
+__device__ __forceinline__ void tmem_ld16_pair(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16], q[16];
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
@@ -87,25 +107,37 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+        "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+      : "r"(taddr + 32)
+      : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(q[i]);
 }
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) { tcp::mbar_arrive(e4::smem_u32(bar)); }
 
+// phase timestamps of CTA 0 (SM clock) into tcp::g_tcp_dbg: [0..15] epilogue thread 0, [16..27] MMA thread, [28] cycles the
+// MMA thread waited for weights, [29] for the epilogue warps (tools/sw_phases.py)
+#define PSW_MARK(slot)                                                  \
+  do {                                                                  \
+    if (blockIdx.x == 0 && has_next) tcp::g_tcp_dbg[slot] = clock64(); \
+  } while (0)
+
 template <int ZD>
 __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_constant__ Args a) {
   extern __shared__ uint8_t smem_raw[];
-  Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((128u - (e4::smem_u32(smem_raw) & 127u)) & 127u));
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (e4::smem_u32(smem_raw) & 1023u)) & 1023u));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * NR;
   const float* __restrict__ W = a.W;
   const float* __restrict__ Wn = a.Wn;
   const bool has_next = Wn != nullptr;
-  constexpr int SBO_R = (ZD / 4) * LBO_A;              // 8-row groups of a [rows x ZD] Rbar head operand
-  constexpr int RB_HALF = 4 * SBO_R;
-  constexpr int NG_R = ZD / 32;                        // 16-byte groups per thread per Rbar head row
+  constexpr int VR_HALF_BYTES = (ZD / 2) * D * 4;      // the fp32 Wvr' block [ZD][128] travels as two ring stages
 
   if (warp == 0) tc::tmem_alloc(&sm.tmem_base, 512);
   if (tid == 32) {
@@ -113,12 +145,9 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
       e4::mbar_init(e4::smem_u32(&sm.full[i]), 1);
       e4::mbar_init(e4::smem_u32(&sm.empty[i]), 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      e4::mbar_init(e4::smem_u32(&sm.rb_ready[i]), EPI_THREADS);
-      e4::mbar_init(e4::smem_u32(&sm.rb_free[i]), 1);
-    }
-    e4::mbar_init(e4::smem_u32(&sm.opnd_ready), EPI_THREADS);
-    e4::mbar_init(e4::smem_u32(&sm.h_ready), EPI_THREADS);
+    e4::mbar_init(e4::smem_u32(&sm.opnd_ready), EPI_WARPS);
+    e4::mbar_init(e4::smem_u32(&sm.h_ready), EPI_WARPS);
+    e4::mbar_init(e4::smem_u32(&sm.sgx_read), EPI_WARPS);
     e4::mbar_init(e4::smem_u32(&sm.h_free), 1);
     for (int i = 0; i < NACC; ++i) e4::mbar_init(e4::smem_u32(&sm.acc_done[i]), 1);
   }
@@ -140,33 +169,32 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = sm.tmem_base;
-  const int n_chunks = has_next ? 68 : 48;
+  const int n_chunks = has_next ? 58 : 42;
 
   if (warp == 8) {
     // ================================================================== weight producer
     if (lane == 0) {
-      constexpr int VR_FLOATS = 16 * ZD * 2;
       for (int i = 0; i < n_chunks; ++i) {
         const float* src;
         uint32_t bytes;
-        if (i < 8) {
-          src = W + (ZD == 96 ? aw::TC_VR96 : aw::TC_VR128) + i * VR_FLOATS;
-          bytes = VR_FLOATS * 4;
-        } else if (i < 16) {
-          src = W + aw::TC_GA + (i - 8) * 8192;      // Wga (4), Wo (4): contiguous
+        if (i < 2) {
+          src = W + (ZD == 96 ? aw::WVRG96T : aw::WVRGT) + i * (VR_HALF_BYTES / 4);   // fp32 [ZD][128]: the FFMA agg
+          bytes = VR_HALF_BYTES;
+        } else if (i < 10) {
+          src = W + aw::TC_GA + (i - 2) * 8192;      // Wga (4), Wo (4): contiguous
           bytes = 32768;
-        } else if (i < 48) {
-          src = W + aw::TC_FF2 + (i - 16) * 8192;    // up_0, up_1, down_0, up_2, down_1, up_3, down_2, down_3 (4 k-chunks each)
+        } else if (i < 42) {
+          src = W + aw::TC_FF2 + (i - 10) * 8192;    // up_0, up_1, down_0, up_2, down_1, up_3, down_2, down_3 (4 k-chunks each)
           bytes = 32768;
-        } else if (i < 56) {
-          src = Wn + aw::TC_S + (i - 48) * 8192;     // next layer's Ws, Wgx (contiguous) ...
+        } else if (i < 46) {
+          src = Wn + aw::TC_Q + (i - 42) * 8192;     // next layer's Wq first (q feeds the Qhat GEMMs) ...
           bytes = 32768;
-        } else if (i < 60) {
-          src = Wn + aw::TC_Q + (i - 56) * 8192;     // ... then Wq
+        } else if (i < 54) {
+          src = Wn + aw::TC_S + (i - 46) * 8192;     // ... then Ws, Wgx (contiguous)
           bytes = 32768;
         } else {
-          src = Wn + aw::TC_KRG + (i - 60) * 4096;
-          bytes = 16384;
+          src = Wn + aw::TC_KRG + (i - 54) * 8192;   // Wkr' of two heads per stage
+          bytes = 32768;
         }
         const int s = i % NST;
         if (i >= NST) tcp::mbar_wait(&sm.empty[s], ((i / NST) - 1) & 1);
@@ -179,41 +207,44 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
   } else if (warp == 9) {
     // ================================================================== MMA issuer
     if (lane == 0) {
-      int ci = 0;
-      uint32_t ph_rb0 = 0, ph_rb1 = 0, ph_op = 0, ph_h = 0;
+      int ci = 2;                                  // chunks 0 and 1 (fp32 Wvr') belong to the epilogue warps
+      uint32_t ph_op = 0, ph_h = 0;
+      long long w_full = 0, w_other = 0;
       auto wait_bar = [&](uint64_t* bar, uint32_t& ph) {
+        const long long t0 = clock64();
         tcp::mbar_wait(bar, ph);
+        w_other += clock64() - t0;
         ph ^= 1;
         tc::fence_after_sync();
       };
       auto next_chunk = [&]() -> uint32_t {
         const int s = ci % NST;
+        const long long t0 = clock64();
         tcp::mbar_wait(&sm.full[s], (ci / NST) & 1);
+        w_full += clock64() - t0;
         tc::fence_after_sync();
         return e4::smem_u32(sm.ring[s]);
       };
-      auto release_chunk = [&]() {
-        tc::mma_commit(&sm.empty[ci % NST]);
-        ++ci;
-      };
-      // D^T[128 features][32 rows] (+)= Wchunk[128 x KC] . X[32 rows][k0 .. k0 + KC)^T
-      auto gemm_sw = [&](auto kc_tag, uint32_t d_col, uint32_t opnd, int k0, bool accumulate) {
+      // D^T[128 features][hi.hi | cross] (+)= Wchunk[128 x KC] . X[rows][k0 .. k0 + KC)^T ; k0 .. k0 + KC stays inside a 32-wide slab
+      // `part` of `parts` weight blocks that share one ring stage
+      auto gemm_sw = [&](auto kc_tag, uint32_t d_col, uint32_t opnd, int k0, bool accumulate, int part = 0, int parts = 1) {
         constexpr int KC_ = decltype(kc_tag)::value;
-        const uint32_t wb = next_chunk();
-        constexpr uint32_t idesc = tc::make_idesc_tf32(128, NR);
+        const uint32_t wb = (part == 0 ? next_chunk() : e4::smem_u32(sm.ring[ci % NST])) + part * (2 * 128 * KC_ * 4);
+        constexpr uint32_t idesc64 = tc::make_idesc_tf32(128, 2 * NR), idesc32 = tc::make_idesc_tf32(128, NR);
         const uint64_t wh0 = tc::make_smem_desc(wb, 128, KC_ * 32);
         const uint64_t wl0 = tc::make_smem_desc(wb + 128 * KC_ * 4, 128, KC_ * 32);
-        const uint64_t xh0 = tc::make_smem_desc(opnd + (k0 >> 2) * LBO_A, LBO_A, SBO_A);
-        const uint64_t xl0 = tc::make_smem_desc(opnd + OPND_HALF + (k0 >> 2) * LBO_A, LBO_A, SBO_A);
+        const uint64_t x0 = make_desc_sw128(opnd + (k0 >> 5) * SLAB_BYTES + (k0 & 31) * 4);
 #pragma unroll
         for (int ks = 0; ks < KC_ / 8; ++ks) {
           const uint64_t wh = wh0 + (uint64_t)(ks * 16), wl = wl0 + (uint64_t)(ks * 16);
-          const uint64_t xh = xh0 + (uint64_t)(ks * (2 * LBO_A / 16)), xl = xl0 + (uint64_t)(ks * (2 * LBO_A / 16));
-          tc::mma_tf32(tmem + d_col, wh, xl, idesc, accumulate || ks > 0);
-          tc::mma_tf32(tmem + d_col, wl, xh, idesc, true);
-          tc::mma_tf32(tmem + d_col, wh, xh, idesc, true);
+          const uint64_t xd = x0 + (uint64_t)(ks * 2);                          // + 32 bytes inside the swizzled row
+          tc::mma_tf32(tmem + d_col, wh, xd, idesc64, accumulate || ks > 0);    // [hi.hi | hi.lo]: rows 0..31 hi, 32..63 lo
+          tc::mma_tf32(tmem + d_col + NR, wl, xd, idesc32, true);               // + lo.hi onto the cross-term half
         }
-        release_chunk();
+        if (part == parts - 1) {
+          tc::mma_commit(&sm.empty[ci % NST]);
+          ++ci;
+        }
       };
       using I16 = std::integral_constant<int, 16>;
       using I32 = std::integral_constant<int, 32>;
@@ -222,40 +253,21 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
         for (int c = 0; c < 4; ++c) gemm_sw(I32{}, d_col, opnd, 32 * c, c > 0);
       };
       const uint32_t actA = e4::smem_u32(sm.actA), actH = e4::smem_u32(sm.actH);
-      // 1. agg (normal orientation): D[row lanes][16 h ..] = Rbar_h[rows x ZD] . Wvr'_h[16 x ZD]^T
-#pragma unroll 1
-      for (int h = 0; h < H; ++h) {
-        if (h & 1) wait_bar(&sm.rb_ready[1], ph_rb1);
-        else wait_bar(&sm.rb_ready[0], ph_rb0);
-        const uint32_t rb = (h & 1) ? actH : actA;
-        const uint32_t wb = next_chunk();
-        constexpr uint32_t idesc = tc::make_idesc_tf32(128, 16);
-        const uint64_t ah0 = tc::make_smem_desc(rb, LBO_A, SBO_R);
-        const uint64_t al0 = tc::make_smem_desc(rb + RB_HALF, LBO_A, SBO_R);
-        const uint64_t bh0 = tc::make_smem_desc(wb, 128, ZD * 32);
-        const uint64_t bl0 = tc::make_smem_desc(wb + 16 * ZD * 4, 128, ZD * 32);
-        const uint32_t d = tmem + AGG_COL + 16 * h;
-#pragma unroll
-        for (int ks = 0; ks < ZD / 8; ++ks) {
-          const uint64_t ah = ah0 + (uint64_t)(ks * (2 * LBO_A / 16)), al = al0 + (uint64_t)(ks * (2 * LBO_A / 16));
-          const uint64_t bh = bh0 + (uint64_t)(ks * 16), bl = bl0 + (uint64_t)(ks * 16);
-          tc::mma_tf32(d, al, bh, idesc, ks > 0);
-          tc::mma_tf32(d, ah, bl, idesc, true);
-          tc::mma_tf32(d, ah, bh, idesc, true);
-        }
-        release_chunk();
-        tc::mma_commit(&sm.rb_free[h & 1]);
-      }
-      tc::mma_commit(&sm.acc_done[A_AGG]);
-      // 2. gate, 3. out projection
+      PSW_MARK(16);
+      // 1. gate, 2. out projection
       wait_bar(&sm.opnd_ready, ph_op);
+      PSW_MARK(18);
       gemm128(slot_col(0), actA);
       tc::mma_commit(&sm.acc_done[A_GATE]);
+      PSW_MARK(19);
       wait_bar(&sm.opnd_ready, ph_op);
+      PSW_MARK(20);
       gemm128(slot_col(1), actA);
       tc::mma_commit(&sm.acc_done[A_OUT]);
-      // 4. FFN: hidden tile t = 128 features; chunks arrive as up_0, up_1, down_0, up_2, down_1, up_3, down_2, down_3
+      PSW_MARK(21);
+      // 3. FFN: hidden tile t = 128 features; chunks arrive as up_0, up_1, down_0, up_2, down_1, up_3, down_2, down_3
       wait_bar(&sm.opnd_ready, ph_op);
+      PSW_MARK(22);
       gemm128(slot_col(2), actA);
       tc::mma_commit(&sm.acc_done[A_UP + 0]);
       gemm128(slot_col(3), actA);
@@ -264,29 +276,40 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
       for (int t = 0; t < 4; ++t) {
         wait_bar(&sm.h_ready, ph_h);
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) gemm_sw(I32{}, slot_col(6), actH, 32 * c, t > 0 || c > 0);
+        for (int c = 0; c < 4; ++c) gemm_sw(I32{}, slot_col(4), actH, 32 * c, t > 0 || c > 0);
         if (t < 3) tc::mma_commit(&sm.h_free);
         else tc::mma_commit(&sm.acc_done[A_DOWN]);
         if (t + 2 < 4) {
-          gemm128(slot_col(2 + t + 2), actA);
+          gemm128(slot_col(2 + t), actA);                 // up_{t+2} reuses the slot of up_t (read before h_ready was signalled)
           tc::mma_commit(&sm.acc_done[A_UP + t + 2]);
         }
       }
+      PSW_MARK(23);
       if (has_next) {
-        // 5. next layer: s, gx, q from LN_dst'(out); then Qhat_h = Wkr'_h[128 x 16] . q_h^T
+        // 4. next layer: q, s, gx from LN_dst'(out); Qhat_h = Wkr'_h[128 x 16] . q_h^T starts as soon as the q operand is
+        //    written (that epilogue runs under the s / gx MMAs); the last two heads reuse the s / gx slots
         wait_bar(&sm.opnd_ready, ph_op);
-        gemm128(slot_col(7), actA);
-        tc::mma_commit(&sm.acc_done[A_S]);
-        gemm128(slot_col(8), actA);
-        tc::mma_commit(&sm.acc_done[A_GX]);
-        gemm128(slot_col(9), actA);
+        PSW_MARK(24);
+        gemm128(slot_col(2), actA);
         tc::mma_commit(&sm.acc_done[A_Q]);
-        wait_bar(&sm.opnd_ready, ph_op);
+        gemm128(slot_col(0), actA);
+        tc::mma_commit(&sm.acc_done[A_S]);
+        gemm128(slot_col(1), actA);
+        tc::mma_commit(&sm.acc_done[A_GX]);
+        PSW_MARK(25);
+        wait_bar(&sm.opnd_ready, ph_op);         // q operand written, slot 2 read
+        PSW_MARK(26);
 #pragma unroll 1
         for (int h = 0; h < H; ++h) {
-          gemm_sw(I16{}, slot_col(qh_slot(h)), actH, 16 * h, false);
+          if (h == 6) {                                  // s and gx read: slots 0 and 1 are free (its own barrier: a warp may
+            uint32_t ph0 = 0;                            // arrive here before another has arrived for the q operand)
+            wait_bar(&sm.sgx_read, ph0);
+          }
+          gemm_sw(I16{}, slot_col(qh_slot(h)), actH, 16 * h, false, h & 1, 2);
           tc::mma_commit(&sm.acc_done[A_QH + h]);
         }
+        PSW_MARK(27);
+        if (blockIdx.x == 0) { tcp::g_tcp_dbg[28] = w_full; tcp::g_tcp_dbg[29] = w_other; }
       }
     }
     __syncwarp();
@@ -299,31 +322,34 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
     const bool rr_ok = row0 + rr < a.n;
     const float* vec = sm.vec;
     float* scr = sm.scratch;
-    uint32_t ph_rbf0 = 0, ph_rbf1 = 0, ph_hfree = 0;
+    uint32_t ph_hfree = 0;
     auto wait_acc = [&](int i) {
       tcp::mbar_wait(&sm.acc_done[i], 0);
       tc::fence_after_sync();
     };
+    // this warp's operand stores are complete and visible to the tensor core: one arrival per warp
     auto publish = [&](uint64_t* bar) {
       e4::fence_proxy_async();
       tc::fence_before_sync();
-      mbar_arrive(bar);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
     };
-    // T-map: 16 rows of this thread's feature -> hi / lo activation operand at `opnd`
+    // T-map: 16 rows of this thread's feature -> hi / lo rows of the swizzled activation operand at `opnd`
     auto t_store_opnd = [&](uint8_t* opnd, const float (&v)[16]) {
-      uint8_t* p = opnd + (f >> 2) * LBO_A + (f & 3) * 4 + (2 * ch) * SBO_A;
+      uint8_t* p = opnd + q4 * SLAB_BYTES + (2 * ch) * 1024 + (lane & 3) * 4;
+      const int c = lane >> 2;                             // 16-byte chunk of the row before the swizzle
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float hi = tcp::tf32_rna_finite(v[i]);
         const float lo = tcp::tf32_rna_finite(v[i] - hi);
-        uint8_t* pe = p + (i >> 3) * SBO_A + (i & 7) * 16;
+        uint8_t* pe = p + (i >> 3) * 1024 + (i & 7) * 128 + ((c ^ (i & 7)) << 4);
         *reinterpret_cast<float*>(pe) = hi;
-        *reinterpret_cast<float*>(pe + OPND_HALF) = lo;
+        *reinterpret_cast<float*>(pe + LO_OFF) = lo;
       }
     };
-    // R-map: this thread's 4 groups of 4 features of row rr -> hi / lo activation operand
+    // R-map: this thread's 4 groups of 4 features of row rr (group sg + 8 i = chunk sg of slab i)
     auto r_store_opnd = [&](uint8_t* opnd, const float (&v)[16]) {
-      uint8_t* p = opnd + (rr >> 3) * SBO_A + (rr & 7) * 16 + sg * LBO_A;
+      uint8_t* p = opnd + (rr >> 3) * 1024 + (rr & 7) * 128 + ((sg ^ (rr & 7)) << 4);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float4 hi, lo;
@@ -331,8 +357,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
         hi.y = tcp::tf32_rna_finite(v[4 * i + 1]); lo.y = tcp::tf32_rna_finite(v[4 * i + 1] - hi.y);
         hi.z = tcp::tf32_rna_finite(v[4 * i + 2]); lo.z = tcp::tf32_rna_finite(v[4 * i + 2] - hi.z);
         hi.w = tcp::tf32_rna_finite(v[4 * i + 3]); lo.w = tcp::tf32_rna_finite(v[4 * i + 3] - hi.w);
-        *reinterpret_cast<float4*>(p + 8 * i * LBO_A) = hi;
-        *reinterpret_cast<float4*>(p + 8 * i * LBO_A + OPND_HALF) = lo;
+        *reinterpret_cast<float4*>(p + i * SLAB_BYTES) = hi;
+        *reinterpret_cast<float4*>(p + i * SLAB_BYTES + LO_OFF) = lo;
       }
     };
     auto r_load_scr = [&](float (&v)[16]) {
@@ -409,72 +435,69 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
 #pragma unroll
       for (int i = 0; i < 16; ++i) scr[(16 * ch + i) * SCR_LD + f] = v[i];
     };
-
-    // ---- 0. Rbar_h -> A-side operand tiles (hi | lo), heads alternate between the two operand buffers
+#define PSW_EMARK(slot) do { if (tid == 0) PSW_MARK(slot); } while (0)
+    PSW_EMARK(0);
+    float v[16];
+    // ---- 0. agg[row][16 h ..] = AggV + sum_d Rbar[row][h][d] Wvr'[d][16 h ..]   (H-map: row = lane, head = warp)
+    //         fp32 FFMA, the row's Rbar_h in registers, the weights read as warp-wide broadcasts from the ring (two
+    //         stages hold the fp32 [ZD][128] block); ascending d like the FFMA node kernels
     {
-      const float* rb_row = a.rbar + (size_t)(row0 + rr) * (H * ZD);
-      float4 cur[NG_R], nxt[NG_R];
-      auto load_head = [&](int h, float4 (&dst)[NG_R]) {
+      const bool ok = row0 + lane < a.n;
+      float4 rb[ZD / 4];
+      float2 av[8];
+      const float4* rp = reinterpret_cast<const float4*>(a.rbar + (size_t)(row0 + lane) * (H * ZD) + warp * ZD);
 #pragma unroll
-        for (int i = 0; i < NG_R; ++i) {
-          dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rr_ok) dst[i] = __ldg(reinterpret_cast<const float4*>(rb_row + h * ZD) + sg + 8 * i);
-        }
-      };
-      load_head(0, cur);
-#pragma unroll 1
-      for (int h = 0; h < H; ++h) {
-        if (h + 1 < H) load_head(h + 1, nxt);
-        if (h >= 2) {
-          if (h & 1) { tcp::mbar_wait(&sm.rb_free[1], ph_rbf1); ph_rbf1 ^= 1; }
-          else { tcp::mbar_wait(&sm.rb_free[0], ph_rbf0); ph_rbf0 ^= 1; }
-        }
-        uint8_t* p = ((h & 1) ? sm.actH : sm.actA) + (rr >> 3) * SBO_R + (rr & 7) * 16 + sg * LBO_A;
+      for (int i = 0; i < ZD / 4; ++i) rb[i] = ok ? __ldg(rp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < NG_R; ++i) {
-          float4 hi, lo;
-          hi.x = tcp::tf32_rna_finite(cur[i].x); lo.x = tcp::tf32_rna_finite(cur[i].x - hi.x);
-          hi.y = tcp::tf32_rna_finite(cur[i].y); lo.y = tcp::tf32_rna_finite(cur[i].y - hi.y);
-          hi.z = tcp::tf32_rna_finite(cur[i].z); lo.z = tcp::tf32_rna_finite(cur[i].z - hi.z);
-          hi.w = tcp::tf32_rna_finite(cur[i].w); lo.w = tcp::tf32_rna_finite(cur[i].w - hi.w);
-          *reinterpret_cast<float4*>(p + 8 * i * LBO_A) = hi;
-          *reinterpret_cast<float4*>(p + 8 * i * LBO_A + RB_HALF) = lo;
-        }
-        publish(&sm.rb_ready[h & 1]);
-#pragma unroll
-        for (int i = 0; i < NG_R; ++i) cur[i] = nxt[i];
+      for (int i = 0; i < 4; ++i) {
+        float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) t4 = __ldg(reinterpret_cast<const float4*>(a.aggv + (size_t)(row0 + lane) * D + 16 * warp) + i);
+        av[2 * i] = make_float2(t4.x, t4.y);
+        av[2 * i + 1] = make_float2(t4.z, t4.w);
       }
-    }
-    float v[16], t[16];
-    // ---- 1. agg = AGG accumulator (rows on lanes 0..31) + AggV -> scratch (fp32, for the gate) and operand A
-    r_load_glb(a.aggv, t);
-    wait_acc(A_AGG);
-    if (q4 == 0) {   // warps 0 and 4 own TMEM lanes 0..31: thread = row, 64 columns each
-      float w[32];
-#pragma unroll 1
-      for (int c0 = 64 * ch; c0 < 64 * ch + 64; c0 += 32) {
-        tc::tmem_ld32(tmem + AGG_COL + c0, w);
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          *reinterpret_cast<float4*>(scr + lane * SCR_LD + c0 + 4 * i) = make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+      for (int half = 0; half < 2; ++half) {
+        tcp::mbar_wait(&sm.full[half], 0);
+        const float* wv = reinterpret_cast<const float*>(sm.ring[half]) + 16 * warp;
+#pragma unroll
+        for (int dq = 0; dq < ZD / 8; ++dq) {
+          const float4 r4 = rb[half * (ZD / 8) + dq];
+          const float rv[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float* wr = wv + (dq * 4 + j) * D;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 w4 = *reinterpret_cast<const float4*>(wr + 4 * i);
+              const float2 rr2 = make_float2(rv[j], rv[j]);      // packed FFMA2: two columns per instruction (same rounding)
+              av[2 * i] = __ffma2_rn(rr2, make_float2(w4.x, w4.y), av[2 * i]);
+              av[2 * i + 1] = __ffma2_rn(rr2, make_float2(w4.z, w4.w), av[2 * i + 1]);
+            }
+          }
+        }
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4*>(scr + lane * SCR_LD + 16 * warp + 4 * i) = make_float4(av[2 * i].x, av[2 * i].y, av[2 * i + 1].x, av[2 * i + 1].y);
+      epi_barrier();
+      if (tid == 0) {          // every epilogue thread has read the two weight stages
+        mbar_arrive(&sm.empty[0]);
+        mbar_arrive(&sm.empty[1]);
+      }
+      PSW_EMARK(1);
+      r_load_scr(v);           // agg stays in the scratch tile (fp32) for the gate
+      r_store_opnd(sm.actA, v);
+      publish(&sm.opnd_ready);
+      PSW_EMARK(3);
     }
-    epi_barrier();
-    r_load_scr(v);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] += t[i];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      *reinterpret_cast<float4*>(scr + rr * SCR_LD + 4 * (sg + 8 * i)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    r_store_opnd(sm.actA, v);
-    publish(&sm.opnd_ready);
-    // ---- 2. gate: g = sigmoid(acc + Gx) ; u = agg + g (S - agg) -> operand A        (T-map)
+    // ---- 1. gate: g = sigmoid(acc + Gx) ; u = agg + g (S - agg) -> operand A        (T-map)
     {
       float gxv[16], sv[16];
       t_load_glb(a.gx, gxv);
       t_load_glb(a.s, sv);
       wait_acc(A_GATE);
-      tmem_ld16(lb + slot_col(0) + 16 * ch, v);
+      PSW_EMARK(4);
+      tmem_ld16_pair(lb + slot_col(0) + 16 * ch, v);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float ag = scr[(16 * ch + i) * SCR_LD + f];
@@ -483,14 +506,16 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
       }
       t_store_opnd(sm.actA, v);
       publish(&sm.opnd_ready);
+      PSW_EMARK(5);
     }
-    // ---- 3. o = acc + bo ; x1 = x + LN_post(o) (kept in registers, R-map) ; LN_ffpre(x1) -> operand A
+    // ---- 2. o = acc + bo ; x1 = x + LN_post(o) (kept in registers, R-map) ; LN_ffpre(x1) -> operand A
     float x1[16];
     {
       r_load_glb(a.x, x1);
       const float bo = vec[tcp::V_BO + f];
       wait_acc(A_OUT);
-      tmem_ld16(lb + slot_col(1) + 16 * ch, v);
+      PSW_EMARK(6);
+      tmem_ld16_pair(lb + slot_col(1) + 16 * ch, v);
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] += bo;
       t_store_scr(v);
@@ -505,13 +530,14 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
       r_layernorm(v, tcp::V_LNFFPRE_G, tcp::V_LNFFPRE_B);
       r_store_opnd(sm.actA, v);
       publish(&sm.opnd_ready);
+      PSW_EMARK(7);
     }
-    // ---- 4. FFN hidden tiles: h_t = relu(acc + b1) -> operand H                     (T-map)
+    // ---- 3. FFN hidden tiles: h_t = relu(acc + b1) -> operand H                     (T-map)
 #pragma unroll 1
     for (int tt = 0; tt < 4; ++tt) {
       const float b1 = vec[tcp::V_B1 + 128 * tt + f];
       wait_acc(A_UP + tt);
-      tmem_ld16(lb + slot_col(2 + tt) + 16 * ch, v);
+      tmem_ld16_pair(lb + slot_col(2 + (tt & 1)) + 16 * ch, v);
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + b1, 0.f);
       if (tt > 0) {
@@ -524,8 +550,10 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
     // ---- y = acc + b2 ; out = x1 + LN_ffpost(y) -> global ; LN_dst'(out) -> operand A
     {
       const float b2 = vec[tcp::V_B2 + f];
+      PSW_EMARK(8);
       wait_acc(A_DOWN);
-      tmem_ld16(lb + slot_col(6) + 16 * ch, v);
+      PSW_EMARK(9);
+      tmem_ld16_pair(lb + slot_col(4) + 16 * ch, v);
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] += b2;
       t_store_scr(v);
@@ -540,13 +568,26 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
         r_store_opnd(sm.actA, v);
         publish(&sm.opnd_ready);
       }
+      PSW_EMARK(10);
     }
     if (has_next) {
-      // ---- 5. s, gx, q (+ bias) -> global (coalesced lines, T-map); q also -> operand H; then the eight Qhat_h
+      // ---- 4. q, s, gx (+ bias) -> global as coalesced lines (T-map); q also -> operand H
+      {
+        const float bq = vec[tcp::V_BQ + f];
+        wait_acc(A_Q);
+        PSW_EMARK(11);
+        tmem_ld16_pair(lb + slot_col(2) + 16 * ch, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += bq;
+        t_store_opnd(sm.actH, v);             // every MMA that read the hidden operand completed before acc_done[DOWN]
+        publish(&sm.opnd_ready);              // q operand written, slot 2 read
+        PSW_EMARK(12);
+        t_store_glb(a.q_n, D, 0, v);
+      }
       {
         const float bs = vec[tcp::V_BS + f];
         wait_acc(A_S);
-        tmem_ld16(lb + slot_col(7) + 16 * ch, v);
+        tmem_ld16_pair(lb + slot_col(0) + 16 * ch, v);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] += bs;
         t_store_glb(a.s_n, D, 0, v);
@@ -554,27 +595,20 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
       {
         const float bg = vec[tcp::V_BG + f];
         wait_acc(A_GX);
-        tmem_ld16(lb + slot_col(8) + 16 * ch, v);
+        tmem_ld16_pair(lb + slot_col(1) + 16 * ch, v);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] += bg;
+        publish(&sm.sgx_read);                // slots 0 and 1 read: the last two Qhat GEMMs may overwrite them
         t_store_glb(a.gx_n, D, 0, v);
       }
-      {
-        const float bq = vec[tcp::V_BQ + f];
-        wait_acc(A_Q);
-        tmem_ld16(lb + slot_col(9) + 16 * ch, v);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += bq;
-        t_store_opnd(sm.actH, v);             // every MMA that read the hidden operand completed before acc_done[DOWN]
-        publish(&sm.opnd_ready);
-        t_store_glb(a.q_n, D, 0, v);
-      }
+      // ---- 5. Qhat_h: the eight small GEMMs are issued back to back; stream them out as they complete
 #pragma unroll 1
       for (int h = 0; h < H; ++h) {
         wait_acc(A_QH + h);
-        tmem_ld16(lb + slot_col(qh_slot(h)) + 16 * ch, v);
+        tmem_ld16_pair(lb + slot_col(qh_slot(h)) + 16 * ch, v);
         t_store_glb(a.qhat_n, (size_t)H * D, h * D, v);
       }
+      PSW_EMARK(13);
     }
   }
   tc::fence_before_sync();

@@ -73,20 +73,29 @@ class GraphedForward:
         model = self.model
         ent = _Entry()
         ent.batch = synthetic.clone_batch(batch, model.device)[0]
-        ent.plan = model._plan(ent.batch)
+        # The graph bakes in device addresses.  Everything it touches therefore belongs to this entry: a PRIVATE index plan
+        # (never shared through the model's plan cache -- every replay overwrites its device maps in place) and a PRIVATE
+        # set of model work buffers (the model replaces a buffer when a larger batch arrives, which would free memory an
+        # earlier graph still reads and writes).
+        ent.plan = model._plan(ent.batch, private=True)
         ent.inputs = _tensors(ent.batch)
         pristine = [t.clone() for t in ent.inputs]
-        cur = torch.cuda.current_stream()
-        side = torch.cuda.Stream()
-        side.wait_stream(cur)
-        with torch.cuda.stream(side), torch.no_grad():
-            for _ in range(2):              # warm-up: allocates every model buffer, sets kernel attributes
-                model.forward(ent.batch, mode)
-        cur.wait_stream(side)
-        torch.cuda.synchronize()
-        ent.graph = torch.cuda.CUDAGraph()
-        with torch.no_grad(), torch.cuda.graph(ent.graph):
-            ent.out = model.forward(ent.batch, mode)[model.tasks[0]]
+        saved_bufs, ent.bufs = model._bufs, {}
+        model._bufs = ent.bufs
+        try:
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side), torch.no_grad():
+                for _ in range(2):              # warm-up: allocates every model buffer, sets kernel attributes
+                    model.forward(ent.batch, mode)
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            ent.graph = torch.cuda.CUDAGraph()
+            with torch.no_grad(), torch.cuda.graph(ent.graph):
+                ent.out = model.forward(ent.batch, mode)[model.tasks[0]]
+        finally:
+            model._bufs = saved_bufs
         for dst, src in zip(ent.inputs, pristine):
             dst.copy_(src)
         return ent

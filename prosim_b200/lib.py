@@ -20,7 +20,7 @@ SYMBOLS = (
 )
 
 KERNEL_CLASSES = {'pointnet': 0, 'radius': 1, 'knn': 2, 'edge_pe': 3, 'attn_kv': 4, 'attn_dstpre': 5, 'attn_edge': 6,
-                  'attn_post': 7, 'head': 8, 'mlp2': 9, 'state': 10, 'edge_qk': 11, 'edge_av': 12}
+                  'attn_post': 7, 'head': 8, 'mlp2': 9, 'state': 10, 'edge_qk': 11, 'edge_av': 12, 'attn_post_sw': 13}
 
 
 class Graph(Structure):
@@ -147,3 +147,4 @@ def set_tensor_core(on):
 def set_stack_split(parts):
     """Row-split chains of the fixed-source attention stacks (1 = single stream, the default; bit-identical results)."""
     call('prosim_set_stack_split', int(parts))
+

@@ -34,38 +34,33 @@ class _Plan:
     pass
 
 
-class _RolloutTrajs(Mapping):
-    """``rollout_trajs`` of the reference (traj_sam.py:582-593): {"b-id": {traj [steps,4], init_pos [2], init_heading [1],
-    vel [steps,2]}} as views of the state buffers.  The per-agent views are created on first access (all of them with four
-    ``unbind`` calls when iterated) instead of 8 Python indexing ops per agent per forward -- 35 ms at 4096 agents."""
+class _RolloutTrajs(dict):
+    """``rollout_trajs`` of the reference (traj_sam.py:582-593): {"b-id": {traj [steps, 4], init_pos [2], init_heading [1],
+    vel [steps, 2]}} as views of the state buffers.  A real ``dict`` (the reference returns one) that fills itself on first
+    use: the per-agent views come from four ``unbind`` calls instead of 8 Python indexing ops per agent per forward (35 ms
+    at 4096 agents), and a caller that only reads ``_state`` never pays for them."""
 
-    def __init__(self, names, rows, st):
-        self._names, self._rows, self._st = names, [int(r) for r in rows], st
-        self._index = None
-        self._all = None
+    def __init__(self, names, rows, st, last_step=None):
+        super().__init__()
+        self._names, self._rows, self._st = list(names), [int(r) for r in rows], st
+        self._last = int(last_step) if last_step is not None else st['traj'].shape[2]
+        self._filled = False
 
-    def _materialise(self):
-        if self._all is None:
+    def _fill(self):
+        if not self._filled:
+            self._filled = True
             st = self._st
             T = st['traj'].shape[2]
-            traj = st['traj'].view(-1, T, 4)[:, HIST:].unbind(0)
-            vel = st['vel'].view(-1, T, 2)[:, HIST:].unbind(0)
+            traj = st['traj'].view(-1, T, 4)[:, HIST:self._last].unbind(0)
+            vel = st['vel'].view(-1, T, 2)[:, HIST:self._last].unbind(0)
             pos = st['init_pos'].view(-1, 2).unbind(0)
             head = st['init_heading'].view(-1, 1).unbind(0)
-            self._all = {n: {'traj': traj[r], 'init_pos': pos[r], 'init_heading': head[r], 'vel': vel[r]}
-                         for n, r in zip(self._names, self._rows)}
-        return self._all
+            dict.update(self, {n: {'traj': traj[r], 'init_pos': pos[r], 'init_heading': head[r], 'vel': vel[r]}
+                               for n, r in zip(self._names, self._rows)})
+        return self
 
     def __getitem__(self, name):
-        if self._all is not None:
-            return self._all[name]
-        if self._index is None:
-            self._index = {n: r for n, r in zip(self._names, self._rows)}
-        r = self._index[name]
-        st = self._st
-        T = st['traj'].shape[2]
-        return {'traj': st['traj'].view(-1, T, 4)[r, HIST:], 'init_pos': st['init_pos'].view(-1, 2)[r],
-                'init_heading': st['init_heading'].view(-1, 1)[r], 'vel': st['vel'].view(-1, T, 2)[r, HIST:]}
+        return dict.__getitem__(self._fill(), name)
 
     def __iter__(self):
         return iter(self._names)
@@ -73,11 +68,31 @@ class _RolloutTrajs(Mapping):
     def __len__(self):
         return len(self._names)
 
+    def __contains__(self, name):
+        return dict.__contains__(self._fill(), name)
+
+    def get(self, name, default=None):
+        return dict.get(self._fill(), name, default)
+
+    def keys(self):
+        return dict.keys(self._fill())
+
     def items(self):
-        return self._materialise().items()
+        return dict.items(self._fill())
 
     def values(self):
-        return self._materialise().values()
+        return dict.values(self._fill())
+
+    def __repr__(self):
+        return dict.__repr__(self._fill())
+
+
+def _norm_device(device):
+    """'cuda' -> 'cuda:<current>' (tensor.device always carries an index; comparisons need one too)."""
+    d = torch.device(device)
+    if d.type == 'cuda' and d.index is None and torch.cuda.is_available():
+        d = torch.device('cuda', torch.cuda.current_device())
+    return d
 
 
 def _pad4(a):
@@ -97,6 +112,8 @@ class ProSimB200(nn.Module):
         self.use_condition = len(cfg.PROMPT.CONDITION.TYPES) > 0
         self.cond_types = tuple(cfg.PROMPT.CONDITION.TYPES)
         self.rollout_steps = cfg.ROLLOUT.POLICY.REPLAN_FREQ
+        self.rollout_top_k = cfg.ROLLOUT.POLICY.TOP_K                  # traj_sam.py:25-26
+        self.rollout_top_k_train = cfg.ROLLOUT.POLICY.TOP_K_TRAIN
         self.hist_step = cfg.DATASET.FORMAT.HISTORY.STEPS
         assert self.rollout_steps == STEP and self.hist_step == HIST and cfg.DATASET.FORMAT.TARGET.STEPS == STEP
         self.num_layers = cfg.MODEL.POLICY.ACT_DECODER.ATTN.NUM_LAYER
@@ -106,12 +123,15 @@ class ProSimB200(nn.Module):
         # generator with the reference's shapes ([P, 1, 10, 2] per tick), noise_fn can be replaced to inject given draws
         self.noise_std = float(cfg.MODEL.POLICY.ACT_DECODER.RANDOM_NOISE_STD)
         self.noise_fn = lambda shape: torch.randn(shape, device=self._device, dtype=torch.float32)
-        self._device = torch.device(device if device is not None else 'cuda')
+        self._device = _norm_device(device if device is not None else 'cuda')
         self._sd = None
         self._arena = None
         self._off = None
         self._bufs = {}
         self._plan_cache = []
+        # the reference's sub-module handles (traj_sam.py:28-57) as far as the rollout drives them from outside
+        self.scene_encoder = SceneEncoderB200(self)
+        self.policy = PolicyB200(self)
         used = [t for t in cfg.PROMPT.CONDITION.MOTION_TAG.USED_TAGS if t in weights.V_ACTION_TAG_ID]   # condition_encoders.py:58
         if 'v_action_tag' in self.cond_types and tuple(used) != weights.V_ACTION_TAGS:
             raise NotImplementedError('PROMPT.CONDITION.MOTION_TAG.USED_TAGS differs from the released list')
@@ -132,25 +152,59 @@ class ProSimB200(nn.Module):
         return dict(self._sd)
 
     def load_state_dict(self, state_dict, strict=True, assign=False):
-        want = [n for n, _, _ in weights.param_specs(self.cond_types, self.num_layers, self.cond_layers)]
+        """Same contract as nn.Module.load_state_dict: strict raises on missing / unexpected keys; strict=False (how the
+        reference loads its checkpoints, trainer.py:162-163) keeps the current value of a missing parameter (the seeded
+        initialisation before the first load) and ignores unexpected keys; both lists are returned."""
+        specs = weights.param_specs(self.cond_types, self.num_layers, self.cond_layers)
+        want = [n for n, _, _ in specs]
         missing = [k for k in want if k not in state_dict]
         unexpected = [k for k in state_dict if k not in set(want)]
-        if missing or (strict and unexpected):
-            raise RuntimeError(f'load_state_dict: missing {missing[:5]} unexpected {unexpected[:5] if strict else []}')
-        self._sd = {k: state_dict[k].detach().float().cpu().clone() for k in want}
+        if strict and (missing or unexpected):
+            raise RuntimeError(f'load_state_dict: missing {missing[:5]} unexpected {unexpected[:5]}')
+        bad = [k for k, shp, _ in specs if k in state_dict and tuple(state_dict[k].shape) != tuple(shp)]
+        if bad:
+            raise RuntimeError(f'load_state_dict: size mismatch for {bad[:5]}')
+        base = self._sd if self._sd is not None else (weights.random_state_dict(0, self.cond_types) if missing else {})
+        self._sd = {k: (state_dict[k] if k in state_dict else base[k]).detach().float().cpu().clone() for k in want}
         arena, self._off = weights.pack_model(self._sd, self.num_layers, self.cond_layers)
         lib.load()  # fail loudly here, not at the first kernel call, if the native library is absent
         self._arena = arena.to(self._device)
         return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
 
     def to(self, device=None, *a, **k):
-        if device is not None and torch.device(device) != self._device:
-            self._device = torch.device(device)
+        """Moves the packed weight arena; dtype arguments are rejected (the path computes in fp32 only)."""
+        if isinstance(device, torch.dtype) or k.get('dtype') is not None or any(isinstance(x, torch.dtype) for x in a):
+            raise NotImplementedError('ProSimB200 computes in fp32; no other dtype is built')
+        if device is not None and _norm_device(device) != self._device:
+            if torch.device(device).type != 'cuda':
+                raise lib.ProSimLibError('ProSimB200 runs on CUDA devices only (no CPU path)')
+            self._device = _norm_device(device)
             self._arena = self._arena.to(self._device)
             self._bufs = {}
+            self._plan_cache = []
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device('cuda', device) if isinstance(device, int) else (device or 'cuda'))
+
+    def half(self):
+        return self.to(torch.float16)
+
+    def bfloat16(self):
+        return self.to(torch.bfloat16)
+
+    def double(self):
+        return self.to(torch.float64)
+
+    def float(self):
         return self
 
     def eval(self):
+        return self
+
+    def train(self, mode=True):
+        if mode:
+            raise NotImplementedError('ProSimB200 is an inference (rollout) model; training is out of scope')
         return self
 
     def _note_edges(self, kind, edges, n_layers):
@@ -168,12 +222,55 @@ class ProSimB200(nn.Module):
         return b[:n].view(shape)
 
     # ------------------------------------------------------------------ bookkeeping
-    def _plan(self, batch):
-        if getattr(batch, '_b200_plan', None) is not None:
+    def _check_batch(self, batch):
+        """The kernels hard-code the released data format (24 features x 11 steps per agent, 11 features x 19 vectors per
+        polyline; config.check_supported pins the config side): any other layout is rejected here instead of being read
+        out of bounds on the device."""
+        ex = batch.extras
+        obs, mp = ex['init_obs'], ex['init_map']
+        prm = ex['prompt'][self.tasks[0]]
+
+        def chk(t, name, tail, dtype, lead=None):
+            if not isinstance(t, torch.Tensor):
+                raise TypeError(f'{name} must be a tensor')
+            if tuple(t.shape[len(t.shape) - len(tail):]) != tuple(tail) or (lead is not None and tuple(t.shape[:len(lead)]) != tuple(lead)):
+                raise ValueError(f'{name}: shape {tuple(t.shape)} does not end in {tuple(tail)} (leading {lead})')
+            if t.dtype not in (dtype if isinstance(dtype, tuple) else (dtype,)):
+                raise TypeError(f'{name}: dtype {t.dtype}, expected {dtype}')
+            if not t.is_contiguous():
+                raise ValueError(f'{name} must be contiguous')
+            if t.device != self._device:
+                raise lib.ProSimLibError(f'{name} is on {t.device}, the model on {self._device} (batch.to(device) first; no CPU path)')
+
+        B, A = obs['input'].shape[:2]
+        M = mp['input'].shape[1]
+        N = prm['prompt_mask'].shape[1]
+        bmask = (torch.bool, torch.uint8)
+        for name, d in [('init_obs', obs)] + [(f'fut_obs[{t}]', ex['fut_obs'][t]) for t in ex['fut_obs'].keys()]:
+            chk(d['input'], f'{name}.input', (HIST, 24), torch.float32, (B, A))
+            chk(d['mask'], f'{name}.mask', (HIST, 24), bmask, (B, A))
+            chk(d['position'], f'{name}.position', (2,), torch.float32, (B, A))
+            chk(d['heading'], f'{name}.heading', (A,), torch.float32, (B,))
+        chk(mp['input'], 'init_map.input', (19, 11), torch.float32, (B, M))
+        chk(mp['mask'], 'init_map.mask', (19,), bmask, (B, M))
+        chk(mp['position'], 'init_map.position', (1, 2), torch.float32, (B, M))
+        chk(mp['heading'], 'init_map.heading', (1,), torch.float32, (B, M))
+        chk(prm['prompt'], 'prompt.prompt', (7,), torch.float32, (B, N))
+        chk(prm['prompt_mask'], 'prompt.prompt_mask', (N,), bmask, (B,))
+        chk(prm['position'], 'prompt.position', (2,), torch.float32, (B, N))
+        chk(prm['heading'], 'prompt.heading', (1,), torch.float32, (B, N))
+        chk(prm['agent_type'], 'prompt.agent_type', (N,), torch.int64, (B,))
+
+    def _plan(self, batch, private=False):
+        """private: build a plan that is neither looked up in nor added to the plan cache and owns its device index maps
+        (GraphedForward overwrites them in place on every replay)."""
+        if getattr(batch, '_b200_plan', None) is not None and not private:
             return batch._b200_plan
         ex = batch.extras
         obs, mp = ex['init_obs'], ex['init_map']
         prm = ex['prompt'][self.tasks[0]]
+        if obs['input'].is_cuda:
+            self._check_batch(batch)
         pl = _Plan()
         pl.all_t = sorted(int(t) for t in ex['all_t_indices'].cpu().numpy().tolist())
         pl.B, pl.A = obs['input'].shape[:2]
@@ -190,7 +287,7 @@ class ProSimB200(nn.Module):
         id_lists = [obs['agent_ids'], prm['agent_ids']] + [f['agent_ids'] for f in futs]
         sig = (B, A, M, N, tuple(pl.all_t), str(self._device))
         mask_bytes = flat.tobytes()
-        for ent in self._plan_cache:
+        for ent in ([] if private else self._plan_cache):
             if ent[0] == sig and ent[1] == mask_bytes and len(ent[2]) == len(id_lists) and \
                     all(a is b or a == b for a, b in zip(ent[2], id_lists)):
                 batch._b200_plan = ent[3]
@@ -202,6 +299,7 @@ class ProSimB200(nn.Module):
 
         ids = prm['agent_ids']
         pl.policy_ids = ids
+        pl.obs_id_lists = [obs['agent_ids']] + [f['agent_ids'] for f in futs]
         n_b = np.array([len(x) for x in ids], dtype=np.int64)
         for b in range(B):
             if not (pm[b, :n_b[b]].all() and not pm[b, n_b[b]:].any()):
@@ -277,8 +375,9 @@ class ProSimB200(nn.Module):
         pl.steps = len(pl.all_t) * STEP
         pl.T = HIST + pl.steps
         batch._b200_plan = pl
-        self._plan_cache.insert(0, (sig, mask_bytes, id_lists, pl))
-        del self._plan_cache[4:]
+        if not private:
+            self._plan_cache.insert(0, (sig, mask_bytes, id_lists, pl))
+            del self._plan_cache[4:]
         return pl
 
     # ------------------------------------------------------------------ reference API
@@ -287,9 +386,10 @@ class ProSimB200(nn.Module):
         if not batch.extras['init_obs']['input'].is_cuda:
             raise lib.ProSimLibError('ProSimB200 needs the batch on the GPU (batch.to(device)); there is no CPU path')
         self.mode = mode
-        scene_embs = self.encode_scene(batch)
-        prompt_encs = self.encode_prompt(batch)
-        return self.decode_batch(scene_embs, prompt_encs, batch, mode)
+        with torch.cuda.device(self._device):        # every launch goes to this device's current stream
+            scene_embs = self.encode_scene(batch)
+            prompt_encs = self.encode_prompt(batch)
+            return self.decode_batch(scene_embs, prompt_encs, batch, mode)
 
     def decode_batch(self, scene_embs, prompt_encs, batch, mode):
         """traj_sam.py:103-116."""
@@ -332,14 +432,12 @@ class ProSimB200(nn.Module):
         for i in range(self.num_layers):
             ops.attn_layer(xa, xa, e_a, ar, off['enc_a2a'] + i * lf, out=xa, workspace=ws)
             ops.attn_layer(tok, tok, e_s, ar, off['enc_s2s'] + i * lf, out=tok, workspace=ws)
-        # built from the already-uploaded index arrays: no pageable H2D copy (it would stall the host behind the encoder)
-        sb = pl.i['tok_scene'].long()
-        st = torch.cat([torch.zeros(NM, dtype=torch.long, device=self._device),
-                        torch.ones(NA, dtype=torch.long, device=self._device)])
         pl.edges_enc = (e_a, e_s)
-        return {'obs_mask': obs['mask'].all(-1).any(-1), 'map_mask': mp['mask'].any(-1), 'scene_batch_idx': sb,
-                'scene_type': st, 'scene_pos': tok_pos, 'scene_ori': tok_ori.view(-1, 1), 'scene_tokens': tok,
-                'max_map_num': pl.M, 'max_agent_num': pl.A, '_plan': pl}
+        # the reference's flat arrays (scene_tokens / scene_pos / scene_ori / scene_batch_idx / scene_type, map rows first)
+        # are views / concatenations made on first access (_SceneEmbs); the model itself uses the private entries
+        return _SceneEmbs({'obs_mask': obs['mask'].all(-1).any(-1), 'map_mask': mp['mask'].any(-1),
+                           'max_map_num': pl.M, 'max_agent_num': pl.A, '_plan': pl, '_tok': tok, '_tok_pos': tok_pos,
+                           '_tok_ori': tok_ori, '_agent': (tok[NM:], tok_pos[NM:], tok_ori[NM:]), '_slot': 0, '_shared': {}})
 
     def encode_prompt(self, batch, prompt_dict={}):
         """traj_sam.py:79-101 -> prompt_encoder/base.py:37-50 (MLP on the valid prompt rows)."""
@@ -371,8 +469,11 @@ class ProSimB200(nn.Module):
             x_p = enc['_emd_flat'] if '_emd_flat' in enc else enc['prompt_emd'].reshape(-1, D)[rows].contiguous()
             p_pos = enc['position'].reshape(-1, 2)[rows].contiguous()
             p_ori = enc['heading'].reshape(-1)[rows].contiguous()
-            tok, tok_pos = scene_embs['scene_tokens'], scene_embs['scene_pos']
-            tok_ori = scene_embs['scene_ori'].reshape(-1)
+            if scene_embs.get('_slot', 0) == 0 and '_tok' in scene_embs:
+                tok, tok_pos, tok_ori = scene_embs['_tok'], scene_embs['_tok_pos'], scene_embs['_tok_ori']
+            else:
+                tok, tok_pos = scene_embs['scene_tokens'], scene_embs['scene_pos']
+                tok_ori = scene_embs['scene_ori'].reshape(-1)
             S = tok.shape[0]
             cap = dcfg.MAX_NUM_NEIGH
             e_pp = ops.radius_edges(p_pos, pl.i['p_scene'], p_pos, pl.i['seg_prompt'].view(-1, 4), dcfg.PROMPT_RADIUS, cap,
@@ -457,7 +558,9 @@ class ProSimB200(nn.Module):
         return emd_flat + x_c
 
     def init_agent_trajs(self, policy_agent_ids, batch, all_t_indices=None):
-        """traj_sam.py:597-633 (3-argument form accepted for rollout/gpu_utils.py:196)."""
+        """traj_sam.py:597-633 (3-argument form accepted for rollout/gpu_utils.py:196).  The trajectory buffers are
+        preallocated for the whole rollout ([B, N, 11 + steps, 4]; the reference grows them with torch.cat each tick):
+        ``last_step`` says how many steps are valid, exactly like the reference's ``a_traj[task]['last_step']``."""
         pl = self._plan(batch)
         obs = batch.extras['init_obs']
         R = pl.B * pl.N
@@ -472,98 +575,381 @@ class ProSimB200(nn.Module):
               'last_step': HIST}
         return {task: st for task in self.tasks}
 
+    def _select_k_emd_from_batch(self, policy_emds, batch):
+        """traj_sam.py:402-439.  One policy token per agent (DECODER.GOAL_PRED disabled, emd [B, N, D]): nothing to select.
+        With K goal-conditioned tokens per agent (emd [B, N, K, D] + goal_prob / goal_point, e.g. handed over by a sampler
+        model): inference picks uniformly among the top-``ROLLOUT.POLICY.TOP_K`` goal probabilities, training the token
+        whose goal point is closest to the ground-truth goal -- index bookkeeping, torch ops like the reference."""
+        if policy_emds['emd'].ndim == 3:
+            return policy_emds
+        goal_prob, goal_point = policy_emds['goal_prob'], policy_emds['goal_point']
+        B, N, K, Dm = policy_emds['emd'].shape
+        if self.mode == 'train':
+            gt_goal = batch.extras['io_pairs_batch']['goal'][:, 0, :]
+            goal_idxs = torch.norm(goal_point - gt_goal[:, :, None, :], dim=-1).min(dim=-1)[1]
+        else:
+            rollout_k = min(self.rollout_top_k, K)
+            top = torch.topk(goal_prob, rollout_k, dim=-1)[1]
+            rand_idxs = torch.randint(0, rollout_k, (B, N,)).to(device=self._device)
+            goal_idxs = torch.gather(top, -1, rand_idxs[..., None]).squeeze(-1)
+        policy_emds = dict(policy_emds)
+        policy_emds.pop('_emd_flat', None)
+        policy_emds['select_idx'] = goal_idxs
+        policy_emds['emd'] = torch.gather(policy_emds['emd'], -2, goal_idxs[..., None, None].repeat(1, 1, 1, Dm)).squeeze(-2)
+        policy_emds['goal'] = torch.gather(goal_point, -2, goal_idxs[..., None, None].repeat(1, 1, 1, 2)).squeeze(-2)
+        return policy_emds
+
     def rollout_batch(self, batch, scene_embs, policy_emds, policy_agent_ids, agent_trajs, all_t_indices, mode):
-        """traj_sam.py:144-175 (tick loop) + 205-274 step_env + 178-202 decode_output + 276-349 step_agent_traj
-        + 562-595 _process_rollout."""
+        """traj_sam.py:144-175: the closed-loop tick loop, written against the same four methods as the reference
+        (step_env -> decode_output -> step_agent_traj, then _process_rollout), so a caller may drive the ticks itself."""
+        self.mode = mode if mode is not None else self.mode
+        task = self.tasks[0]
+        policy_emds = dict(policy_emds)
+        policy_emds[task] = self._select_k_emd_from_batch(policy_emds[task], batch)
+        all_t = [int(t) for t in all_t_indices]
+        pl = self._plan(batch)
+        pl.tick_edges = []
+        self._last_plan = pl
+        model_outputs = []
+        for t in all_t:
+            scene_embs, agent_positions = self.step_env(scene_embs, agent_trajs, batch, policy_agent_ids, t, all_t)
+            model_output = self.decode_output(policy_emds, scene_embs, policy_agent_ids, batch, agent_positions, t, None)
+            agent_trajs = self.step_agent_traj(agent_trajs, model_output, policy_agent_ids, t, mode)
+            model_outputs.append(model_output)
+        return self._process_rollout(agent_trajs, model_outputs, policy_agent_ids)
+
+    def step_env(self, scene_embs, a_traj, batch, policy_agent_ids, t, all_t_indices):
+        """traj_sam.py:205-274: current world pose of every policy agent; for every tick but the first of
+        ``all_t_indices`` the agents' 11-step observation windows are rebuilt in the frame of their last step, written
+        into ``batch.extras['fut_obs'][t]`` in place (like the reference) and re-encoded (``_update_scene_emb``).
+        Returns (scene_embs of this tick, agent positions {'position' [B, N, 2], 'heading' [B, N, 1]})."""
         task = self.tasks[0]
         pl = self._plan(batch)
-        ar, off = self._arena, self._off
-        ex = batch.extras
-        obs = ex['init_obs']
-        lf = weights.ATTN_LAYER_FLOATS
-        L = self.num_layers
-        acfg = self.config.MODEL.POLICY.ACT_DECODER.ATTN
-        P, NM, T = pl.P, pl.NM, pl.T
-        st = agent_trajs[task]
+        self._last_plan = pl
+        st = a_traj[task]
+        T = st['traj'].shape[2]
+        tidx = int(st['last_step'])
         traj, vel = st['traj'].view(-1, T, 4), st['vel'].view(-1, T, 2)
         init_pos, init_heading = st['init_pos'].view(-1, 2), st['init_heading'].view(-1)
-        tok = scene_embs['scene_tokens']
-        tok_pos, tok_ori = scene_embs['scene_pos'], scene_embs['scene_ori'].reshape(-1)
-        pe = policy_emds[task]
+        p_pos, p_ori = self._buf('p_pos', (pl.P, 2)), self._buf('p_ori', (pl.P,))
+        all_t = [int(x) for x in all_t_indices]
+        t_idx = all_t.index(int(t))                  # the reference decides "first tick" by position in the list it was given
+        if t_idx == 0:
+            ops.step_env(traj, vel, init_pos, init_heading, pl.i['p_row'], pl.i['p_slot0'], T, tidx, p_pos, p_ori)
+            scene_embs_next = scene_embs
+        else:
+            i = pl.all_t.index(int(t))               # plan slot of this tick's fut_obs (index maps, valid-agent rows)
+            fut = batch.extras['fut_obs'][t]
+            ops.step_env(traj, vel, init_pos, init_heading, pl.i['p_row'], pl.i[f'p_slot{i}'], T, tidx, p_pos, p_ori,
+                         fut=(fut['input'], fut['mask'], fut['position'], fut['heading']))
+            old_obs = batch.extras['fut_obs'][all_t[t_idx - 1]] if t_idx > 1 else batch.extras['init_obs']
+            scene_embs_next = self._update_scene_emb(scene_embs, fut, old_obs['agent_ids'], _slot=i)
+        return scene_embs_next, _AgentPositions(p_pos, p_ori, pl)
+
+    def _update_scene_emb(self, last_scene_embs, batch_obs_new, old_obs_agent_ids, _slot=None):
+        """traj_sam.py:541-550 (the reference clones every tensor of the dict first; nothing is modified in place here)."""
+        return self.scene_encoder.update_scene_emb(last_scene_embs, batch_obs_new, old_obs_agent_ids, _slot=_slot)
+
+    def decode_output(self, policy_emds, scene_embs, policy_agent_ids, batch, agent_positions=None, target_t=None,
+                      latent_state_dict=None):
+        """traj_sam.py:178-202: gather the per-row policy inputs of this tick and run the policy."""
+        task = list(policy_emds.keys())[0]
+        batch_policy_emd, batch_obs, batch_map, batch_pos, batch_pair_names = self._get_policy_batch_input(
+            batch, policy_agent_ids[task], policy_emds[task], scene_embs, agent_positions, target_t)
+        latent_state = None if latent_state_dict is None else self.policy.format_latent_state(latent_state_dict, [batch_pair_names])
+        all_output = self.get_action(batch_policy_emd, batch_obs, batch_map, batch_pos, [batch_pair_names], latent_state=latent_state)
+        all_output['pair_names'] = batch_pair_names
+        all_output['_p_row'] = self._plan(batch).i['p_row']
+        return {task: all_output}
+
+    def _get_policy_batch_input(self, batch, policy_agent_ids, policy_emds, scene_embs, agent_positions, target_t):
+        """traj_sam.py:441-525 for the rollout case (agent_positions given): one row per (scene, policy agent).  The
+        reference scatters the flat scene tokens into dense [B, S, 128] tensors which the policy immediately re-flattens
+        (act_decoder.py:224-237); here the flat tokens are handed over as they are, with per-scene ranges."""
+        if agent_positions is None:
+            raise NotImplementedError('open-loop decoding from io_pairs_batch is the training path (out of scope)')
+        pl = self._plan(batch)
         rows = pl.i['p_row'].long()
-        emd_flat = pe['_emd_flat'] if '_emd_flat' in pe else pe['emd'].reshape(-1, D)[rows].contiguous()
-        a_type = pe['agent_type'].reshape(-1)[rows].to(torch.int32).contiguous()
-        dim_t = ar[off['dim_t16']:off['dim_t16'] + 16]
-        n_ticks = len(all_t_indices)
-        max_na = max(pl.NA)
+        emd_flat = policy_emds['_emd_flat'] if '_emd_flat' in policy_emds else policy_emds['emd'].reshape(-1, D)[rows].contiguous()
+        if '_atype_flat' not in policy_emds:
+            policy_emds['_atype_flat'] = policy_emds['agent_type'].reshape(-1)[rows].to(torch.int32).contiguous()
+        batch_policy_emd = {'emd': emd_flat, 'agent_type': policy_emds['_atype_flat'], 'batch_idx': pl.i['p_scene'],
+                            '_cache': policy_emds}
+        for key in ('goal', 'goal_prob', 'goal_point', 'select_idx'):
+            if key in policy_emds:
+                batch_policy_emd[key] = policy_emds[key].reshape((-1,) + tuple(policy_emds[key].shape[2:]))[rows]
+        if isinstance(agent_positions, _AgentPositions):
+            batch_pos = {'position': agent_positions.p_pos, 'heading': agent_positions.p_ori.view(-1, 1)}
+        else:
+            batch_pos = {key: agent_positions[key].reshape(pl.B * pl.N, -1)[rows].contiguous() for key in ('position', 'heading')}
+        slot = scene_embs.get('_slot', 0)
+        x_a, a_pos, a_ori = scene_embs['_agent']
+        NM = pl.NM
+        batch_obs = {'tokens': x_a, 'pos': a_pos, 'ori': a_ori, 'seg': pl.i[f'seg_agent{slot}'].view(-1, 4), 'max_per_scene': pl.max_a}
+        batch_map = {'tokens': scene_embs['_tok'][:NM], 'pos': scene_embs['_tok_pos'][:NM], 'ori': scene_embs['_tok_ori'][:NM],
+                     'seg': pl.i['seg_map'].view(-1, 4), 'max_per_scene': pl.max_m, '_cache': scene_embs['_shared']}
+        if '_names' not in policy_emds:
+            policy_emds['_names'] = [f'{b}-{a}' for b, ids in enumerate(policy_agent_ids) for a in ids]
+        batch_pair_names = [f'{n}-{target_t}' for n in policy_emds['_names']]
+        return batch_policy_emd, batch_obs, batch_map, batch_pos, batch_pair_names
 
-        x_m, m_pos, m_ori = tok[:NM], tok_pos[:NM], tok_ori[:NM]
-        kv_m = ops.attn_kv(x_m, ar, off['pol_m2p'], L, lf, kv=self._buf('kv_m', (L, NM, 2 * D)))
-        stride_a = min(acfg.MAX_NUM_NEIGH, max(pl.max_a, 1))
-        stride_m = min(acfg.MAX_NUM_NEIGH, max(pl.max_m, 1))
-        nbr_a, deg_a = self._buf('nbr_a', (P * stride_a,), torch.int32), self._buf('deg_a', (P,), torch.int32)
-        nbr_m, deg_m = self._buf('nbr_m', (P * stride_m,), torch.int32), self._buf('deg_m', (P,), torch.int32)
-        z_a, z_m = self._buf('z_a', (P * stride_a, 96)), self._buf('z_m', (P * stride_m, 96))
-        self._buf('kv_a', (L, max_na, 2 * D))
-        x_a_buf = self._buf('x_a', (max_na, D))
-        a_pos_buf, a_ori_buf = self._buf('a_pos', (max_na, 2)), self._buf('a_ori', (max_na,))
-        p_pos, p_ori = self._buf('p_pos', (P, 2)), self._buf('p_ori', (P,))
-        fuse = self._buf('fuse', (P, D))
-        ws = self._buf('attn_ws', (lib.load().prosim_attn_workspace_floats(P, 0, max(stride_a, stride_m)),))
-        motion_pred = torch.empty(n_ticks, P, 1, STEP, 5, device=self._device)
-        tidx = int(st['last_step'])
-        pl.tick_edges = []
+    def get_action(self, policy_emb, obs_data, map_data, pos_data, pair_names, latent_state=None):
+        """traj_sam.py:635-640."""
+        pair_names_all = []
+        for pair_name in pair_names:
+            pair_names_all += pair_name
+        return self.policy(policy_emb, obs_data, map_data, pos_data, pair_names_all, latent_state)
 
-        for k, t in enumerate(all_t_indices):
-            i = pl.all_t.index(int(t))  # plan slot of this tick (a caller may roll out a sub-range of ticks)
-            na = pl.NA[i]
-            if i == 0:
-                ops.step_env(traj, vel, init_pos, init_heading, pl.i['p_row'], pl.i['p_slot0'], T, tidx, p_pos, p_ori)
-                x_a, a_pos, a_ori = tok[NM:], tok_pos[NM:], tok_ori[NM:]
-            else:
-                fut = ex['fut_obs'][t]
-                ops.step_env(traj, vel, init_pos, init_heading, pl.i['p_row'], pl.i[f'p_slot{i}'], T, tidx, p_pos, p_ori,
-                             fut=(fut['input'], fut['mask'], fut['position'], fut['heading']))
-                x_a, a_pos, a_ori = x_a_buf[:na], a_pos_buf[:na], a_ori_buf[:na]
-                ops.pointnet(0, fut['input'], fut['mask'], pl.i[f'agent_rows{i}'], ar, off['obs_enc'], out=x_a, tc_off=off['obs_enc_tc'])
-                ops.gather_pose(fut['position'], fut['heading'], pl.i[f'agent_rows{i}'], a_pos, a_ori)
-            e_a = ops.radius_edges(p_pos, pl.i['p_scene'], a_pos, pl.i[f'seg_agent{i}'].view(-1, 4), acfg.AGENT_RADIUS,
-                                   acfg.MAX_NUM_NEIGH, stride_a, nbr=nbr_a, deg=deg_a)
-            e_m = ops.radius_edges(p_pos, pl.i['p_scene'], m_pos, pl.i['seg_map'].view(-1, 4), acfg.MAP_RADIUS,
-                                   acfg.MAX_NUM_NEIGH, stride_m, nbr=nbr_m, deg=deg_m)
-            e_m.warps_per_row = 2     # map radius 50 m: a policy row typically sees ~40 of the scene's polylines
-            ops.edge_pe(e_a, p_pos, p_ori, a_pos, a_ori, dim_t, z=z_a)
-            ops.edge_pe(e_m, p_pos, p_ori, m_pos, m_ori, dim_t, z=z_m)
-            kva = ops.attn_kv(x_a, ar, off['pol_a2p'], L, lf, kv=self._buf('kv_a', (L, na, 2 * D)))
-            ops.attn_stack(emd_flat, L, ops.stack_side(ar, off['pol_a2p'], e_a, kva),
-                           ops.stack_side(ar, off['pol_m2p'], e_m, kv_m), out=fuse, workspace=ws)
-            self._note_edges('pol_a2p', e_a, L)
-            self._note_edges('pol_m2p', e_m, L)
-            noise = self.noise_fn((P, 1, STEP, 2)) if self.noise_std > 0 else None
-            ops.policy_head(fuse, a_type, ar, off['head'], motion_pred=motion_pred[k], noise=noise, noise_std=self.noise_std)
-            if self.noise_std > 0:       # traj_sam.py:313: the (degenerate, TOP_K = 1) mode draw still advances the generator
-                torch.randint(0, 1, (P,), device=self._device)
-            ops.step_agent_traj(motion_pred[k], pl.i['p_row'], T, tidx, traj, vel)
-            tidx += STEP
-            if getattr(self, 'keep_tick_edges', False):
-                pl.tick_edges.append((e_a.to_edge_index(), e_m.to_edge_index()))
-        st['last_step'] = tidx
-        reconst = ops.reconst(emd_flat, ar, off['head'])
-        return self._process_rollout(pl, st, motion_pred, reconst, all_t_indices)
-
-    def _process_rollout(self, pl, st, motion_pred, reconst, all_t):
-        """traj_sam.py:562-595: concatenate per-tick outputs, per-agent views of the state buffers."""
+    def step_agent_traj(self, a_traj, model_output, policy_agent_ids, t, mode):
+        """traj_sam.py:276-349: rotate the 10 predicted steps into each agent's t0 frame and append them.  Rows are matched
+        by position (row p of the policy output is policy agent p of the plan; the reference searches the pair-name strings)."""
         task = self.tasks[0]
-        n_ticks, P = motion_pred.shape[:2]
-        res = {'motion_pred': motion_pred.view(n_ticks * P, 1, STEP, 5),
-               'motion_prob': torch.ones(n_ticks * P, 1, device=self._device),
-               'reconst_pred': reconst.repeat(n_ticks, 1)}
-        names, agent_names = [], []
-        for b, ids in enumerate(pl.policy_ids):
-            agent_names += [f'{b}-{a}' for a in ids]
-        for t in all_t:
-            names += [f'{n}-{t}' for n in agent_names]
-        res['pair_names'] = names
-        res['rollout_trajs'] = _RolloutTrajs(agent_names, pl.p_b * pl.N + pl.p_n, st)
+        out = model_output[task]
+        st = a_traj[task]
+        B, N, T = st['traj'].shape[:3]
+        tidx = int(st['last_step'])
+        if tidx + STEP > T:            # a caller-made buffer without room: grow it like the reference's torch.cat
+            grow = tidx + STEP - T
+            st['traj'] = torch.cat([st['traj'], torch.zeros(B, N, grow, 4, device=self._device)], dim=2)
+            st['vel'] = torch.cat([st['vel'], torch.zeros(B, N, grow, 2, device=self._device)], dim=2)
+            T = tidx + STEP
+        motion_pred = out['motion_pred']
+        P = motion_pred.shape[0]
+        rollout_k = self.rollout_top_k_train if mode == 'train' else self.rollout_top_k
+        rollout_k = min(rollout_k, motion_pred.shape[1])
+        if rollout_k > 1 or self.noise_std > 0:       # traj_sam.py:311-313 (the draw also keeps the generator stream aligned)
+            top = torch.topk(out['motion_prob'], rollout_k, dim=1)[1]
+            rand_idxs = torch.randint(0, rollout_k, (P,), device=self._device)
+            if motion_pred.shape[1] > 1:
+                sel = top[torch.arange(P, device=self._device), rand_idxs]
+                motion_pred = motion_pred[torch.arange(P, device=self._device), sel][:, None]
+        p_row = out.get('_p_row')
+        if p_row is None:
+            p_row = self._buf_rows(policy_agent_ids[task], N)
+        ops.step_agent_traj(motion_pred.contiguous(), p_row, T, tidx, st['traj'].view(-1, T, 4), st['vel'].view(-1, T, 2))
+        st['last_step'] = tidx + STEP
+        return a_traj
+
+    def _buf_rows(self, agent_ids, N):
+        key = tuple(len(x) for x in agent_ids) + (N,)
+        cache = self.__dict__.setdefault('_rows_cache', {})
+        if key not in cache:
+            rows = np.concatenate([b * N + np.arange(len(ids)) for b, ids in enumerate(agent_ids)]).astype(np.int32)
+            cache[key] = torch.from_numpy(rows).to(self._device)
+        return cache[key]
+
+    def _process_rollout(self, agent_trajs, model_outputs, policy_agent_ids):
+        """traj_sam.py:562-595: concatenate the per-tick outputs; per-agent views of the state buffers."""
+        task = self.tasks[0]
+        st = agent_trajs[task]
+        res = {}
+        for key in ('motion_pred', 'motion_prob', 'goal', 'pair_names', 'goal_prob', 'goal_point', 'select_idx', 'reconst_pred'):
+            if key not in model_outputs[0][task]:
+                continue
+            if key == 'pair_names':
+                res[key] = [n for mo in model_outputs for n in mo[task][key]]
+            else:
+                res[key] = torch.cat([mo[task][key] for mo in model_outputs], dim=0)
+        N = st['traj'].shape[1]
+        agent_names = [f'{b}-{a}' for b, ids in enumerate(policy_agent_ids[task]) for a in ids]
+        rows = np.concatenate([b * N + np.arange(len(ids)) for b, ids in enumerate(policy_agent_ids[task])]) \
+            if agent_names else np.zeros(0, np.int64)
+        res['rollout_trajs'] = _RolloutTrajs(agent_names, rows, st, int(st['last_step']))
         res['_state'] = st
         return {task: res}
+
+
+class _AgentPositions(Mapping):
+    """``a_pos`` of traj_sam.py:209-215: {'position': [B, N, 2], 'heading': [B, N, 1]}.  The kernels produce the poses of the P
+    policy rows; the dense [B, N] tensors are scattered on first access (only a caller outside the model ever asks)."""
+
+    def __init__(self, p_pos, p_ori, pl):
+        self.p_pos, self.p_ori, self._pl, self._dense = p_pos, p_ori, pl, {}
+
+    def __getitem__(self, key):
+        if key not in ('position', 'heading'):
+            raise KeyError(key)
+        if key not in self._dense:
+            pl = self._pl
+            w = 2 if key == 'position' else 1
+            out = torch.zeros(pl.B * pl.N, w, device=self.p_pos.device)
+            out[pl.i['p_row'].long()] = (self.p_pos if key == 'position' else self.p_ori.view(-1, 1))
+            self._dense[key] = out.view(pl.B, pl.N, w)
+        return self._dense[key]
+
+    def __iter__(self):
+        return iter(('position', 'heading'))
+
+    def __len__(self):
+        return 2
+
+
+class _SceneEmbs(dict):
+    """Scene-embedding dict of the reference (scene_encoder/base.py:31-46, attn_fusion.py:205-236).  The model keeps map
+    tokens and agent tokens in separate buffers (map tokens are never copied between ticks); the reference's flat
+    ``scene_tokens / scene_pos / scene_ori / scene_batch_idx / scene_type`` arrays (map rows first, then agent rows) are
+    concatenated on first access."""
+    _LAZY = ('scene_tokens', 'scene_pos', 'scene_ori', 'scene_batch_idx', 'scene_type', 'obs_mask')
+
+    def __missing__(self, key):
+        if key not in self._LAZY:
+            raise KeyError(key)
+        pl, NM = self['_plan'], self['_plan'].NM
+        x_a, a_pos, a_ori = self['_agent']
+        slot = self.get('_slot', 0)
+        dev = x_a.device
+        if key == 'obs_mask':
+            val = self['_obs_mask_src'].all(-1).any(-1)
+        elif key == 'scene_tokens':
+            val = torch.cat([self['_tok'][:NM], x_a])
+        elif key == 'scene_pos':
+            val = torch.cat([self['_tok_pos'][:NM], a_pos])
+        elif key == 'scene_ori':
+            val = torch.cat([self['_tok_ori'][:NM], a_ori]).view(-1, 1)
+        elif key == 'scene_batch_idx':
+            seg = pl.i[f'seg_agent{slot}'].view(-1, 4)[:, 1].long()
+            val = torch.cat([pl.i['tok_scene'][:NM].long(), torch.repeat_interleave(torch.arange(pl.B, device=dev), seg)])
+        else:
+            val = torch.cat([torch.zeros(NM, dtype=torch.long, device=dev), torch.ones(x_a.shape[0], dtype=torch.long, device=dev)])
+        self[key] = val
+        return val
+
+    def get(self, key, default=None):
+        try:
+            return self[key]
+        except KeyError:
+            return default
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self._LAZY
+
+
+@registry.register_scene_encoder(name='attn_fusion_relpe_b200')
+class SceneEncoderB200(nn.Module):
+    """``model.scene_encoder`` of the reference (AttentionSceneEncoderRelPE, scene_encoder/attn_fusion.py:13-251) as far as
+    the rollout drives it: ``forward(batch)`` = encode_scene, ``update_scene_emb`` = the per-tick re-encoding of the agent
+    histories.  Holds no parameters of its own (the model owns the packed weight arena)."""
+
+    def __init__(self, model):
+        super().__init__()
+        object.__setattr__(self, '_m', model)
+
+    def forward(self, batch):
+        return self._m.encode_scene(batch)
+
+    def update_scene_emb(self, scene_emds, batch_obs, old_obs_agent_ids, _slot=None):
+        """attn_fusion.py:238-251 with OBS_UPDATE.FUSION = 'replace': the agent tokens become the PointNet encoding of the
+        new observation windows, the map tokens are untouched (attn_fusion.py:205-236 re-concatenates the flat arrays; here
+        the new agent tokens simply live in their own buffer)."""
+        m = self._m
+        pl = scene_emds['_plan']
+        if _slot is None:           # called from outside the model: find the tick this observation belongs to
+            _slot = next((i for i, ids in enumerate(pl.obs_id_lists) if i > 0 and (ids is batch_obs['agent_ids'] or ids == batch_obs['agent_ids'])), None)
+            if _slot is None:
+                raise ValueError('update_scene_emb: batch_obs is not one of the fut_obs entries this batch was planned with')
+        na = pl.NA[_slot]
+        max_na = max(pl.NA)
+        x_a = m._buf('x_a', (max_na, D))[:na]
+        a_pos, a_ori = m._buf('a_pos', (max_na, 2))[:na], m._buf('a_ori', (max_na,))[:na]
+        rows = pl.i[f'agent_rows{_slot}']
+        ops.pointnet(0, batch_obs['input'], batch_obs['mask'], rows, m._arena, m._off['obs_enc'], out=x_a, tc_off=m._off['obs_enc_tc'])
+        ops.gather_pose(batch_obs['position'], batch_obs['heading'], rows, a_pos, a_ori)
+        out = _SceneEmbs({k: v for k, v in dict.items(scene_emds) if k not in _SceneEmbs._LAZY})
+        out['_agent'] = (x_a, a_pos, a_ori)
+        out['_slot'] = _slot
+        out['_obs_mask_src'] = batch_obs['mask']
+        out['max_agent_num'] = batch_obs['input'].shape[1]
+        return out
+
+
+@registry.register_policy(name='rel_pe_temporal_b200')
+class PolicyB200(nn.Module):
+    """``model.policy`` of the reference (Policy_RelPE_Temporal -> PolicyNoRNN -> AttnRelPE -> ActDecoder; policy/base.py:9-23,
+    temporal_ar.py:66-92, act_decoder.py:78-135, :239-279): one policy tick for P rows."""
+
+    def __init__(self, model):
+        super().__init__()
+        object.__setattr__(self, '_m', model)
+
+    def format_latent_state(self, latent_state_dict, all_batch_pair_names):
+        return None                 # PolicyNoRNN keeps no recurrent state (temporal_ar.py:71-73)
+
+    def forward(self, policy_emd, batch_obs, batch_map, batch_pos, pair_names, latent_state):
+        m = self._m
+        ar, off = m._arena, m._off
+        lf = weights.ATTN_LAYER_FLOATS
+        L = m.num_layers
+        acfg = m.config.MODEL.POLICY.ACT_DECODER.ATTN
+        dev = m._device
+        batch_obs, batch_map = _flat_tokens(batch_obs, dev), _flat_tokens(batch_map, dev)
+        emd = policy_emd['emd']
+        P = emd.shape[0]
+        p_scene = policy_emd['batch_idx'].to(torch.int32)
+        a_type = policy_emd['agent_type'].to(torch.int32)
+        p_pos = batch_pos['position'].reshape(P, 2).contiguous()
+        p_ori = batch_pos['heading'].reshape(P).contiguous()
+        dim_t = ar[off['dim_t16']:off['dim_t16'] + 16]
+        x_a, a_pos, a_ori = batch_obs['tokens'], batch_obs['pos'], batch_obs['ori'].reshape(-1)
+        x_m, m_pos, m_ori = batch_map['tokens'], batch_map['pos'], batch_map['ori'].reshape(-1)
+        na, nm = x_a.shape[0], x_m.shape[0]
+        stride_a = min(acfg.MAX_NUM_NEIGH, max(int(batch_obs['max_per_scene']), 1))
+        stride_m = min(acfg.MAX_NUM_NEIGH, max(int(batch_map['max_per_scene']), 1))
+        # map-side K'|V' of all layers: the map tokens and the weights never change during a rollout, so they are computed
+        # once per scene encoding and reused by every tick (the reference recomputes them 8 times)
+        cache = batch_map.get('_cache')
+        kv_m = None if cache is None else cache.get('kv_m')
+        if kv_m is None:
+            kv_m = ops.attn_kv(x_m, ar, off['pol_m2p'], L, lf, kv=m._buf('kv_m', (L, nm, 2 * D)))
+            if cache is not None:
+                cache['kv_m'] = kv_m
+        nbr_a, deg_a = m._buf('nbr_a', (P * stride_a,), torch.int32), m._buf('deg_a', (P,), torch.int32)
+        nbr_m, deg_m = m._buf('nbr_m', (P * stride_m,), torch.int32), m._buf('deg_m', (P,), torch.int32)
+        z_a, z_m = m._buf('z_a', (P * stride_a, 96)), m._buf('z_m', (P * stride_m, 96))
+        e_a = ops.radius_edges(p_pos, p_scene, a_pos, batch_obs['seg'], acfg.AGENT_RADIUS, acfg.MAX_NUM_NEIGH, stride_a,
+                               nbr=nbr_a, deg=deg_a)
+        e_m = ops.radius_edges(p_pos, p_scene, m_pos, batch_map['seg'], acfg.MAP_RADIUS, acfg.MAX_NUM_NEIGH, stride_m,
+                               nbr=nbr_m, deg=deg_m)
+        e_m.warps_per_row = 2     # map radius 50 m: a policy row typically sees ~40 of the scene's polylines
+        ops.edge_pe(e_a, p_pos, p_ori, a_pos, a_ori, dim_t, z=z_a)
+        ops.edge_pe(e_m, p_pos, p_ori, m_pos, m_ori, dim_t, z=z_m)
+        kva = ops.attn_kv(x_a, ar, off['pol_a2p'], L, lf, kv=m._buf('kv_a', (L, na, 2 * D)))
+        fuse = m._buf('fuse', (P, D))
+        ws = m._buf('attn_ws', (lib.load().prosim_attn_workspace_floats(P, 0, max(stride_a, stride_m)),))
+        ops.attn_stack(emd, L, ops.stack_side(ar, off['pol_a2p'], e_a, kva), ops.stack_side(ar, off['pol_m2p'], e_m, kv_m),
+                       out=fuse, workspace=ws)
+        m._note_edges('pol_a2p', e_a, L)
+        m._note_edges('pol_m2p', e_m, L)
+        noise = m.noise_fn((P, 1, STEP, 2)) if m.noise_std > 0 else None
+        motion_pred = ops.policy_head(fuse, a_type, ar, off['head'], noise=noise, noise_std=m.noise_std)
+        result = {'motion_pred': motion_pred, 'motion_prob': torch.ones(P, 1, device=dev)}
+        if m.config.LOSS.ROLLOUT_TRAJ.USE_GOAL_PRED_LOSS:
+            pc = policy_emd.get('_cache')
+            rc = None if pc is None else pc.get('_reconst')     # pred_mlp(emd) does not depend on the tick
+            if rc is None:
+                rc = ops.reconst(emd, ar, off['head'])
+                if pc is not None:
+                    pc['_reconst'] = rc
+            result['reconst_pred'] = rc
+        for key in ('goal', 'goal_prob', 'goal_point'):
+            if key in policy_emd:
+                result[key] = policy_emd[key]
+        result['latent_state'] = latent_state
+        if getattr(m, 'keep_tick_edges', False):
+            pl = getattr(m, '_last_plan', None)
+            if pl is not None:
+                pl.tick_edges.append((e_a.to_edge_index(), e_m.to_edge_index()))
+        return result
+
+
+def _flat_tokens(d, dev):
+    """Policy-side token set: the model's flat form {'tokens' [n, 128], 'pos' [n, 2], 'ori' [n], 'seg' int32 [B, 4],
+    'max_per_scene'} passes through; the reference's dense form {'input' [B, S, 128], 'mask' [B, S], 'pos' [B, S, 2],
+    'ori' [B, S, 1]} (traj_sam.py:356-400) is flattened by its mask the way act_decoder.py:224-237 does."""
+    if 'tokens' in d:
+        return d
+    mask = d['mask'].bool()
+    cnt = mask.sum(dim=1).cpu()
+    off = torch.cumsum(cnt, 0) - cnt
+    seg = torch.stack([off, cnt, torch.zeros_like(cnt), torch.zeros_like(cnt)], dim=1).to(torch.int32).to(dev)
+    return {'tokens': d['input'][mask].contiguous(), 'pos': d['pos'][mask].contiguous(), 'ori': d['ori'][mask].reshape(-1).contiguous(),
+            'seg': seg, 'max_per_scene': int(cnt.max()) if cnt.numel() else 0}

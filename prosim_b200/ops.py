@@ -24,6 +24,9 @@ def _chk(t, dtype, name):
         return
     if not t.is_cuda:
         raise lib.ProSimLibError(f'{name} must be a CUDA tensor (no CPU fallback on this path)')
+    if t.device.index != torch.cuda.current_device():
+        raise lib.ProSimLibError(f'{name} lives on {t.device} but the current device is cuda:{torch.cuda.current_device()} '
+                                 '(the kernels launch on the current device\'s stream)')
     if t.dtype != dtype:
         raise TypeError(f'{name}: expected {dtype}, got {t.dtype}')
     if not t.is_contiguous():
@@ -208,16 +211,25 @@ def cond_pool(emb, slot):
 
 
 def init_traj(obs_in, obs_pos, obs_head, p_slot, p_row, T, traj, vel, init_pos, init_heading):
+    for t, n in ((obs_in, 'obs input'), (obs_pos, 'obs position'), (obs_head, 'obs heading'), (traj, 'traj'), (vel, 'vel'),
+                 (init_pos, 'init_pos'), (init_heading, 'init_heading')):
+        _chk(t, torch.float32, n)
+    _chk(p_slot, torch.int32, 'p_slot'), _chk(p_row, torch.int32, 'p_row')
     lib.call('prosim_init_traj', ptr(obs_in), ptr(obs_pos), ptr(obs_head), ptr(p_slot), ptr(p_row), p_row.shape[0], int(T),
              ptr(traj), ptr(vel), ptr(init_pos), ptr(init_heading), _stream())
 
 
 def step_env(traj, vel, init_pos, init_heading, p_row, p_slot, T, tidx, p_pos, p_ori, fut=None):
     """fut: None on the first tick, else (input, mask, position, heading) tensors of fut_obs[t] (written in place)."""
+    for t, n in ((traj, 'traj'), (vel, 'vel'), (init_pos, 'init_pos'), (init_heading, 'init_heading'), (p_pos, 'p_pos'),
+                 (p_ori, 'p_ori')):
+        _chk(t, torch.float32, n)
+    _chk(p_row, torch.int32, 'p_row'), _chk(p_slot, torch.int32, 'p_slot')
     f_in = f_mask = f_pos = f_head = None
     if fut is not None:
         f_in, f_mask, f_pos, f_head = fut
         f_mask = as_u8(f_mask)
+        _chk(f_mask, torch.uint8, 'fut mask')
         for t, n in ((f_in, 'fut input'), (f_pos, 'fut position'), (f_head, 'fut heading')):
             _chk(t, torch.float32, n)
     lib.call('prosim_step_env', ptr(traj), ptr(vel), ptr(init_pos), ptr(init_heading), ptr(p_row), ptr(p_slot),
@@ -226,11 +238,16 @@ def step_env(traj, vel, init_pos, init_heading, p_row, p_slot, T, tidx, p_pos, p
 
 
 def gather_pose(pos, head, rows, out_pos, out_ori):
-    _chk(pos, torch.float32, 'pos'), _chk(head, torch.float32, 'head')
+    _chk(pos, torch.float32, 'pos'), _chk(head, torch.float32, 'head'), _chk(rows, torch.int32, 'rows')
+    _chk(out_pos, torch.float32, 'out_pos'), _chk(out_ori, torch.float32, 'out_ori')
     lib.call('prosim_gather_pose', ptr(pos), ptr(head), ptr(rows), rows.shape[0], ptr(out_pos), ptr(out_ori), _stream())
 
 
 def step_agent_traj(motion_pred, p_row, T, tidx, traj, vel):
+    _chk(motion_pred, torch.float32, 'motion_pred'), _chk(traj, torch.float32, 'traj'), _chk(vel, torch.float32, 'vel')
+    _chk(p_row, torch.int32, 'p_row')
+    if motion_pred.numel() != p_row.shape[0] * 50:
+        raise ValueError('motion_pred must hold [P, 1, 10, 5] values')
     lib.call('prosim_step_agent_traj', ptr(motion_pred), ptr(p_row), p_row.shape[0], int(T), int(tidx), ptr(traj), ptr(vel),
              _stream())
 

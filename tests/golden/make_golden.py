@@ -20,7 +20,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle import ref_shim  # noqa: E402
 from prosim_b200 import synthetic, weights  # noqa: E402
 
-from tests.helpers import CASES, cond_suffix, to_double as _to_double  # noqa: E402
+from tests.helpers import BENCH_CASES, CASES, cond_suffix, to_double as _to_double  # noqa: E402
 
 
 def _collect(out, ids):
@@ -40,7 +40,8 @@ def _collect(out, ids):
 def main():
     torch.set_num_threads(os.cpu_count())
     only = sys.argv[1:]                      # optional: regenerate just the named cases
-    cases = {n: c for n, c in CASES.items() if not only or n in only}
+    keep = {n: c[2] for n, c in BENCH_CASES.items()}
+    cases = {n: c[:2] for n, c in list(CASES.items()) + list(BENCH_CASES.items()) if not only or n in only}
     models = {}
     for goal in dict.fromkeys(c[1] for c in cases.values()):
         sd = weights.random_state_dict(0, goal)
@@ -71,6 +72,16 @@ def main():
         res['traj64'], res['vel64'], res['motion_pred64'] = r64['traj'], r64['vel'], r64['motion_pred']
         gap = np.abs(res['traj'][..., :2].astype(np.float64) - res['traj64'][..., :2]).reshape(len(res['traj']), -1, 10, 2)
         print(name, 'fp32-vs-fp64 xy gap per tick:', ['%.1e' % g for g in gap.max(axis=(0, 2, 3))])
+        if name in keep:                     # large batch: keep the rows of a few scenes of THIS run (file size)
+            scenes = [int(n.split('-')[0]) for n in res['agent_names']]
+            rows = np.array([i for i, sc in enumerate(scenes) if sc in keep[name]])
+            P = len(scenes)
+            pair_rows = np.concatenate([rows + k * P for k in range(len(res['pair_names']) // P)])
+            for k in ('traj', 'vel', 'init_pos', 'init_heading', 'agent_names', 'traj64', 'vel64'):
+                res[k] = res[k][rows]
+            for k in ('motion_pred', 'motion_prob', 'reconst_pred', 'pair_names', 'motion_pred64'):
+                res[k] = res[k][pair_rows]
+            res['rows'], res['n_rows'] = rows, np.array(P)
         np.savez_compressed(os.path.join(HERE, name + '.npz'), **res)
 
 

@@ -25,6 +25,14 @@ CASES = {
 }
 
 
+# The benchmarked shape (bench.py: scenes x 128 agents x 512 polylines x 80 steps): 8 scenes = 1024 policy rows, so every
+# launch takes the kernels the bench workload runs (tcgen05 node kernels, policy_head2_kernel).  The golden holds the rows of
+# KEEP_SCENES of the reference's own B = 8 run (fp32 and fp64): name -> (make_batch kwargs, condition types, kept scenes)
+BENCH_CASES = {
+    'bench_b8_a128_m512_s80': (dict(n_scenes=8, n_agents=128, n_map=512, steps=80), False, (0, 3, 7)),
+}
+
+
 def cond_suffix(cond):
     """File-name suffix of the per-model fixtures."""
     return '' if not cond else '_goal' if cond is True else '_' + '_'.join(cond)

@@ -288,10 +288,12 @@ def test_tensor_core_chunk_pipeline_is_race_free(ctx):
 
 
 # ------------------------------------------------------------------------------------ heads
-def test_policy_head_and_reconst_match_oracle(ctx):
+@pytest.mark.parametrize('P', [45, 1024, 4100])
+def test_policy_head_and_reconst_match_oracle(ctx, P):
+    """P = 45: policy_head_kernel (per-thread weight loads); P >= 1024: policy_head2_kernel (weights through the
+    shared-memory stream), the kernel every launch of the bench workload takes."""
     ops, orc = ctx['ops'], ctx['oracle']
     g = torch.Generator().manual_seed(17)
-    P = 45
     feat, emd = torch.randn(P, 128, generator=g), torch.randn(P, 128, generator=g)
     a_type = torch.randint(1, 4, (P,), generator=g)
     ref = orc.policy_head(feat, a_type, emd)
