@@ -10,7 +10,9 @@
  * Conventions: every pointer is a DEVICE pointer owned by the caller (PyTorch's allocator on the Python
  * side); nothing is allocated, freed or retained; calls only ENQUEUE work on `stream` and return
  * 0 on success, a positive cudaError_t on a launch failure, or a negative value for a bad argument.
- * All functions are re-entrant; there is no global state besides one-time kernel attribute setup.
+ * The data-path functions keep no state besides one-time per-device kernel attribute setup and a per-host-thread cache of
+ * encoded TMA descriptors.  The measurement / A-B switches (prosim_set_tensor_core, prosim_set_stack_split,
+ * prosim_profile_enable, prosim_launch_count) ARE process-global by design: set them from one thread, not mid-forward.
  * Index arrays are int32, masks are uint8 (torch.bool), floats are IEEE fp32.
  */
 #ifndef PROSIM_B200_H
@@ -47,10 +49,11 @@ typedef struct {
 } prosim_stack_side_t;
 
 int prosim_abi_version(void);
-/* Tensor-core kernels: 1 (default) = tcgen05 / TMEM 3xTF32 for the node-side GEMMs of the AttentionLayer (csrc/tc_post.cuh,
- * launches of >= 1024 rows), the K'|V' projections (csrc/kv_tc.cuh) and the PointNet encoders (csrc/pointnet_tc.cuh);
- * 0 = fp32 FFMA kernels everywhere (A/B measurement and parity cross-checks).  Other values select kernels by bit
- * (1 node kernel, 2 K'|V', 4 PointNet) for fault isolation. */
+/* Tensor-core kernels: 1 (default) = tcgen05 / TMEM 3xTF32 for the node-side GEMMs of the AttentionLayer (launches of
+ * >= 1024 rows: csrc/post_sw.cuh, 32 rows per CTA, up to 9472 rows; csrc/tc_post.cuh, 128 rows per CTA, above), the K'|V'
+ * projections (csrc/kv_tc.cuh) and the PointNet encoders (csrc/pointnet_tc.cuh); 0 = fp32 FFMA kernels everywhere (A/B
+ * measurement and parity cross-checks).  Other values select kernels by bit (1 node kernels, 2 K'|V', 4 PointNet, 8 allow
+ * the 32-row node kernel) for fault isolation.  PROCESS-GLOBAL switch. */
 int prosim_set_tensor_core(int on);
 /* prosim_attn_stack_fwd with fixed sources on both sides runs as up to `parts` (1..4, default 1) independent row chains of
  * >= 1024 rows on internal side streams (forked from / joined to the caller's stream with events; capturable in a CUDA
@@ -168,6 +171,61 @@ int prosim_step_agent_traj(const float* motion_pred, const int32_t* p_row, int P
  * (rollout/utils.py:347-392): agent-t0-frame trajectories -> world (x, y, heading); tf = 3x3 row-major, out [P][steps][3] */
 int prosim_rollout_to_world(const float* traj, const float* init_pos, const float* init_heading, const int32_t* p_row,
                             int P, int T, int t0, int steps, const float* tf, float* out, prosim_stream_t stream);
+
+/* ---- one whole policy tick in ONE call (reference loop body traj_sam.py:159-170 ->
+ * policy/temporal_ar.py:75-92 -> act_decoder.py:239-279 attn_fuse + :78-135 _compute_traj [-> traj_sam.py:276-349]).
+ * Enqueues, on `stream`: the two radius graphs (policy rows -> agent tokens, policy rows -> map tokens), their relative
+ * PE, the agent-side K'|V' of all layers, n_layers x (a2p, m2p) attention layers, the MCG head, and -- if `traj` is given
+ * -- the state update.  Same kernels and the same bits as the per-step entry points above; what it saves is ~10 host
+ * round trips through the binding per tick.  All scratch (neighbour lists, z, K'|V' of the agents, the attention
+ * workspace) is carved from ONE caller-provided workspace of prosim_workspace_bytes(&cfg) bytes (256-byte aligned). */
+typedef struct {
+  int32_t n_policy_rows;        /* P                                                                                */
+  int32_t n_agent_tokens;       /* agent tokens of this tick (all scenes)                                           */
+  int32_t n_map_tokens;         /* map tokens (all scenes)                                                          */
+  int32_t max_agents_per_scene; /* bounds the agent neighbour-list stride: min(max_neigh, this)                     */
+  int32_t max_map_per_scene;    /* bounds the map neighbour-list stride                                             */
+  int32_t max_neigh;            /* MODEL.POLICY.ACT_DECODER.ATTN.MAX_NUM_NEIGH (768)                                 */
+  int32_t n_layers;             /* MODEL.POLICY.ACT_DECODER.ATTN.NUM_LAYER (6)                                       */
+} prosim_cfg_t;
+size_t prosim_workspace_bytes(const prosim_cfg_t* cfg);
+
+typedef struct {
+  prosim_cfg_t cfg;
+  /* policy rows (one per controlled agent) */
+  const float* emd;             /* [P][128] policy tokens (SymCoordDecoder output rows)                             */
+  const int32_t* agent_type;    /* [P] in {1,2,3}                                                                    */
+  const int32_t* p_scene;       /* [P] scene of each row                                                             */
+  const float* p_pos;           /* [P][2] current world pose of each row (prosim_step_env output)                   */
+  const float* p_ori;           /* [P]                                                                               */
+  /* agent tokens of this tick: scene_tokens rows of type 1 (attn_fusion.py:205-236) */
+  const float* x_agent;         /* [n_agent_tokens][128]                                                             */
+  const float* agent_pos;       /* [n_agent_tokens][2]                                                               */
+  const float* agent_ori;       /* [n_agent_tokens]                                                                  */
+  const int32_t* seg_agent;     /* [B][4] {start, len, 0, 0} token range of each scene                               */
+  /* map tokens: never change during a rollout */
+  const float* map_pos;         /* [n_map_tokens][2]                                                                 */
+  const float* map_ori;         /* [n_map_tokens]                                                                    */
+  const int32_t* seg_map;       /* [B][4]                                                                            */
+  const float* kv_map;          /* [n_layers][n_map_tokens][256] prosim_attn_kv(map tokens, m2p weights), once per scene */
+  /* weights (packed arena sections) */
+  const float* w_a2p;           /* n_layers x prosim_attn_layer_floats()                                             */
+  const float* w_m2p;
+  const float* w_head;          /* prosim_head_floats()                                                              */
+  const float* dim_t16;         /* FourierEmbeddingFix denominators                                                  */
+  float agent_radius, map_radius;
+  const float* noise;           /* nullable [P][10][2] standard-normal draws                                        */
+  float noise_std;
+  /* outputs */
+  float* fuse;                  /* [P][128] attn_fuse output (kept for callers that want the features)              */
+  float* motion_pred;           /* [P][10][5]                                                                        */
+  /* optional state update (prosim_step_agent_traj); traj == NULL skips it */
+  const int32_t* p_row;
+  int32_t T, tidx;
+  float* traj;
+  float* vel;
+} prosim_tick_t;
+int prosim_policy_tick(const prosim_tick_t* t, void* workspace, size_t workspace_bytes, prosim_stream_t stream);
 
 /* tcgen05 / TMEM building block under validation (csrc/tc_gemm.cuh): c[m][128] = a[m][128] * w[128][128]^T with
  * kind::tf32 tensor-core MMAs, accumulators in tensor memory; split3 = 1 selects the fp32-class 3xTF32 scheme. */

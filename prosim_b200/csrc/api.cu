@@ -362,7 +362,7 @@ int launch_post(const float* x, int n, int zd, const float* rbar, const float* a
 
 extern "C" {
 
-int prosim_abi_version(void) { return 7; }
+int prosim_abi_version(void) { return 8; }
 int prosim_tc_debug_read(long long* out32) {
   if (!out32) return ERR_ARG;
   return (int)cudaMemcpyFromSymbol(out32, tcp::g_tcp_dbg, 32 * sizeof(long long));
@@ -793,6 +793,92 @@ int prosim_rollout_to_world(const float* traj, const float* init_pos, const floa
   to_world_kernel<<<(P * steps + 255) / 256, 256, 0, S(stream)>>>(traj, init_pos, init_heading, p_row, P, T, t0, steps, tf,
                                                                   out);
   PROSIM_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---- one policy tick: scratch layout inside the caller's workspace (all offsets 256-byte aligned)
+namespace {
+struct TickWs {
+  size_t nbr_a, deg_a, nbr_m, deg_m, z_a, z_m, kv_a, attn, total;
+  int stride_a, stride_m;
+  size_t attn_floats;
+};
+inline size_t al256(size_t x) { return (x + 255) / 256 * 256; }
+bool tick_layout(const prosim_cfg_t& c, TickWs& w) {
+  if (c.n_policy_rows < 0 || c.n_agent_tokens < 0 || c.n_map_tokens < 0 || c.max_neigh <= 0 || c.n_layers <= 0) return false;
+  const size_t P = (size_t)c.n_policy_rows;
+  w.stride_a = c.max_agents_per_scene < c.max_neigh ? c.max_agents_per_scene : c.max_neigh;
+  w.stride_m = c.max_map_per_scene < c.max_neigh ? c.max_map_per_scene : c.max_neigh;
+  if (w.stride_a < 1) w.stride_a = 1;
+  if (w.stride_m < 1) w.stride_m = 1;
+  size_t off = 0;
+  w.nbr_a = off; off = al256(off + P * w.stride_a * 4);
+  w.deg_a = off; off = al256(off + P * 4);
+  w.nbr_m = off; off = al256(off + P * w.stride_m * 4);
+  w.deg_m = off; off = al256(off + P * 4);
+  w.z_a = off;   off = al256(off + P * w.stride_a * 96 * 4);
+  w.z_m = off;   off = al256(off + P * w.stride_m * 96 * 4);
+  w.kv_a = off;  off = al256(off + (size_t)c.n_layers * c.n_agent_tokens * 256 * 4);
+  w.attn_floats = prosim_attn_workspace_floats(c.n_policy_rows, 0, w.stride_a > w.stride_m ? w.stride_a : w.stride_m);
+  w.attn = off;  off = al256(off + w.attn_floats * 4);
+  w.total = off;
+  return true;
+}
+}  // namespace
+
+size_t prosim_workspace_bytes(const prosim_cfg_t* cfg) {
+  TickWs w;
+  if (!cfg || !tick_layout(*cfg, w)) return 0;
+  return w.total;
+}
+
+int prosim_policy_tick(const prosim_tick_t* t, void* workspace, size_t workspace_bytes, prosim_stream_t stream) {
+  if (!t) return ERR_ARG;
+  TickWs w;
+  if (!tick_layout(t->cfg, w)) return ERR_ARG;
+  const int P = t->cfg.n_policy_rows, L = t->cfg.n_layers;
+  if (P == 0) return 0;
+  if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return ERR_ARG;
+  if (workspace_bytes < w.total) return ERR_WORKSPACE;
+  if (!t->emd || !t->agent_type || !t->p_scene || !t->p_pos || !t->p_ori || !t->seg_agent || !t->seg_map || !t->w_a2p ||
+      !t->w_m2p || !t->w_head || !t->dim_t16 || !t->fuse || !t->motion_pred)
+    return ERR_ARG;
+  if ((t->cfg.n_agent_tokens > 0 && (!t->x_agent || !t->agent_pos || !t->agent_ori)) ||
+      (t->cfg.n_map_tokens > 0 && (!t->map_pos || !t->map_ori || !t->kv_map)))
+    return ERR_ARG;
+  uint8_t* base = static_cast<uint8_t*>(workspace);
+  int32_t* nbr_a = reinterpret_cast<int32_t*>(base + w.nbr_a);
+  int32_t* deg_a = reinterpret_cast<int32_t*>(base + w.deg_a);
+  int32_t* nbr_m = reinterpret_cast<int32_t*>(base + w.nbr_m);
+  int32_t* deg_m = reinterpret_cast<int32_t*>(base + w.deg_m);
+  float* z_a = reinterpret_cast<float*>(base + w.z_a);
+  float* z_m = reinterpret_cast<float*>(base + w.z_m);
+  float* kv_a = reinterpret_cast<float*>(base + w.kv_a);
+  float* attn = reinterpret_cast<float*>(base + w.attn);
+  const int cap = t->cfg.max_neigh;
+  if (int e = prosim_build_radius_edges(t->p_pos, t->p_scene, P, t->agent_pos, t->seg_agent, t->agent_radius, cap, 0, nbr_a,
+                                        deg_a, w.stride_a, stream)) return e;
+  if (int e = prosim_build_radius_edges(t->p_pos, t->p_scene, P, t->map_pos, t->seg_map, t->map_radius, cap, 0, nbr_m, deg_m,
+                                        w.stride_m, stream)) return e;
+  if (int e = prosim_edge_pe(t->p_pos, t->p_ori, P, t->agent_pos, t->agent_ori, nbr_a, deg_a, w.stride_a, t->dim_t16, nullptr,
+                             96, z_a, stream)) return e;
+  if (int e = prosim_edge_pe(t->p_pos, t->p_ori, P, t->map_pos, t->map_ori, nbr_m, deg_m, w.stride_m, t->dim_t16, nullptr, 96,
+                             z_m, stream)) return e;
+  const size_t kv_a_stride = (size_t)t->cfg.n_agent_tokens * 256, kv_m_stride = (size_t)t->cfg.n_map_tokens * 256;
+  if (t->cfg.n_agent_tokens > 0)
+    if (int e = prosim_attn_kv(t->x_agent, t->cfg.n_agent_tokens, t->w_a2p, aw::SIZE, L, kv_a, kv_a_stride, stream)) return e;
+  prosim_stack_side_t sa, sb;
+  sa.w = t->w_a2p; sa.kv = kv_a; sa.kv_layer_stride = kv_a_stride;
+  sa.graph = prosim_graph_t{z_a, nbr_a, deg_a, w.stride_a, w.stride_a, 96, 0};
+  sb.w = t->w_m2p; sb.kv = t->kv_map; sb.kv_layer_stride = kv_m_stride;
+  sb.graph = prosim_graph_t{z_m, nbr_m, deg_m, w.stride_m, w.stride_m, 96, 2};
+  if (int e = prosim_attn_stack_fwd(t->emd, P, L, &sa, &sb, attn, w.attn_floats, t->fuse, stream)) return e;
+  if (int e = prosim_policy_head_fwd(t->fuse, t->agent_type, P, t->w_head, t->noise, t->noise_std, t->motion_pred, stream))
+    return e;
+  if (t->traj) {
+    if (!t->vel || !t->p_row) return ERR_ARG;
+    if (int e = prosim_step_agent_traj(t->motion_pred, t->p_row, P, t->T, t->tidx, t->traj, t->vel, stream)) return e;
+  }
   return 0;
 }
 

@@ -8,7 +8,7 @@ from ctypes import POINTER, Structure, c_float, c_int, c_int32, c_size_t, c_void
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libprosim_b200.so')
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 SYMBOLS = (
     'prosim_abi_version', 'prosim_attn_layer_floats', 'prosim_pointnet_floats', 'prosim_head_floats',
@@ -16,7 +16,7 @@ SYMBOLS = (
     'prosim_build_knn_edges', 'prosim_edge_pe', 'prosim_attn_kv', 'prosim_attn_layer_fwd', 'prosim_attn_stack_fwd',
     'prosim_policy_head_fwd', 'prosim_reconst_fwd', 'prosim_mlp2_fwd', 'prosim_init_traj', 'prosim_step_env',
     'prosim_gather_pose', 'prosim_step_agent_traj', 'prosim_launch_count', 'prosim_profile_enable', 'prosim_profile_read',
-    'prosim_rollout_to_world', 'prosim_tc_gemm_test', 'prosim_set_tensor_core', 'prosim_tc_debug_read', 'prosim_set_stack_split', 'prosim_tag_embed_fwd', 'prosim_cond_pool_fwd',
+    'prosim_rollout_to_world', 'prosim_tc_gemm_test', 'prosim_set_tensor_core', 'prosim_tc_debug_read', 'prosim_set_stack_split', 'prosim_tag_embed_fwd', 'prosim_cond_pool_fwd', 'prosim_workspace_bytes', 'prosim_policy_tick',
 )
 
 KERNEL_CLASSES = {'pointnet': 0, 'radius': 1, 'knn': 2, 'edge_pe': 3, 'attn_kv': 4, 'attn_dstpre': 5, 'attn_edge': 6,
@@ -30,6 +30,19 @@ class Graph(Structure):
 
 class StackSide(Structure):
     _fields_ = [('w', c_void_p), ('kv', c_void_p), ('kv_layer_stride', c_size_t), ('graph', Graph)]
+
+
+class Cfg(Structure):
+    _fields_ = [(n, c_int32) for n in ('n_policy_rows', 'n_agent_tokens', 'n_map_tokens', 'max_agents_per_scene',
+                                       'max_map_per_scene', 'max_neigh', 'n_layers')]
+
+
+class Tick(Structure):
+    _fields_ = [('cfg', Cfg)] + [(n, c_void_p) for n in (
+        'emd', 'agent_type', 'p_scene', 'p_pos', 'p_ori', 'x_agent', 'agent_pos', 'agent_ori', 'seg_agent', 'map_pos', 'map_ori',
+        'seg_map', 'kv_map', 'w_a2p', 'w_m2p', 'w_head', 'dim_t16')] + [('agent_radius', c_float), ('map_radius', c_float),
+        ('noise', c_void_p), ('noise_std', c_float), ('fuse', c_void_p), ('motion_pred', c_void_p), ('p_row', c_void_p),
+        ('T', c_int32), ('tidx', c_int32), ('traj', c_void_p), ('vel', c_void_p)]
 
 
 class ProSimLibError(RuntimeError):
@@ -59,6 +72,7 @@ _SIGS = {
     'prosim_set_tensor_core': [c_int],
     'prosim_tc_debug_read': [_P],
     'prosim_set_stack_split': [c_int],
+    'prosim_policy_tick': [POINTER(Tick), _P, c_size_t, _P],
 }
 
 _lib = None
@@ -88,6 +102,8 @@ def load():
     lib.prosim_profile_read.argtypes = [POINTER(ctypes.c_double), POINTER(c_int)]
     lib.prosim_attn_workspace_floats.restype = c_size_t
     lib.prosim_attn_workspace_floats.argtypes = [c_int, c_int, c_int]
+    lib.prosim_workspace_bytes.restype = c_size_t
+    lib.prosim_workspace_bytes.argtypes = [POINTER(Cfg)]
     for name, sig in _SIGS.items():
         fn = getattr(lib, name)
         fn.restype = c_int

@@ -132,6 +132,7 @@ class ProSimB200(nn.Module):
         # the reference's sub-module handles (traj_sam.py:28-57) as far as the rollout drives them from outside
         self.scene_encoder = SceneEncoderB200(self)
         self.policy = PolicyB200(self)
+        self.fused_tick = True      # policy ticks through prosim_policy_tick (one C call); False = one call per kernel family
         used = [t for t in cfg.PROMPT.CONDITION.MOTION_TAG.USED_TAGS if t in weights.V_ACTION_TAG_ID]   # condition_encoders.py:58
         if 'v_action_tag' in self.cond_types and tuple(used) != weights.V_ACTION_TAGS:
             raise NotImplementedError('PROMPT.CONDITION.MOTION_TAG.USED_TAGS differs from the released list')
@@ -902,6 +903,18 @@ class PolicyB200(nn.Module):
             kv_m = ops.attn_kv(x_m, ar, off['pol_m2p'], L, lf, kv=m._buf('kv_m', (L, nm, 2 * D)))
             if cache is not None:
                 cache['kv_m'] = kv_m
+        fuse = m._buf('fuse', (P, D))
+        noise = m.noise_fn((P, 1, STEP, 2)) if m.noise_std > 0 else None
+        debug = getattr(m, 'keep_tick_edges', False) or getattr(m, 'edge_log', None) is not None or not m.fused_tick
+        if not debug:
+            # the whole tick through ONE C call (prosim_policy_tick): same kernels, same bits as the step-by-step path below
+            cfg = ops.tick_cfg(P, na, nm, batch_obs['max_per_scene'], batch_map['max_per_scene'], acfg.MAX_NUM_NEIGH, L)
+            tick_ws = m._buf('tick_ws', (ops.tick_workspace_bytes(cfg) + 256,), torch.uint8)
+            tick_ws = tick_ws[(-tick_ws.data_ptr()) % 256:]
+            motion_pred = ops.policy_tick(cfg, emd, a_type, p_scene, p_pos, p_ori, x_a, a_pos, a_ori, batch_obs['seg'], m_pos, m_ori,
+                                          batch_map['seg'], kv_m, ar, off['pol_a2p'], off['pol_m2p'], off['head'], dim_t,
+                                          acfg.AGENT_RADIUS, acfg.MAP_RADIUS, tick_ws, fuse, noise=noise, noise_std=m.noise_std)
+            return self._result(policy_emd, emd, motion_pred, latent_state)
         nbr_a, deg_a = m._buf('nbr_a', (P * stride_a,), torch.int32), m._buf('deg_a', (P,), torch.int32)
         nbr_m, deg_m = m._buf('nbr_m', (P * stride_m,), torch.int32), m._buf('deg_m', (P,), torch.int32)
         z_a, z_m = m._buf('z_a', (P * stride_a, 96)), m._buf('z_m', (P * stride_m, 96))
@@ -913,15 +926,23 @@ class PolicyB200(nn.Module):
         ops.edge_pe(e_a, p_pos, p_ori, a_pos, a_ori, dim_t, z=z_a)
         ops.edge_pe(e_m, p_pos, p_ori, m_pos, m_ori, dim_t, z=z_m)
         kva = ops.attn_kv(x_a, ar, off['pol_a2p'], L, lf, kv=m._buf('kv_a', (L, na, 2 * D)))
-        fuse = m._buf('fuse', (P, D))
         ws = m._buf('attn_ws', (lib.load().prosim_attn_workspace_floats(P, 0, max(stride_a, stride_m)),))
         ops.attn_stack(emd, L, ops.stack_side(ar, off['pol_a2p'], e_a, kva), ops.stack_side(ar, off['pol_m2p'], e_m, kv_m),
                        out=fuse, workspace=ws)
         m._note_edges('pol_a2p', e_a, L)
         m._note_edges('pol_m2p', e_m, L)
-        noise = m.noise_fn((P, 1, STEP, 2)) if m.noise_std > 0 else None
         motion_pred = ops.policy_head(fuse, a_type, ar, off['head'], noise=noise, noise_std=m.noise_std)
-        result = {'motion_pred': motion_pred, 'motion_prob': torch.ones(P, 1, device=dev)}
+        if getattr(m, 'keep_tick_edges', False):
+            pl = getattr(m, '_last_plan', None)
+            if pl is not None:
+                pl.tick_edges.append((e_a.to_edge_index(), e_m.to_edge_index()))
+        return self._result(policy_emd, emd, motion_pred, latent_state)
+
+    def _result(self, policy_emd, emd, motion_pred, latent_state):
+        m = self._m
+        ar, off = m._arena, m._off
+        P = emd.shape[0]
+        result = {'motion_pred': motion_pred, 'motion_prob': torch.ones(P, 1, device=m._device)}
         if m.config.LOSS.ROLLOUT_TRAJ.USE_GOAL_PRED_LOSS:
             pc = policy_emd.get('_cache')
             rc = None if pc is None else pc.get('_reconst')     # pred_mlp(emd) does not depend on the tick
@@ -934,10 +955,6 @@ class PolicyB200(nn.Module):
             if key in policy_emd:
                 result[key] = policy_emd[key]
         result['latent_state'] = latent_state
-        if getattr(m, 'keep_tick_edges', False):
-            pl = getattr(m, '_last_plan', None)
-            if pl is not None:
-                pl.tick_edges.append((e_a.to_edge_index(), e_m.to_edge_index()))
         return result
 
 

@@ -174,6 +174,47 @@ def policy_head(feat, agent_type, w_arena, w_off, motion_pred=None, noise=None, 
     return motion_pred
 
 
+def tick_cfg(P, n_agent, n_map, max_a, max_m, max_neigh, n_layers):
+    return lib.Cfg(int(P), int(n_agent), int(n_map), int(max_a), int(max_m), int(max_neigh), int(n_layers))
+
+
+def tick_workspace_bytes(cfg):
+    return int(lib.load().prosim_workspace_bytes(ctypes.byref(cfg)))
+
+
+def policy_tick(cfg, emd, agent_type, p_scene, p_pos, p_ori, x_a, a_pos, a_ori, seg_a, m_pos, m_ori, seg_m, kv_m, w_arena,
+                off_a2p, off_m2p, off_head, dim_t16, agent_radius, map_radius, workspace, fuse, motion_pred=None, noise=None,
+                noise_std=0.0):
+    """One policy tick through the single C entry point (include/prosim_b200.h: prosim_policy_tick); workspace: uint8 tensor
+    of at least tick_workspace_bytes(cfg) bytes.  Returns motion_pred [P, 1, 10, 5]."""
+    for t, n in ((emd, 'emd'), (p_pos, 'p_pos'), (p_ori, 'p_ori'), (x_a, 'x_a'), (a_pos, 'a_pos'), (a_ori, 'a_ori'), (m_pos, 'm_pos'),
+                 (m_ori, 'm_ori'), (kv_m, 'kv_m'), (fuse, 'fuse'), (noise, 'noise'), (dim_t16, 'dim_t16')):
+        _chk(t, torch.float32, n)
+    for t, n in ((agent_type, 'agent_type'), (p_scene, 'p_scene'), (seg_a, 'seg_agent'), (seg_m, 'seg_map')):
+        _chk(t, torch.int32, n)
+    _chk(workspace, torch.uint8, 'workspace')
+    P = cfg.n_policy_rows
+    if emd.shape[0] != P or x_a.shape[0] != cfg.n_agent_tokens or m_pos.shape[0] != cfg.n_map_tokens:
+        raise ValueError('policy_tick: tensor sizes do not match the tick configuration')
+    if noise is not None and noise.numel() != P * 20:
+        raise ValueError('noise must hold [P, 1, 10, 2] values')
+    if motion_pred is None:
+        motion_pred = torch.empty(P, 1, 10, 5, device=emd.device, dtype=torch.float32)
+    t = lib.Tick()
+    t.cfg = cfg
+    for name, val in (('emd', emd), ('agent_type', agent_type), ('p_scene', p_scene), ('p_pos', p_pos), ('p_ori', p_ori),
+                      ('x_agent', x_a), ('agent_pos', a_pos), ('agent_ori', a_ori), ('seg_agent', seg_a), ('map_pos', m_pos),
+                      ('map_ori', m_ori), ('seg_map', seg_m), ('kv_map', kv_m), ('dim_t16', dim_t16), ('noise', noise),
+                      ('fuse', fuse), ('motion_pred', motion_pred)):
+        setattr(t, name, ptr(val))
+    t.w_a2p, t.w_m2p, t.w_head = ptr(w_arena, off_a2p), ptr(w_arena, off_m2p), ptr(w_arena, off_head)
+    t.agent_radius, t.map_radius, t.noise_std = float(agent_radius), float(map_radius), float(noise_std)
+    t.p_row = t.traj = t.vel = None
+    t.T = t.tidx = 0
+    lib.call('prosim_policy_tick', ctypes.byref(t), ptr(workspace), workspace.numel(), _stream())
+    return motion_pred
+
+
 def reconst(emd, w_arena, w_off):
     _chk(emd, torch.float32, 'emd')
     out = torch.empty(emd.shape[0], 2, device=emd.device, dtype=torch.float32)

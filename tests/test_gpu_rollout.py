@@ -283,6 +283,22 @@ def test_tick_loop_driven_from_outside_equals_rollout_batch():
     assert torch.equal(again['motion_pred'], outs[-1]['motion_pred']['motion_pred'])
 
 
+def test_fused_tick_entry_point_is_bit_identical():
+    """prosim_policy_tick (the whole tick in one C call) against the same tick issued kernel family by
+    kernel family through the per-step entry points: identical bits, for FFMA-sized and tensor-core-sized launches."""
+    model = _model(False)
+    for kw in (dict(agents_per_scene=[14, 9, 21], map_per_scene=[40, 32, 25], steps=30, permute_obs=True),
+               dict(n_scenes=9, n_agents=120, n_map=70, steps=20)):
+        try:
+            model.fused_tick = True
+            a, _ = _run_gpu(kw, False)
+            model.fused_tick = False
+            b, _ = _run_gpu(kw, False)
+        finally:
+            model.fused_tick = True
+        assert torch.equal(a['motion_pred'], b['motion_pred']) and torch.equal(a['_state']['traj'], b['_state']['traj'])
+
+
 def test_batch_invariance_and_replicas():
     """A scene rolled out alone equals the same scene inside a batch bit for bit (fixed-order reductions,
     no cross-scene coupling) -- the property the multi-GPU scene sharding relies on."""

@@ -32,6 +32,24 @@ def test_library_layout_matches_packer():
     assert l.prosim_attn_workspace_floats(10, 0, 32) >= 10 * (2 * (128 + 1024 + 256) + 1024 + 128 + 256 + 16 * 32)
 
 
+def test_tick_workspace_layout():
+    """prosim_workspace_bytes(cfg): monotone in every size, 256-byte granular, rejects nonsense (no compute, no GPU)."""
+    from prosim_b200 import ops
+    base = dict(P=4096, n_agent=4096, n_map=16384, max_a=128, max_m=512, max_neigh=768, n_layers=6)
+    b0 = ops.tick_workspace_bytes(ops.tick_cfg(**base))
+    # dominated by z: P x (128 + 512) x 96 floats
+    assert b0 % 256 == 0 and b0 > 4096 * (128 + 512) * 96 * 4
+    for k in base:
+        bigger = dict(base, **{k: base[k] * 2})
+        assert ops.tick_workspace_bytes(ops.tick_cfg(**bigger)) >= b0
+    assert ops.tick_workspace_bytes(ops.tick_cfg(**dict(base, max_neigh=0))) == 0
+    # strides are capped by MAX_NUM_NEIGH
+    capped = ops.tick_workspace_bytes(ops.tick_cfg(**dict(base, max_m=100000)))
+    assert capped == ops.tick_workspace_bytes(ops.tick_cfg(**dict(base, max_m=768)))
+    import prosim_b200.model  # noqa: F401  (registers the sub-modules)
+    assert registry.get_scene_encoder('attn_fusion_relpe_b200') is not None and registry.get_policy('rel_pe_temporal_b200') is not None
+
+
 def test_pack_model_sections():
     for goal in (False, True):
         arena, off = weights.pack_model(weights.random_state_dict(0, goal))
