@@ -7,14 +7,19 @@ One "step" = one full ``model.forward(batch, 'val')`` (scene encoder + prompt en
 rollout ticks) over this rank's batch of synthetic Waymo-shaped scenes.  Workload (config.workload): the
 per-GPU shard of BASELINE.json configs[4] -- 32 scenes x 128 agents x 512 map polylines x 80 steps per GPU,
 weak scaling (256 scenes at 8 GPUs); each scene is BASELINE.json configs[2].  Scenes are independent, so ranks
-share no data-path collective (DESIGN.md "Multi-GPU").
+share no data-path collective (DESIGN.md "Multi-GPU"); the only exchange is the gather of the results (inside e2e).
 
-  value  device-resident: inputs already in HBM; CUDA events around each forward; max over ranks
-  e2e    reference-facing call with HOST buffers: pinned H2D of the batch + forward + D2H of the trajectories
+  value    device-resident: inputs already in HBM; CUDA events around each forward; L2 flushed; max over ranks
+  e2e      reference-facing call with HOST buffers: pinned H2D of the batch + the per-batch index plan rebuilt (plan cache
+           cleared every step: a stream of distinct scenes) + forward + NCCL gather to rank 0 (N > 1) + D2H of the trajectories
+  configs2 the literal BASELINE configs[2] (ONE scene, latency bound) as a line of its own: eager, CUDA graph, roofline, CPU at B = 1
+  strong_scaling  BASELINE configs[4] with the scene count fixed at 256 (256 / N scenes per GPU)
   roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md "Measurement"
 
---impl reference times the CPU restatement of the reference (oracle/prosim_oracle.py, bit-equal to the
-reference's own code on CPU) on a bounded sample of the same workload, on all host threads.
+--impl reference times the reference's own CPU implementation of the path on all host threads: the UNMODIFIED reference
+(tier A: baseline/_ref staged by baseline/install_ref.py, or /root/reference, behind oracle/ref_shim.py) when it is
+importable, else the CPU restatement oracle/prosim_oracle.py (bit-equal to it on CPU) -- on a bounded sample of the same
+workload and config.
 """
 import argparse
 import json
@@ -43,22 +48,26 @@ def parse():
     ap.add_argument('--agents', type=int, default=128)
     ap.add_argument('--map', type=int, default=512)
     ap.add_argument('--rollout-steps', type=int, default=80)
-    ap.add_argument('--ref-scenes', type=int, default=2, help='scenes per step of the CPU reference arm')
+    ap.add_argument('--ref-scenes', type=int, default=2, help='scenes per step of the CPU reference arm (bounded sample)')
     ap.add_argument('--cpu-baseline-scenes', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-single-scene', action='store_true')
-    ap.add_argument('--large-batch-scenes', type=int, default=128, help='secondary figure: scenes per forward (0 = skip)')
+    ap.add_argument('--strong-scenes', type=int, default=256, help='fixed total scene count of the strong-scaling line (0 = skip)')
     return ap.parse_args()
 
 
-def workload_name(a):
-    return (f'{a.scenes_per_gpu} scenes/GPU x {a.agents} agents x {a.map} map polylines x {a.rollout_steps}-step '
-            f'closed-loop rollout (BASELINE configs[2] scenes, configs[4] per-GPU shard)')
+def bench_config(a):
+    """The SAME dict for both arms (the driver compares them): what is computed, not how it was sampled or timed."""
+    return {'workload': (f'{a.scenes_per_gpu} scenes/GPU x {a.agents} agents x {a.map} map polylines x {a.rollout_steps}-step '
+                         f'closed-loop rollout (BASELINE configs[2] scenes, configs[4] per-GPU shard)'),
+            'scenes_per_gpu': a.scenes_per_gpu, 'agents': a.agents, 'map_polylines': a.map, 'rollout_steps': a.rollout_steps,
+            'weights': 'seeded random init under the reference state_dict names (no checkpoint ships)',
+            'scenes': 'synthetic Waymo-shaped, seeded (prosim_b200/synthetic.py, SURVEY.md section 8d)'}
 
 
 # ----------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """Samples SM clock / throttle reasons with nvidia-smi every 200 ms while the timed region runs."""
+    """Samples SM clock / throttle reasons with nvidia-smi every 100 ms while the timed region runs."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
@@ -104,42 +113,74 @@ class ClockSampler:
         return {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(mx), 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-# ----------------------------------------------------------------------------------------------- reference arm
-def time_oracle(n_scenes, agents, n_map, rsteps, repeats, warmup, first_scene=0):
-    import torch
-    from oracle.prosim_oracle import ProSimOracle
-    from prosim_b200 import synthetic, weights
-    cores = len(os.sched_getaffinity(0))
-    torch.set_num_threads(cores)
-    orc = ProSimOracle(weights.random_state_dict(0), faithful_bookkeeping=True)
-    times = []
-    for i in range(warmup + repeats):
-        batch = synthetic.make_batch(n_scenes=n_scenes, n_agents=agents, n_map=n_map, steps=rsteps,
-                                     first_scene=first_scene + i * n_scenes)
-        t0 = time.perf_counter()
-        orc.forward(batch)
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-    return times, cores
+# ----------------------------------------------------------------------------------------------- CPU reference
+class CpuReference:
+    """The reference's CPU path: tier A (the reference's own code) when its tree is importable, else the tier-B port."""
+
+    def __init__(self):
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):      # the reference prints while it builds its model: keep stdout for the JSON line
+            self._init()
+
+    def _init(self):
+        import torch
+        from oracle import ref_shim
+        from prosim_b200 import weights
+        self.cores = len(os.sched_getaffinity(0))
+        torch.set_num_threads(self.cores)
+        sd = weights.random_state_dict(0)
+        if ref_shim.reference_available():
+            self.kind = 'reference'
+            self.model, _ = ref_shim.build_reference_model(())
+            self.model.load_state_dict(sd)
+            self.what = (f'the UNMODIFIED reference ({ref_shim.REF_ROOT}) behind oracle/ref_shim.py (torch_cluster / PyG boundary '
+                         f'restated), torch fp32 eager')
+            self._fwd = lambda b: self.model.forward(b, 'val')
+        else:
+            from oracle.prosim_oracle import ProSimOracle
+            self.kind = 'port'
+            orc = ProSimOracle(sd, faithful_bookkeeping=True)
+            self.what = 'oracle port (bit-equal to the reference on CPU) with the reference\'s per-tick string bookkeeping, torch fp32 eager'
+            self._fwd = orc.forward
+
+    def time(self, n_scenes, agents, n_map, rsteps, repeats, warmup, first_scene=0):
+        import torch
+        from prosim_b200 import synthetic
+        import contextlib
+        times = []
+        with torch.no_grad(), contextlib.redirect_stdout(sys.stderr):
+            for i in range(warmup + repeats):
+                batch = synthetic.make_batch(n_scenes=n_scenes, n_agents=agents, n_map=n_map, steps=rsteps,
+                                             first_scene=first_scene + i * n_scenes)
+                t0 = time.perf_counter()
+                self._fwd(batch)
+                dt = time.perf_counter() - t0
+                if i >= warmup:
+                    times.append(dt)
+        return times
 
 
 def run_reference(a):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    times, cores = time_oracle(a.ref_scenes, a.agents, a.map, a.rollout_steps, a.steps, a.warmup)
+    ref = CpuReference()
+    times = ref.time(a.ref_scenes, a.agents, a.map, a.rollout_steps, a.steps, a.warmup)
     per_step = sum(times) / len(times)
     value = a.ref_scenes * a.agents * a.rollout_steps / per_step
-    sample = (f'{a.ref_scenes} of the {a.scenes_per_gpu} scenes of one GPU shard per step, {a.steps} steps, oracle port '
-              f'with the reference\'s per-tick string bookkeeping, torch fp32 eager, {cores} threads')
+    sample = (f'{a.ref_scenes} of the {a.scenes_per_gpu} scenes of one GPU shard per step, {a.steps} steps after {a.warmup} warm-ups; '
+              f'{ref.what}, {ref.cores} threads (agent-steps/s of the CPU path is flat in the scene count: DESIGN.md section 6)')
+    one = ref.time(1, a.agents, a.map, a.rollout_steps, repeats=3, warmup=1, first_scene=5000)
+    one_ms = 1e3 * statistics.median(one)
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps,
         'warmup': a.warmup, 'ms_per_step': per_step * 1e3, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_name(a), 'sample': sample},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': bench_config(a),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': ref.cores, 'kind': ref.kind, 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'configs2': {'workload': f'1 scene x {a.agents} agents x {a.map} polylines x {a.rollout_steps} steps (BASELINE configs[2])',
+                     'ms_per_forward': one_ms, 'value': a.agents * a.rollout_steps / (one_ms * 1e-3), 'unit': UNIT,
+                     'kind': ref.kind, 'cores': ref.cores},
     }))
 
 
@@ -158,26 +199,57 @@ def edge_kernel_bytes(edge_log):
 
 
 def ncu_traffic(kernel_key):
-    """DRAM bytes of one launch of a kernel from the committed `ncu --set full` capture (profiles/r1_kernel_traffic.json)."""
-    try:
-        t = json.load(open(os.path.join(ROOT, 'profiles', 'r1_kernel_traffic.json')))[kernel_key]
-        return t
-    except Exception:
-        return None
+    """DRAM bytes of one launch of a kernel from the committed `ncu --set full` captures (profiles/r*_kernel_traffic.json)."""
+    for name in ('r2_kernel_traffic.json', 'r1_kernel_traffic.json'):
+        try:
+            t = json.load(open(os.path.join(ROOT, 'profiles', name)))[kernel_key]
+            return t
+        except Exception:
+            continue
+    return None
 
 
-def algorithmic_flops_post(n_rows):
-    """attn_post_kernel (+ fused next-layer dst projections), 2 FLOP/MAC: Wvr' contraction 128x128, gate 128x128,
-    out-proj 128x128, FFN 128x512 + 512x128, next q/s/gx 3 x 128x128, Qhat 8 x 16x128  (DESIGN.md)."""
-    macs = 3 * 128 * 128 + 2 * 128 * 512 + 3 * 128 * 128 + 8 * 16 * 128
+def algorithmic_flops_post(n_rows, with_next=True):
+    """Node side of one AttentionLayer (+ the next layer's destination-side projections), 2 FLOP/MAC: Wvr' contraction
+    8 x 96 x 16, gate 128x128, out-proj 128x128, FFN 128x512 + 512x128, next q/s/gx 3 x 128x128, Qhat 8 x 16x128."""
+    macs = 8 * 96 * 16 + 2 * 128 * 128 + 2 * 128 * 512 + (3 * 128 * 128 + 8 * 16 * 128 if with_next else 0)
     return 2.0 * macs * n_rows
+
+
+def timed_forward(model, batch, flush=None, i=0):
+    import torch
+    if flush is not None:
+        flush.fill_(float(i))                      # evict L2 between iterations (256 MB > 126 MB L2)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = model.forward(batch, 'val')
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1), out
+
+
+def class_times(model, lib, make_batch, classes):
+    """Average launch time and launch count per kernel class over one forward each (the library's CUDA-event hooks)."""
+    import torch
+    out = {}
+    for name in classes:
+        b = make_batch()
+        lib.profile_enable(name)
+        t_fwd, _ = timed_forward(model, b)
+        ms, n = lib.profile_read()
+        lib.profile_enable(None)
+        out[name] = {'ms': ms, 'launches': n, 'forward_ms': t_fwd}
+    torch.cuda.synchronize()
+    return out
 
 
 def run_b200(a):
     import torch
     import torch.distributed as dist
     from prosim_b200 import lib, synthetic, weights
-    from prosim_b200.model import ProSimB200
+    from prosim_b200.model import HIST, ProSimB200
+    from prosim_b200.sharding import gather_rollouts, shard_scenes
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -194,6 +266,7 @@ def run_b200(a):
                                   pin_memory=True) for v in range(n_var)]
     pristine = [synthetic.clone_batch(h, dev)[0] for h in hosts]
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    my_scenes = list(range(rank * S, rank * S + S))
 
     def barrier():
         if world > 1:
@@ -202,25 +275,27 @@ def run_b200(a):
 
     def forward_device(i):
         batch, _ = synthetic.clone_batch(pristine[i % n_var])
-        flush.fill_(float(i))                      # evict L2 between iterations (256 MB > 126 MB L2)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        out = model.forward(batch, 'val')
-        e1.record()
-        e1.synchronize()
-        return e0.elapsed_time(e1), out
+        return timed_forward(model, batch, flush, i)
 
     def forward_e2e(i):
+        """Host batch in pinned memory -> device -> plan (rebuilt: cache cleared, as for a stream of distinct scenes) ->
+        forward -> [N > 1: NCCL gather of the rolled-out steps to rank 0] -> host."""
         torch.cuda.synchronize()
+        model._plan_cache.clear()
         t0 = time.perf_counter()
         batch, h2d = synthetic.clone_batch(hosts[i % n_var], dev, non_blocking=True)
         st = model.forward(batch, 'val')['motion_pred']['_state']
-        traj = st['traj'].to('cpu', non_blocking=True)
-        vel = st['vel'].to('cpu', non_blocking=True)
+        traj, vel = st['traj'][:, :, HIST:], st['vel'][:, :, HIST:]
+        if world > 1:
+            got = gather_rollouts(traj.contiguous(), vel.contiguous(), my_scenes)
+            traj, vel = got[:2] if got is not None else (None, None)
+        d2h = 0
+        if traj is not None:
+            th, vh = traj.to('cpu', non_blocking=True), vel.to('cpu', non_blocking=True)
+            d2h = th.numel() * 4 + vh.numel() * 4
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        return dt * 1e3, h2d, traj.numel() * 4 + vel.numel() * 4
+        return dt * 1e3, h2d, d2h
 
     with torch.no_grad():
         for i in range(a.warmup):
@@ -234,40 +309,33 @@ def run_b200(a):
         edge_ms, edge_n = lib.profile_read()
         lib.profile_enable(None)
         launches = lib.launch_count() - n0
-        # untimed extra forwards: edge counts of every attention launch, and the dense node kernel's share
+        # untimed extra forwards: edge counts of every attention launch, and the node kernels' launch times
         model.edge_log = []
         forward_device(0)
         edge_log, model.edge_log = model.edge_log, None
-        lib.profile_enable('attn_post')
-        t_extra = forward_device(1)[0]
-        post_ms, post_n = lib.profile_read()
-        lib.profile_enable(None)
+        ct = class_times(model, lib, lambda: synthetic.clone_batch(pristine[1])[0], ('attn_post', 'attn_post_sw'))
 
         for i in range(min(a.warmup, 2)):
             forward_e2e(i)
         barrier()
         e2e = [forward_e2e(a.warmup + i) for i in range(a.steps)]
         barrier()
+        model._plan_cache.clear()
 
+        # ---- the literal BASELINE configs[2]: ONE scene (latency bound), as a line of its own
         single = None
         if not a.no_single_scene and rank == 0:
             one = synthetic.clone_batch(synthetic.make_batch(n_scenes=1, n_agents=A, n_map=M, steps=RS), dev)[0]
-            lat = []
-            for i in range(8):
-                b1, _ = synthetic.clone_batch(one)
-                torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                model.forward(b1, 'val')
-                e1.record()
-                e1.synchronize()
-                lat.append(e0.elapsed_time(e1))
+            lat = [timed_forward(model, synthetic.clone_batch(one)[0])[0] for _ in range(13)]
             ms = statistics.median(lat[3:])
+            n1 = lib.launch_count()
+            timed_forward(model, synthetic.clone_batch(one)[0])
+            one_launches = lib.launch_count() - n1
             from prosim_b200.graph_runner import GraphedForward
             runner = GraphedForward(model)
             one_host = synthetic.make_batch(n_scenes=1, n_agents=A, n_map=M, steps=RS, pin_memory=True)
             glat = []
-            for i in range(8):
+            for i in range(13):
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
                 st1 = runner(one_host, 'val')['motion_pred']['_state']
@@ -275,29 +343,59 @@ def run_b200(a):
                 torch.cuda.synchronize()
                 glat.append((time.perf_counter() - t0) * 1e3)
             gms = statistics.median(glat[3:])
+            cls = ('attn_post', 'attn_edge', 'edge_qk', 'edge_av', 'attn_kv', 'attn_dstpre', 'pointnet', 'edge_pe', 'head', 'radius', 'knn', 'state')
+            c1 = class_times(model, lib, lambda: synthetic.clone_batch(one)[0], cls)
+            top = max(c1, key=lambda k: c1[k]['ms'])
+            model.edge_log = []
+            timed_forward(model, synthetic.clone_batch(one)[0])
+            elog1, model.edge_log = model.edge_log, None
             single = {'workload': f'1 scene x {A} agents x {M} polylines x {RS} steps (BASELINE configs[2])',
                       'ms_per_forward': ms, 'value': A * RS / (ms * 1e-3), 'unit': UNIT,
-                      'cuda_graph_e2e_ms': gms, 'cuda_graph_e2e_value': A * RS / (gms * 1e-3)}
+                      'cuda_graph_e2e_ms': gms, 'cuda_graph_e2e_value': A * RS / (gms * 1e-3), 'gpu_launches': one_launches,
+                      'kernel_ms': {k: round(v['ms'], 3) for k, v in c1.items()}, 'dominant_kernel_class': top}
+            peaks1 = {}
+            try:
+                peaks1 = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+            except Exception:
+                pass
+            ne, nb, nl = edge_kernel_bytes(elog1)
+            em = c1['attn_edge']
+            if em['launches']:
+                ach = nb / nl / (em['ms'] / em['launches'] * 1e-3) / 1e9
+                hp = peaks1.get('hbm_gbs') or 6650.0
+                single['roofline'] = {'kernel': 'attn_edge4_kernel', 'bound': 'hbm', 'achieved': ach, 'peak': hp, 'unit': 'GB/s',
+                                      'frac': ach / hp, 'traffic': None, 'share_of_step': em['ms'] / em['forward_ms'],
+                                      'note': 'one scene = 128 destination rows per launch: every kernel of this config is a '
+                                              'latency chain (one warp per row, < 1 CTA per SM); the fraction says how far '
+                                              'a 128-row launch is from streaming speed, not that HBM binds it'}
+            pm = c1['attn_post']
+            if pm['launches']:
+                fl = algorithmic_flops_post(A) / (pm['ms'] / pm['launches'] * 1e-3) / 1e12
+                fp = 148 * 128 * 2 * peaks1.get('sm_max_mhz', 1965.0) * 1e6 / 1e12
+                single['roofline_dense_kernel'] = {'kernel': 'attn_post_kernel (fp32 FFMA, launches < 1024 rows)', 'bound': 'tensor',
+                                                   'achieved': fl, 'peak': peaks1.get('bf16_tflops_sustained') or 1400.0,
+                                                   'unit': 'TFLOP/s', 'frac': fl / (peaks1.get('bf16_tflops_sustained') or 1400.0),
+                                                   'fp32_ffma_frac': fl / fp, 'share_of_step': pm['ms'] / pm['forward_ms']}
 
-        large = None
-        if a.large_batch_scenes > 0 and rank == 0 and world == 1:
-            # secondary figure: the node kernel occupies one SM per 128 rows, so a 32-scene shard uses 32 of 148 SMs of it
-            LS = a.large_batch_scenes
-            big = synthetic.clone_batch(synthetic.make_batch(n_scenes=LS, n_agents=A, n_map=M, steps=RS, first_scene=1000), dev)[0]
+        # ---- strong scaling: BASELINE configs[4] with the total scene count fixed (256 scenes / N GPUs)
+        strong = None
+        if a.strong_scenes > 0:
+            mine = shard_scenes(a.strong_scenes, world, rank)
+            big = synthetic.clone_batch(synthetic.make_batch(n_scenes=len(mine), n_agents=A, n_map=M, steps=RS,
+                                                             first_scene=10000 + mine[0]), dev)[0]
             lt = []
             for i in range(5):
                 bb, _ = synthetic.clone_batch(big)
-                torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                model.forward(bb, 'val')
-                e1.record()
-                e1.synchronize()
-                lt.append(e0.elapsed_time(e1))
-            lms = statistics.median(lt[2:])
-            large = {'workload': f'{LS} scenes x {A} agents x {M} polylines x {RS} steps in one forward (device resident)',
-                     'ms_per_forward': lms, 'value': LS * A * RS / (lms * 1e-3), 'unit': UNIT}
+                barrier()
+                lt.append(timed_forward(model, bb)[0])
             del big
+            t_strong = torch.tensor([statistics.median(lt[2:])], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t_strong, op=dist.ReduceOp.MAX)
+            sms = float(t_strong[0])
+            strong = {'workload': f'{a.strong_scenes} scenes x {A} agents x {M} polylines x {RS} steps, total fixed (BASELINE configs[4])',
+                      'scenes_per_gpu': len(mine), 'ms_per_forward': sms, 'value': a.strong_scenes * A * RS / (sms * 1e-3),
+                      'unit': UNIT, 'scaling': 'strong'}
 
     total = torch.tensor([sum(times), sum(t for t, _, _ in e2e)], device=dev, dtype=torch.float64)
     if world > 1:
@@ -313,89 +411,93 @@ def run_b200(a):
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
         except Exception:
             pass
-        # dominant kernel: attn_post_kernel (row-tile fp32 GEMMs of every attention layer).  It computes on the
-        # fp32 CUDA cores (IEEE fp32 is required for parity, DESIGN.md "Numerics"); the fraction is reported
-        # against the tensor-pipe peak the contract names AND against the fp32 FFMA peak it is actually bound by.
-        roof = None
         sm_mhz = peaks.get('sm_max_mhz', 1965.0)
         ffma_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        roof_edge = None
         if edge_n > 0:
-            # attn_edge4_kernel (z streaming + per-edge 8x96 contractions).  Arithmetic intensity
-            # 3.1 kFLOP / 448 B = 7 FLOP/B is below the fp32 machine balance (11 FLOP/B): HBM is its roofline.
+            # attn_edge4_kernel (z streaming + per-edge 8x96 contractions).  Arithmetic intensity 3.1 kFLOP / 448 B = 7 FLOP/B is
+            # below the fp32 machine balance (11 FLOP/B): HBM is its roofline.
             n_edges, n_bytes, n_launch = edge_kernel_bytes(edge_log)
             avg_ms = edge_ms / edge_n
             achieved = n_bytes / n_launch / (avg_ms * 1e-3) / 1e9
             hbm_peak = peaks.get('hbm_gbs') or 6650.0
-            roof = {'kernel': 'attn_edge4_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
-                    'frac': achieved / hbm_peak,
-                    'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6.65 TB/s',
-                    'traffic': None, 'avg_launch_ms': avg_ms, 'launches_timed': edge_n,
-                    'algorithmic_bytes_per_launch': n_bytes / n_launch, 'edges_per_forward': n_edges,
-                    'share_of_step': edge_ms / total_ms if world == 1 else None,
-                    'fp32_ffma_frac': (n_edges * 3072.0 / n_launch) / (avg_ms * 1e-3) / 1e12 / ffma_peak,
-                    'note': 'one warp per row, z tiles by TMA; issue/latency bound at 12 warps per SM (profiles/), DESIGN.md '
-                            'section 5.  Reported as THE roofline kernel because the edge phase (edge_qk + attn_edge4 + edge_av) '
-                            'is the largest share of a step (45 %); the single largest kernel class by a hair is the tcgen05 '
-                            'node kernel, reported under roofline_dense_kernel'}
+            roof_edge = {'kernel': 'attn_edge4_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
+                         'frac': achieved / hbm_peak,
+                         'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6.65 TB/s',
+                         'traffic': None, 'avg_launch_ms': avg_ms, 'launches_timed': edge_n,
+                         'algorithmic_bytes_per_launch': n_bytes / n_launch, 'edges_per_forward': n_edges,
+                         'share_of_step': edge_ms / total_ms if world == 1 else None,
+                         'fp32_ffma_frac': (n_edges * 3072.0 / n_launch) / (avg_ms * 1e-3) / 1e12 / ffma_peak,
+                         'note': 'one warp per row, z tiles by TMA (materialised LayerNorm(rel PE), 384 B per edge, re-streamed by each '
+                                 'of the 6 layers of a graph); issue / latency bound at 12 warps per SM (profiles/), DESIGN.md section 5'}
             cap = ncu_traffic('attn_edge4_kernel a2p')
             if cap is not None:
-                # the committed ncu --set full capture is ONE launch (first policy a2p layer); its algorithmic bytes are
-                # given beside it so that traffic / algorithmic compares like with like
                 a2p = [(e, n) for k, e, n, _ in edge_log if k == 'pol_a2p']
-                roof['traffic'] = cap['dram_bytes_read'] + cap['dram_bytes_write']
-                roof['traffic_launch'] = cap['launch']
+                roof_edge['traffic'] = cap['dram_bytes_read'] + cap['dram_bytes_write']
+                roof_edge['traffic_launch'] = cap['launch']
                 if a2p:
                     e, n = int(a2p[0][0]), a2p[0][1]
-                    roof['traffic_launch_algorithmic_bytes'] = e * (384 + 32 + 32) + n * (8 * 128 * 4 + 8 * 96 * 4) + e
-                roof['traffic_source'] = cap['source']
-        roof2 = None
-        if post_n > 0:
-            avg_ms = post_ms / post_n
-            # policy ticks: 12 layers x 8 ticks on S*A rows; generator: 12 layers on S*A rows; encoder: 6 on S*A and 6 on
-            # S*(A+M) rows -> average algorithmic FLOPs per launch
-            nt = RS // 10
-            rows_sum = (12 * nt + 12 + 6) * S * A + 6 * S * (A + M)
-            n_launch_step = 12 * nt + 12 + 12
-            flops_per_launch = algorithmic_flops_post(rows_sum / n_launch_step)
+                    roof_edge['traffic_launch_algorithmic_bytes'] = e * (384 + 32 + 32) + n * (8 * 128 * 4 + 8 * 96 * 4) + e
+                roof_edge['traffic_source'] = cap['source']
+        roof_post = None
+        sw = ct['attn_post_sw']
+        if sw['launches'] > 0:
+            avg_ms = sw['ms'] / sw['launches']
+            # every 32-row-kernel launch of this workload has S * A destination rows (ticks, generator, encoder agent layers)
+            flops_per_launch = algorithmic_flops_post(S * A)
             achieved = flops_per_launch / (avg_ms * 1e-3) / 1e12
             tensor_peak = peaks.get('bf16_tflops_sustained') or 1400.0
-            roof2 = {'kernel': 'attn_post_tc_kernel', 'bound': 'tensor', 'achieved': achieved, 'peak': tensor_peak,
-                    'unit': 'TFLOP/s', 'frac': achieved / tensor_peak,
-                    'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)'
-                    if peaks else 'fallback 1.4 PFLOP/s',
-                    'traffic': None,
-                    'note': 'tcgen05 kind::tf32, 3 MMAs per product (3xTF32 = fp32-class accuracy): the usable peak is 1/6 of '
-                            'the bf16 figure, and a 4096-row launch fills 32 of 148 SMs (DESIGN.md section 5)',
-                    'fp32_ffma_equiv': {'peak': ffma_peak, 'frac': achieved / ffma_peak,
-                                        'note': 'against the fp32 FFMA peak the previous CUDA-core kernel was bound by'},
-                    'avg_launch_ms': avg_ms, 'launches_timed': post_n, 'share_of_step': post_ms / t_extra
-                    if world == 1 else None}
-            cap = ncu_traffic('tcp::attn_post_tc_kernel a2p')
+            roof_post = {'kernel': 'psw::attn_post_sw_kernel', 'bound': 'tensor', 'achieved': achieved, 'peak': tensor_peak,
+                         'unit': 'TFLOP/s', 'frac': achieved / tensor_peak,
+                         'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)'
+                         if peaks else 'fallback 1.4 PFLOP/s',
+                         'traffic': None,
+                         'note': 'tcgen05 kind::tf32, fp32-class accuracy by hi/lo operand splits (3 products per MAC in 2 MMAs per '
+                                 'k-step): at most 1/6 of the bf16 figure is usable; 32 destination rows per CTA (128 CTAs per '
+                                 '4096-row launch); SS-mode operand fetch from shared memory (~64 B/clk), not the math, paces the '
+                                 'tensor pipe at N = 32 / 64 (DESIGN.md section 5a)',
+                         'fp32_ffma_equiv': {'peak': ffma_peak, 'frac': achieved / ffma_peak},
+                         'avg_launch_ms': avg_ms, 'launches_timed': sw['launches'],
+                         'share_of_step': sw['ms'] / sw['forward_ms'] if world == 1 else None,
+                         'all_node_kernels': {'avg_launch_ms': ct['attn_post']['ms'] / max(ct['attn_post']['launches'], 1),
+                                              'launches': ct['attn_post']['launches'],
+                                              'share_of_step': ct['attn_post']['ms'] / ct['attn_post']['forward_ms']}}
+            cap = ncu_traffic('psw::attn_post_sw_kernel a2p')
             if cap is not None:
-                roof2['traffic'] = cap['dram_bytes_read'] + cap['dram_bytes_write']
-                roof2['traffic_launch'] = cap['launch']
-                roof2['traffic_source'] = cap['source']
+                roof_post['traffic'] = cap['dram_bytes_read'] + cap['dram_bytes_write']
+                roof_post['traffic_launch'] = cap['launch']
+                roof_post['traffic_source'] = cap['source']
+        # `roofline` = the kernel with the largest share of the step; the other one rides along
+        cands = [r for r in (roof_edge, roof_post) if r is not None]
+        cands.sort(key=lambda r: -(r.get('share_of_step') or 0.0))
+        roof = cands[0] if cands else None
+        roof2 = cands[1] if len(cands) > 1 else None
         cpu = None
         if not a.no_cpu_baseline and world == 1:
-            ts, cores = time_oracle(a.cpu_baseline_scenes, A, M, RS, repeats=2, warmup=1)
+            ref = CpuReference()
+            ts = ref.time(a.cpu_baseline_scenes, A, M, RS, repeats=2, warmup=1)
             v = a.cpu_baseline_scenes * A * RS / (sum(ts) / len(ts))
-            cpu = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                   'sample': f'{a.cpu_baseline_scenes}-scene batch of the same workload, 2 timed forwards after 1 warm-up, '
-                             f'oracle port (bit-equal to the reference on CPU) incl. the reference\'s string bookkeeping'}
+            cpu = {'value': v, 'unit': UNIT, 'cores': ref.cores, 'kind': ref.kind,
+                   'sample': f'{a.cpu_baseline_scenes}-scene batch of the same workload, 2 timed forwards after 1 warm-up; {ref.what}'}
+            if single is not None:
+                t1 = ref.time(1, A, M, RS, repeats=3, warmup=1, first_scene=5000)
+                m1 = 1e3 * statistics.median(t1)
+                single['cpu_baseline'] = {'value': A * RS / (m1 * 1e-3), 'unit': UNIT, 'cores': ref.cores, 'kind': ref.kind,
+                                          'ms_per_forward': m1, 'sample': f'the same single scene shape, 3 timed forwards after 1 warm-up; {ref.what}'}
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
             'ms_per_step': total_ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': workload_name(a), 'scenes_per_gpu': S, 'agents': A, 'map_polylines': M,
-                       'rollout_steps': RS, 'l2': 'L2 flushed with a 256 MB write between timed iterations; 3 rotating input sets',
-                       'weights': 'seeded random init under the reference state_dict names (no checkpoint ships)',
-                       'host_plan': 'the 3 input sets share validity masks and agent-id lists, so the per-batch index plan '
-                                    '(1.4 ms of host bookkeeping + one H2D) is built once and reused (model._plan cache)'},
+            'dtype': 'f32', 'data': 'synthetic', 'config': bench_config(a),
+            'timing': {'l2': 'L2 flushed with a 256 MB write between timed iterations; 3 rotating input sets',
+                       'host_plan': 'value: the 3 input sets share validity masks and agent-id lists, so the per-batch index plan is '
+                                    'reused (model._plan cache); e2e: the cache is cleared every step (plan rebuilt + index maps uploaded '
+                                    'inside the timed region, as for a stream of distinct scenes)',
+                       'e2e_gather': 'N > 1: NCCL gather of the rolled-out steps to rank 0 inside the timed region, D2H on rank 0'},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': e2e[0][1], 'd2h_bytes_per_step': e2e[0][2],
                     'ms_per_step': e2e_ms / a.steps},
-            'gpu_launches': launches, 'roofline': roof, 'roofline_dense_kernel': roof2, 'cpu_baseline': cpu,
+            'gpu_launches': launches, 'roofline': roof, 'roofline_second_kernel': roof2, 'cpu_baseline': cpu,
             'clocks': clk.summary(),
-            'single_scene': single, 'large_batch': large,
+            'configs2': single, 'strong_scaling': strong,
         }
         print(json.dumps(line))
     if world > 1:

@@ -32,7 +32,18 @@ import torch
 import torch.nn as nn
 import yaml
 
-REF_ROOT = os.environ.get('PROSIM_REFERENCE_ROOT', '/root/reference')
+def _find_reference_root():
+    """PROSIM_REFERENCE_ROOT, else the mounted tree (authoring container), else the copy staged by baseline/install_ref.py
+    (git-ignored; travels to the GPU box)."""
+    env = os.environ.get('PROSIM_REFERENCE_ROOT')
+    staged = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'baseline', '_ref')
+    for root in ([env] if env else []) + ['/root/reference', staged]:
+        if os.path.isdir(os.path.join(root, 'prosim')):
+            return root
+    return env or '/root/reference'
+
+
+REF_ROOT = _find_reference_root()
 
 _MOCKED_TOPLEVEL = (
     'pytorch_lightning', 'torchmetrics', 'trajdata', 'matplotlib', 'seaborn', 'shapely',
