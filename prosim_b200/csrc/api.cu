@@ -321,7 +321,10 @@ int launch_post(const float* x, int n, int zd, const float* rbar, const float* a
   if (n <= 0) return 0;
   const int rpt = pick_rpt(n);
   LaunchScope ls(PROSIM_K_ATTN_POST, st);
-  if (pick_rt(n) != 0 && (g_tc_mask & 1) && (g_tc_mask & 8) && n <= SW_MAX_ROWS && (zd == 96 || zd == 128)) {
+  // The 32-row tcgen05 kernel serves every launch size up to two waves of CTAs: for a single 128-agent scene (4 CTAs) its
+  // per-CTA chain (~40 us) is less than half of what the 2-rows-per-CTA FFMA kernel needs to stream 1.1 MB of weights per CTA
+  // (94 us measured per launch, 58 % of a single-scene forward).  Rows never interact, so results do not depend on the size.
+  if ((g_tc_mask & 1) && (g_tc_mask & 8) && n <= SW_MAX_ROWS && (zd == 96 || zd == 128)) {
     LaunchScope ls_sw(PROSIM_K_ATTN_POST_SW, st);   // counted (and timed) under both classes
     psw::Args a;
     a.x = x; a.rbar = rbar; a.aggv = aggv; a.s = cur.s; a.gx = cur.gx; a.out = out;
