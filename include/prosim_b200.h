@@ -143,6 +143,11 @@ int prosim_reconst_fwd(const float* emd, int P, const float* w, float* out, pros
 /* PromptEncoder (prompt_encoder/base.py:30,37-50) / GoalConditionEncoder (condition_encoders.py:21-51) */
 int prosim_mlp2_fwd(const float* in, int ld_in, int k0, int n, int use_ln, const float* w, const float* tpe_t,
                     int tpe_ld, const float* dim_t128, float* out, prosim_stream_t stream);
+/* MODEL.OBS_UPDATE.FUSION = 'mlp' (scene_encoder/attn_fusion.py:177-203): x_new[idx_new[i]] <- obs_update_mlp([x_old[idx_old[i]] |
+ * x_new[idx_new[i]]]) for the n agents observed at the previous tick too, in place (w: prosim_obs_fuse_floats() floats). */
+int prosim_obs_fuse_floats(void);
+int prosim_obs_fuse_fwd(const float* x_old, const int32_t* idx_old, float* x_new, const int32_t* idx_new, int n,
+                        const float* w, prosim_stream_t stream);
 /* MotionTagEncoder for unary action tags (condition_transformer/condition_encoders.py:76-145): tags int64 [n][3] =
  * (tag id, start step, end step); table [16][128] indexed by tag id; out [n][128] = tag vector + FourierEmbeddingFix(64)
  * of start | end.  Rows with an id outside [0, n_tags) become zeros. */

@@ -88,6 +88,9 @@ class ProSimOracle:
         self.noise_fn = torch.randn_like
         self.trace = None  # set to [] to record per-tick state for teacher-forced tests
         self.trace_states = []
+        # MODEL.OBS_UPDATE (attn_fusion.py:15-19, 238-251): 'mlp' fusion iff the checkpoint carries obs_update_mlp
+        self.obs_fusion = 'mlp' if 'scene_encoder.obs_update_mlp.mlp.0.weight' in self.w else 'replace'
+        self.attn_update = False
 
     # ------------------------------------------------------------------------- building blocks
     def lin(self, name, x, bias=True):
@@ -365,6 +368,21 @@ class ProSimOracle:
         fut['heading'][b, o] = a_pos['heading'][b, n].squeeze(-1).to(inp.dtype)
         fut['mask'][b, o, :HIST] = True
         obs_emb, obs_mask = self.obs_encoder(fut)
+        if self.obs_fusion == 'mlp':
+            # attn_fusion.py:177-203: agents present in the old AND the new observation get MLP([old token | new token])
+            old_ids = (batch.extras['fut_obs'][all_t[ti - 1]] if ti > 1 else batch.extras['init_obs'])['agent_ids']
+            bi_, new_o, old_o = [], [], []
+            for bidx in range(obs_emb.shape[0]):
+                lut = {a: i for i, a in enumerate(old_ids[bidx])}
+                for new_oidx, agent_id in enumerate(fut['agent_ids'][bidx]):
+                    if agent_id in lut:
+                        bi_.append(bidx), new_o.append(new_oidx), old_o.append(lut[agent_id])
+            old_mask = scene['obs_mask']
+            old_emb = torch.zeros(old_mask.shape[:2] + (128,), dtype=self.dtype)
+            old_emb[old_mask] = scene['scene_tokens'][scene['scene_type'] == 1]
+            fused = self.mlp('scene_encoder.obs_update_mlp', torch.cat([old_emb[bi_, old_o], obs_emb[bi_, new_o]], dim=-1), 2,
+                             ret_before_act=True)
+            obs_emb[bi_, new_o] = fused
         mt = scene['scene_type'] == 0
         B = obs_emb.shape[0]
         map_b = scene['scene_batch_idx'][mt]
@@ -377,7 +395,32 @@ class ProSimOracle:
         new['scene_ori'] = torch.cat([scene['scene_ori'][mt], fut['heading'].to(self.dtype).view(-1, 1)[obs_mask.view(-1)]])
         new['obs_mask'] = obs_mask
         new['max_agent_num'] = obs_emb.shape[1]
+        if self.attn_update:
+            new = self.update_scene_emb_attn(new)
         return new, a_pos
+
+    def update_scene_emb_attn(self, scene):
+        """attn_fusion.py:136-175 (OBS_UPDATE.ATTN_UPDATE): after the agent tokens were replaced, redo the encoder's agent
+        self-attention and map -> agent attention on radius graphs (100 m / 50 m, 32 neighbours), agent rows only."""
+        mt, at = scene['scene_type'] == 0, scene['scene_type'] == 1
+        m_pos, m_ori, a_pos, a_ori = scene['scene_pos'][mt], scene['scene_ori'][mt], scene['scene_pos'][at], scene['scene_ori'][at]
+        mb, ab = scene['scene_batch_idx'][mt], scene['scene_batch_idx'][at]
+        e_a = graph.radius_graph(a_pos, r=100, batch=ab, loop=False, max_num_neighbors=32)
+        e_am = graph.radius(x=m_pos, y=a_pos, r=50, batch_x=mb, batch_y=ab, max_num_neighbors=32)
+        e_ma = e_am[[1, 0]]
+        pe_a = self.rel_pe(e_a, a_ori, a_pos, a_ori, a_pos)
+        pe_ma = self.rel_pe(e_ma, a_ori, a_pos, m_ori, m_pos)
+        x_a, x_m = scene['scene_tokens'][at], scene['scene_tokens'][mt]
+        for i in range(6):
+            x_a = self.attention_layer(f'scene_encoder.a2a_attn_layers.{i}', x_a, x_a, pe_a, e_a, False)
+            # a non-bipartite module called with (x_src, x_dst): both pre-norms are the one shared LayerNorm (attention_layer.py:48-49)
+            x_a = self.attention_layer(f'scene_encoder.s2s_attn_layers.{i}', x_m, x_a, pe_ma, e_ma, True)
+        scene = dict(scene)
+        tok = scene['scene_tokens'].clone()
+        tok[at] = x_a
+        scene['scene_tokens'] = tok
+        self._dbg_upd = dict(e_a=e_a, e_ma=e_ma)
+        return scene
 
     def policy_tick(self, policy, scene, policy_ids, a_pos, t):
         """traj_sam.py:178-202,441-525 (row gather) + policy/act_decoder.py:239-279 (attn_fuse) +

@@ -112,8 +112,8 @@ def check_supported(cfg):
         problems.append('MODEL.HIDDEN_DIM must be 128')
     if m.REL_POS_EDGE_FUNC != 'radius':
         problems.append("MODEL.REL_POS_EDGE_FUNC must be 'radius'")
-    if m.OBS_UPDATE.FUSION != 'replace' or m.OBS_UPDATE.ATTN_UPDATE:
-        problems.append("MODEL.OBS_UPDATE must be FUSION='replace', ATTN_UPDATE=False")
+    if m.OBS_UPDATE.FUSION not in ('replace', 'mlp'):
+        problems.append("MODEL.OBS_UPDATE.FUSION must be 'replace' or 'mlp'")
     for name, a in (('SCENE_ENCODER', m.SCENE_ENCODER.ATTN), ('DECODER', m.DECODER.ATTN),
                     ('POLICY.ACT_DECODER', m.POLICY.ACT_DECODER.ATTN)):
         if a.LEARNABLE_PE or a.NUM_HEAD != 8 or a.FF_DIM != 16:

@@ -714,6 +714,19 @@ int prosim_mlp2_fwd(const float* in, int ld_in, int k0, int n, int use_ln, const
   return 0;
 }
 
+int prosim_obs_fuse_floats(void) { return fw::SIZE; }
+int prosim_obs_fuse_fwd(const float* x_old, const int32_t* idx_old, float* x_new, const int32_t* idx_new, int n, const float* w,
+                        prosim_stream_t stream) {
+  if (n < 0) return ERR_ARG;
+  if (n == 0) return 0;
+  if (!x_old || !idx_old || !x_new || !idx_new || !w) return ERR_ARG;
+  const int rpt = pick_rpt(n);
+  LaunchScope ls(PROSIM_K_MLP2, S(stream));
+  DISPATCH_RPT(rpt, obs_fuse_kernel<RPT><<<(n + 2 * RPT - 1) / (2 * RPT), 256, 0, S(stream)>>>(x_old, idx_old, x_new, idx_new, n, w));
+  PROSIM_CHECK_LAUNCH();
+  return 0;
+}
+
 int prosim_tag_embed_fwd(const int64_t* tags, int n, int n_tags, const float* table, const float* dim_t64, float* out,
                          prosim_stream_t stream) {
   if (n < 0 || n_tags < 0 || n_tags > 16) return ERR_ARG;

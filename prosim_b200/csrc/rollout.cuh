@@ -450,4 +450,43 @@ __global__ void __launch_bounds__(256) cond_pool_kernel(const float* __restrict_
   if (c == 0) has[p] = cnt > 0;
 }
 
+// MODEL.OBS_UPDATE.FUSION = 'mlp' (scene_encoder/attn_fusion.py:177-203): for every agent that was observed at the previous
+// tick too, new token <- MLP([old token | new token]) (Linear 256 -> 128, LN, ReLU, Linear 128 -> 128), in place.
+// idx_old / idx_new: token rows of the n agents in the old / new agent-token buffers.
+template <int RPT>
+__global__ void __launch_bounds__(256) obs_fuse_kernel(const float* __restrict__ x_old, const int* __restrict__ idx_old,
+                                                       float* __restrict__ x_new, const int* __restrict__ idx_new, int n,
+                                                       const float* __restrict__ W) {
+  constexpr int R = 2 * RPT;
+  constexpr int LDA = 2 * D + 4;
+  __shared__ __align__(16) float sA[R * LDA];
+  __shared__ __align__(16) float sB[R * LDS_PAD];
+  const int row0 = blockIdx.x * R;
+  const int col = threadIdx.x & 127, rg = threadIdx.x >> 7;
+  for (int i = threadIdx.x; i < R * 64; i += 256) {
+    const int r = i >> 6, c4 = i & 63;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row0 + r < n) {
+      const float* src = c4 < 32 ? x_old + (size_t)idx_old[row0 + r] * D + 4 * c4 : x_new + (size_t)idx_new[row0 + r] * D + 4 * (c4 - 32);
+      v = *reinterpret_cast<const float4*>(src);
+    }
+    *reinterpret_cast<float4*>(sA + r * LDA + 4 * c4) = v;
+  }
+  __syncthreads();
+  float acc[RPT];
+  acc_init(acc, __ldg(W + fw::B0 + col));
+  gemm_tile_acc<RPT>(acc, sA, LDA, 2 * D, W + fw::W0, D);
+  acc_store_smem<RPT>(acc, sB, LDS_PAD, false);
+  __syncthreads();
+  ln_tile_inplace<D>(sB, LDS_PAD, R, W + fw::G0, W + fw::BB0, true);
+  __syncthreads();
+  acc_init(acc, __ldg(W + fw::B1 + col));
+  gemm_tile_acc<RPT>(acc, sB, LDS_PAD, D, W + fw::W1, D);
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) {
+    const int row = row0 + rg * RPT + r;
+    if (row < n) x_new[(size_t)idx_new[row] * D + col] = acc[r];
+  }
+}
+
 }  // namespace prosim

@@ -125,4 +125,14 @@ constexpr int W1 = BB0 + 128;                // [128][128]
 constexpr int B1 = W1 + 16384;
 constexpr int SIZE = B1 + 128;
 }  // namespace mw
+
+namespace fw {  // obs_update_mlp (scene_encoder/attn_fusion.py:18-19, 196): Linear(256 -> 128) LN ReLU Linear(128 -> 128)
+constexpr int W0 = 0;                        // [256 k][128 n]: rows 0..127 multiply the OLD token, 128..255 the NEW one
+constexpr int B0 = W0 + 256 * 128;
+constexpr int G0 = B0 + 128;
+constexpr int BB0 = G0 + 128;
+constexpr int W1 = BB0 + 128;                // [128][128]
+constexpr int B1 = W1 + 16384;
+constexpr int SIZE = B1 + 128;
+}  // namespace fw
 }  // namespace prosim

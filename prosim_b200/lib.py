@@ -16,7 +16,7 @@ SYMBOLS = (
     'prosim_build_knn_edges', 'prosim_edge_pe', 'prosim_attn_kv', 'prosim_attn_layer_fwd', 'prosim_attn_stack_fwd',
     'prosim_policy_head_fwd', 'prosim_reconst_fwd', 'prosim_mlp2_fwd', 'prosim_init_traj', 'prosim_step_env',
     'prosim_gather_pose', 'prosim_step_agent_traj', 'prosim_launch_count', 'prosim_profile_enable', 'prosim_profile_read',
-    'prosim_rollout_to_world', 'prosim_tc_gemm_test', 'prosim_set_tensor_core', 'prosim_tc_debug_read', 'prosim_set_stack_split', 'prosim_tag_embed_fwd', 'prosim_cond_pool_fwd', 'prosim_workspace_bytes', 'prosim_policy_tick',
+    'prosim_rollout_to_world', 'prosim_tc_gemm_test', 'prosim_set_tensor_core', 'prosim_tc_debug_read', 'prosim_set_stack_split', 'prosim_tag_embed_fwd', 'prosim_cond_pool_fwd', 'prosim_workspace_bytes', 'prosim_policy_tick', 'prosim_obs_fuse_floats', 'prosim_obs_fuse_fwd',
 )
 
 KERNEL_CLASSES = {'pointnet': 0, 'radius': 1, 'knn': 2, 'edge_pe': 3, 'attn_kv': 4, 'attn_dstpre': 5, 'attn_edge': 6,
@@ -73,6 +73,7 @@ _SIGS = {
     'prosim_tc_debug_read': [_P],
     'prosim_set_stack_split': [c_int],
     'prosim_policy_tick': [POINTER(Tick), _P, c_size_t, _P],
+    'prosim_obs_fuse_fwd': [_P, _P, _P, _P, c_int, _P, _P],
 }
 
 _lib = None
@@ -91,7 +92,7 @@ def load():
     if missing:
         raise ProSimLibError(f'libprosim_b200.so lacks symbols {missing}')
     for name in ('prosim_abi_version', 'prosim_attn_layer_floats', 'prosim_pointnet_floats', 'prosim_head_floats',
-                 'prosim_mlp2_floats'):
+                 'prosim_mlp2_floats', 'prosim_obs_fuse_floats'):
         getattr(lib, name).restype = c_int
         getattr(lib, name).argtypes = []
     lib.prosim_launch_count.restype = ctypes.c_longlong
@@ -112,8 +113,8 @@ def load():
         raise ProSimLibError('libprosim_b200.so ABI version mismatch: rebuild')
     from . import weights
     sizes = (lib.prosim_attn_layer_floats(), lib.prosim_pointnet_floats(), lib.prosim_head_floats(),
-             lib.prosim_mlp2_floats())
-    want = (weights.ATTN_LAYER_FLOATS, weights.POINTNET_FLOATS, weights.HEAD_FLOATS, weights.MLP2_FLOATS)
+             lib.prosim_mlp2_floats(), lib.prosim_obs_fuse_floats())
+    want = (weights.ATTN_LAYER_FLOATS, weights.POINTNET_FLOATS, weights.HEAD_FLOATS, weights.MLP2_FLOATS, weights.OBS_FUSE_FLOATS)
     if sizes != want:
         raise ProSimLibError(f'packed weight layout mismatch: library {sizes} vs packer {want}')
     _lib = lib

@@ -117,6 +117,8 @@ class ProSimB200(nn.Module):
         self.hist_step = cfg.DATASET.FORMAT.HISTORY.STEPS
         assert self.rollout_steps == STEP and self.hist_step == HIST and cfg.DATASET.FORMAT.TARGET.STEPS == STEP
         self.num_layers = cfg.MODEL.POLICY.ACT_DECODER.ATTN.NUM_LAYER
+        self.obs_fusion = cfg.MODEL.OBS_UPDATE.FUSION                  # 'replace' | 'mlp' (attn_fusion.py:238-251)
+        self.attn_update = bool(cfg.MODEL.OBS_UPDATE.ATTN_UPDATE)
         self.cond_layers = cfg.MODEL.CONDITION_TRANSFORMER.NLAYER
         self.mode = 'val'
         # act_decoder.py:113-115: Gaussian noise on the predicted per-step displacements; the draws come from torch's CUDA
@@ -141,7 +143,7 @@ class ProSimB200(nn.Module):
             lut[weights.V_ACTION_TAG_ID[tag]] = pos
         self._tag_slot = lut
         if state_dict is None:
-            state_dict = weights.random_state_dict(0, self.cond_types)
+            state_dict = weights.random_state_dict(0, self.cond_types, obs_fusion=self.obs_fusion)
         self.load_state_dict(state_dict)
 
     # ------------------------------------------------------------------ weights
@@ -156,7 +158,7 @@ class ProSimB200(nn.Module):
         """Same contract as nn.Module.load_state_dict: strict raises on missing / unexpected keys; strict=False (how the
         reference loads its checkpoints, trainer.py:162-163) keeps the current value of a missing parameter (the seeded
         initialisation before the first load) and ignores unexpected keys; both lists are returned."""
-        specs = weights.param_specs(self.cond_types, self.num_layers, self.cond_layers)
+        specs = weights.param_specs(self.cond_types, self.num_layers, self.cond_layers, self.obs_fusion)
         want = [n for n, _, _ in specs]
         missing = [k for k in want if k not in state_dict]
         unexpected = [k for k in state_dict if k not in set(want)]
@@ -165,7 +167,8 @@ class ProSimB200(nn.Module):
         bad = [k for k, shp, _ in specs if k in state_dict and tuple(state_dict[k].shape) != tuple(shp)]
         if bad:
             raise RuntimeError(f'load_state_dict: size mismatch for {bad[:5]}')
-        base = self._sd if self._sd is not None else (weights.random_state_dict(0, self.cond_types) if missing else {})
+        base = self._sd if self._sd is not None else (weights.random_state_dict(0, self.cond_types, obs_fusion=self.obs_fusion)
+                                                      if missing else {})
         self._sd = {k: (state_dict[k] if k in state_dict else base[k]).detach().float().cpu().clone() for k in want}
         arena, self._off = weights.pack_model(self._sd, self.num_layers, self.cond_layers)
         lib.load()  # fail loudly here, not at the first kernel call, if the native library is absent
@@ -350,6 +353,24 @@ class ProSimB200(nn.Module):
             ints[f'p_slot{i}'] = slot
             ints[f'agent_rows{i}'] = np.flatnonzero(valid.reshape(-1))
             ints[f'seg_agent{i}'] = np.stack([a_off[:-1], a_cnt, np.zeros(B), np.zeros(B)], axis=1)
+            if self.attn_update:
+                ints[f'agent_scene{i}'] = np.repeat(np.arange(B), a_cnt)
+            if self.obs_fusion == 'mlp':
+                # token row of every observation slot at this tick, and (i >= 1) the agents observed at tick i - 1 too:
+                # pairs (old token row, new token row) for obs_update_mlp (attn_fusion.py:180-189)
+                pos_of = -np.ones(B * A, dtype=np.int64)
+                pos_of[ints[f'agent_rows{i}']] = np.arange(int(a_cnt.sum()))
+                if i > 0:
+                    new_ids, old_ids = pl.obs_id_lists[i], pl.obs_id_lists[i - 1]
+                    f_old, f_new = [], []
+                    for b in range(B):
+                        lut = {a: k for k, a in enumerate(old_ids[b])}
+                        for k_new, a in enumerate(new_ids[b]):
+                            if a in lut and pos_of[b * A + k_new] >= 0 and prev_pos_of[b * A + lut[a]] >= 0:
+                                f_old.append(prev_pos_of[b * A + lut[a]])
+                                f_new.append(pos_of[b * A + k_new])
+                    ints[f'fuse_old{i}'], ints[f'fuse_new{i}'] = np.array(f_old, dtype=np.int64), np.array(f_new, dtype=np.int64)
+                prev_pos_of = pos_of
             pl.NA.append(int(a_cnt.sum()))
             pl.max_a = max(pl.max_a, int(a_cnt.max()) if B else 0)
             if i == 0:
@@ -850,17 +871,57 @@ class SceneEncoderB200(nn.Module):
                 raise ValueError('update_scene_emb: batch_obs is not one of the fut_obs entries this batch was planned with')
         na = pl.NA[_slot]
         max_na = max(pl.NA)
-        x_a = m._buf('x_a', (max_na, D))[:na]
-        a_pos, a_ori = m._buf('a_pos', (max_na, 2))[:na], m._buf('a_ori', (max_na,))[:na]
+        # two alternating agent-token buffers: the 'mlp' fusion reads the previous tick's tokens while it writes this tick's
+        x_a = m._buf(f'x_a{_slot & 1}', (max_na, D))[:na]
+        a_pos, a_ori = m._buf(f'a_pos{_slot & 1}', (max_na, 2))[:na], m._buf(f'a_ori{_slot & 1}', (max_na,))[:na]
         rows = pl.i[f'agent_rows{_slot}']
-        ops.pointnet(0, batch_obs['input'], batch_obs['mask'], rows, m._arena, m._off['obs_enc'], out=x_a, tc_off=m._off['obs_enc_tc'])
+        ar, off = m._arena, m._off
+        ops.pointnet(0, batch_obs['input'], batch_obs['mask'], rows, ar, off['obs_enc'], out=x_a, tc_off=off['obs_enc_tc'])
         ops.gather_pose(batch_obs['position'], batch_obs['heading'], rows, a_pos, a_ori)
+        if m.obs_fusion == 'mlp':
+            # attn_fusion.py:177-203: agents observed at the previous tick too get MLP([old token | new token])
+            if scene_emds.get('_slot', 0) != _slot - 1:
+                raise ValueError("OBS_UPDATE.FUSION = 'mlp' needs the scene embedding of the previous tick")
+            if pl.i[f'fuse_new{_slot}'].shape[0] > 0:
+                ops.obs_fuse(scene_emds['_agent'][0], pl.i[f'fuse_old{_slot}'], x_a, pl.i[f'fuse_new{_slot}'], ar, off['obs_fuse'])
+        if m.attn_update:
+            self._update_scene_emb_attn(scene_emds, pl, _slot, x_a, a_pos, a_ori)
         out = _SceneEmbs({k: v for k, v in dict.items(scene_emds) if k not in _SceneEmbs._LAZY})
         out['_agent'] = (x_a, a_pos, a_ori)
         out['_slot'] = _slot
         out['_obs_mask_src'] = batch_obs['mask']
         out['max_agent_num'] = batch_obs['input'].shape[1]
         return out
+
+
+    def _update_scene_emb_attn(self, scene_emds, pl, slot, x_a, a_pos, a_ori):
+        """attn_fusion.py:136-175 (OBS_UPDATE.ATTN_UPDATE): redo the encoder's agent self-attention and map -> agent attention
+        on radius graphs over the new agent tokens, in place: 6 x (a2a layer, s2s layer with the map tokens as sources).  The
+        map-side K'|V' of the s2s layers do not change during a rollout: computed once per scene encoding."""
+        m = self._m
+        ar, off = m._arena, m._off
+        lf = weights.ATTN_LAYER_FLOATS
+        L = m.num_layers
+        ecfg = m.config.MODEL.SCENE_ENCODER.ATTN
+        NM = pl.NM
+        na = x_a.shape[0]
+        x_m, m_pos, m_ori = scene_emds['_tok'][:NM], scene_emds['_tok_pos'][:NM], scene_emds['_tok_ori'][:NM]
+        dim_t = ar[off['dim_t16']:off['dim_t16'] + 16]
+        cap = ecfg.MAX_NUM_NEIGH
+        a_scene = pl.i[f'agent_scene{slot}']
+        seg_a = pl.i[f'seg_agent{slot}'].view(-1, 4)
+        e_a = ops.radius_edges(a_pos, a_scene, a_pos, seg_a, ecfg.AGENT_RADIUS, cap, min(cap + 1, max(pl.max_a, 1)), drop_self=True)
+        e_m = ops.radius_edges(a_pos, a_scene, m_pos, pl.i['seg_map'].view(-1, 4), ecfg.SCENE_RADIUS, cap, min(cap, max(pl.max_m, 1)))
+        ops.edge_pe(e_a, a_pos, a_ori, a_pos, a_ori, dim_t, z=m._buf('z_upd_a', (na * e_a.stride, 96)))
+        ops.edge_pe(e_m, a_pos, a_ori, m_pos, m_ori, dim_t, z=m._buf('z_upd_m', (na * e_m.stride, 96)))
+        shared = scene_emds['_shared']
+        kv_m = shared.get('kv_m_enc')
+        if kv_m is None:
+            kv_m = shared['kv_m_enc'] = ops.attn_kv(x_m, ar, off['enc_s2s'], L, lf, kv=m._buf('kv_m_enc', (L, NM, 2 * D)))
+        ws = m._buf('attn_ws_upd', (lib.load().prosim_attn_workspace_floats(na, na, max(e_a.stride, e_m.stride)),))
+        ops.attn_stack(x_a, L, ops.stack_side(ar, off['enc_a2a'], e_a), ops.stack_side(ar, off['enc_s2s'], e_m, kv_m), out=x_a,
+                       workspace=ws)
+        pl.edges_upd = (e_a, e_m)
 
 
 @registry.register_policy(name='rel_pe_temporal_b200')

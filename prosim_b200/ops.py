@@ -232,6 +232,16 @@ def mlp2(x, k0, use_ln, w_arena, w_off, tpe_col=None, dim_t128=None):
     return out
 
 
+def obs_fuse(x_old, idx_old, x_new, idx_new, w_arena, w_off):
+    """x_new[idx_new] <- obs_update_mlp([x_old[idx_old] | x_new[idx_new]]) in place (attn_fusion.py:177-203)."""
+    _chk(x_old, torch.float32, 'x_old'), _chk(x_new, torch.float32, 'x_new')
+    _chk(idx_old, torch.int32, 'idx_old'), _chk(idx_new, torch.int32, 'idx_new')
+    if idx_old.shape[0] != idx_new.shape[0]:
+        raise ValueError('obs_fuse: index lists differ in length')
+    lib.call('prosim_obs_fuse_fwd', ptr(x_old), ptr(idx_old), ptr(x_new), ptr(idx_new), idx_new.shape[0], ptr(w_arena, w_off), _stream())
+    return x_new
+
+
 def tag_embed(tags, table, dim_t64, n_tags=11):
     """tags: int64 [n, 3] (tag id, start, end) -> [n, 128] (condition_encoders.py:76-145)."""
     _chk(tags, torch.int64, 'tags'), _chk(table, torch.float32, 'table'), _chk(dim_t64, torch.float32, 'dim_t64')

@@ -89,7 +89,7 @@ def cond_types(x):
     return tuple(x)
 
 
-def param_specs(goal_condition=False, num_layers=6, cond_layers=3):
+def param_specs(goal_condition=False, num_layers=6, cond_layers=3, obs_fusion='replace'):
     types = cond_types(goal_condition)
     specs = []
     specs += _pointnet('scene_encoder.map_encoder', 11, 5, 3)
@@ -97,6 +97,8 @@ def param_specs(goal_condition=False, num_layers=6, cond_layers=3):
     for stack in ('a2a', 's2s'):
         for i in range(num_layers):
             specs += _attn_layer(f'scene_encoder.{stack}_attn_layers.{i}')
+    if obs_fusion == 'mlp':     # MODEL.OBS_UPDATE.FUSION = 'mlp' (scene_encoder/attn_fusion.py:18-19)
+        specs += _mlp('scene_encoder.obs_update_mlp', [2 * D, D, D], ret_before_act=True)
     specs += _mlp('prompt_encoder.motion_pred.state_encoder', [7, D, D], ret_before_act=True)
     for stack in ('p2p', 's2p'):
         for i in range(num_layers):
@@ -131,20 +133,21 @@ def param_specs(goal_condition=False, num_layers=6, cond_layers=3):
     return specs
 
 
-def random_state_dict(seed=0, goal_condition=False, dtype=torch.float32):
+def random_state_dict(seed=0, goal_condition=False, dtype=torch.float32, obs_fusion='replace'):
     """Seeded random weights, torch-default-like scales; LayerNorm affine is NOT identity on purpose
     (so the gamma/beta folding in the kernels is exercised).  Non-bipartite layers share one LayerNorm
     under two names (attention_layer.py:48-49): the dst copy is tied to the src one.
     goal_condition: False / True (= ('goal',)) / a tuple of PROMPT.CONDITION.TYPES."""
     goal_condition = cond_types(goal_condition)
     sd = OrderedDict()
-    for name, shape, kind in param_specs(goal_condition):
+    shapes = {n: sh for n, sh, _ in param_specs(goal_condition, obs_fusion=obs_fusion)}
+    for name, shape, kind in param_specs(goal_condition, obs_fusion=obs_fusion):
         g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(name.encode())) % (2 ** 63))
         if kind == 'linear_w':
             bound = 1.0 / (shape[1] ** 0.5)
             t = (torch.rand(shape, generator=g, dtype=torch.float64) * 2 - 1) * bound
         elif kind == 'linear_b':
-            fan_in = dict(param_shapes_cache(goal_condition))[name[:-len('bias')] + 'weight'][1]
+            fan_in = shapes[name[:-len('bias')] + 'weight'][1]
             bound = 1.0 / (fan_in ** 0.5)
             t = (torch.rand(shape, generator=g, dtype=torch.float64) * 2 - 1) * bound
         elif kind == 'ln_w':
@@ -179,6 +182,7 @@ POINTNET_FLOATS = (24 * 128 + 384) + (16384 + 384) + (16384 + 128) + (2 * 16384 
 _MLP3_FLOATS = 2 * (16384 + 384) + (64 * 128 + 128)
 HEAD_FLOATS = 3 * 128 + 3 * (16384 + 384) + 2 * _MLP3_FLOATS
 MLP2_FLOATS = 8 * 128 + 384 + 16384 + 128
+OBS_FUSE_FLOATS = 256 * 128 + 384 + 16384 + 128
 
 
 def _f64(t):
@@ -366,6 +370,16 @@ def pack_mlp2(sd, p, with_ln):
     return out
 
 
+def pack_obs_fuse(sd, p='scene_encoder.obs_update_mlp'):
+    """MLP([256, 128, 128], ret_before_act): Linear -> LN -> ReLU -> Linear, first weight K-major [256 k][128 n] with the
+    OLD token's 128 inputs first (torch.cat([old, new]), attn_fusion.py:196) -- csrc/weights_layout.h fw::."""
+    w = lambda n: _f64(sd[f'{p}.{n}'])
+    parts = [w('mlp.0.weight').t(), w('mlp.0.bias'), w('mlp.1.weight'), w('mlp.1.bias'), w('mlp.3.weight').t(), w('mlp.3.bias')]
+    out = torch.cat([x.contiguous().reshape(-1) for x in parts]).float()
+    assert out.numel() == OBS_FUSE_FLOATS
+    return out
+
+
 def pack_model(sd, num_layers=6, cond_layers=3):
     """state_dict -> (arena fp32 [n], {section: float offset}).  Sections are 256-byte aligned."""
     goal = any(k.startswith('condition_transformers.') for k in sd)
@@ -385,6 +399,8 @@ def pack_model(sd, num_layers=6, cond_layers=3):
     for name, prefix, n in stacks:
         sections[name] = torch.cat([pack_attn_layer(sd, f'{prefix}.{i}') for i in range(n)])
     sections['prompt_mlp'] = pack_mlp2(sd, 'prompt_encoder.motion_pred.state_encoder', True)
+    if 'scene_encoder.obs_update_mlp.mlp.0.weight' in sd:
+        sections['obs_fuse'] = pack_obs_fuse(sd)
     ce = 'condition_transformers.policy_decoder.condition_encoders'
     if f'{ce}.goal.goal_encoder.mlp.0.weight' in sd:
         sections['goal_mlp'] = pack_mlp2(sd, f'{ce}.goal.goal_encoder', False)

@@ -283,6 +283,37 @@ def test_tick_loop_driven_from_outside_equals_rollout_batch():
     assert torch.equal(again['motion_pred'], outs[-1]['motion_pred']['motion_pred'])
 
 
+@pytest.mark.parametrize('fusion,attn', [('mlp', False), ('replace', True), ('mlp', True)])
+def test_obs_update_variants_match_oracle(fusion, attn):
+    """MODEL.OBS_UPDATE.{FUSION: 'mlp', ATTN_UPDATE: True} (scene_encoder/attn_fusion.py:136-203): the per-tick scene update
+    with the old / new token MLP (obs_fuse_kernel) and with the re-run agent / map -> agent attention, against the oracle
+    (itself bit-equal to the reference's own code for these variants: tests/test_oracle_vs_reference.py)."""
+    from prosim_b200.config import get_config
+    from prosim_b200.model import ProSimB200
+    sd = weights.random_state_dict(0, obs_fusion=fusion)
+    model = ProSimB200(get_config(opts=['MODEL.OBS_UPDATE.FUSION', fusion, 'MODEL.OBS_UPDATE.ATTN_UPDATE', attn]), sd, device='cuda')
+    kw = dict(agents_per_scene=[20, 13, 31], map_per_scene=[48, 37, 60], steps=40, permute_obs=True)
+    orc = ProSimOracle(sd)
+    orc.attn_update = attn
+    ref = orc.forward(synthetic.make_batch(**kw))['motion_pred']
+    with torch.no_grad():
+        out = model.forward(synthetic.make_batch(**kw).to('cuda'), 'val')['motion_pred']
+    assert out['pair_names'] == ref['pair_names']
+    P = 64
+    assert (out['motion_pred'][:P].cpu() - ref['motion_pred'][:P]).abs().max() < 1e-5          # tick 0: no update yet
+    assert (out['motion_pred'][P:2 * P].cpu() - ref['motion_pred'][P:2 * P]).abs().max() < 5e-5  # tick 1: first updated scene
+    _, traj, _ = stack_rollout(out)
+    _, traj_ref, _ = stack_rollout(ref)
+    print(fusion, attn, 'per-tick max |traj - oracle|', per_tick_max(traj, traj_ref))
+    assert np.abs(traj - traj_ref).max() < 1e-4
+    if attn:
+        pl = model._last_plan
+        assert edge_set(pl.edges_upd[0].to_edge_index()) == edge_set(orc._dbg_upd['e_a'])
+        assert edge_set(pl.edges_upd[1].to_edge_index()) == edge_set(orc._dbg_upd['e_ma'])
+    plain = ProSimOracle(weights.random_state_dict(0)).forward(synthetic.make_batch(**kw))['motion_pred']
+    assert np.abs(traj - stack_rollout(plain)[1]).max() > 1e-3                                  # the variant is really active
+
+
 def test_fused_tick_entry_point_is_bit_identical():
     """prosim_policy_tick (the whole tick in one C call) against the same tick issued kernel family by
     kernel family through the per-step entry points: identical bits, for FFMA-sized and tensor-core-sized launches."""

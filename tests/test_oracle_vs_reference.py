@@ -45,6 +45,30 @@ def test_oracle_bit_equal_to_reference(goal):
             assert torch.equal(torch.nan_to_num(a.float()), torch.nan_to_num(b.float())), (t, key)
 
 
+@pytest.mark.parametrize('fusion,attn', [('mlp', False), ('replace', True), ('mlp', True)])
+def test_oracle_bit_equal_to_reference_obs_update_variants(fusion, attn):
+    """MODEL.OBS_UPDATE.{FUSION: 'mlp', ATTN_UPDATE: True} (scene_encoder/attn_fusion.py:136-203): the per-tick scene update
+    with the old / new token MLP and with the re-run agent / map->agent attention, tier B == the reference's own code."""
+    opts = ['MODEL.OBS_UPDATE.FUSION', fusion, 'MODEL.OBS_UPDATE.ATTN_UPDATE', str(attn)]
+    m, cfg = ref_shim.build_reference_model((), opts=opts)
+    assert cfg.MODEL.OBS_UPDATE.FUSION == fusion and bool(cfg.MODEL.OBS_UPDATE.ATTN_UPDATE) == attn
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(n, tuple(sh)) for n, sh, _ in weights.param_specs(False, obs_fusion=fusion)]
+    sd = weights.random_state_dict(0, obs_fusion=fusion)
+    m.load_state_dict(sd)
+    kw = dict(agents_per_scene=[20, 13], map_per_scene=[48, 37], steps=40, permute_obs=True)
+    with torch.no_grad():
+        ref = m.forward(synthetic.make_batch(**kw), 'val')['motion_pred']
+    orc = ProSimOracle(sd)
+    assert orc.obs_fusion == fusion
+    orc.attn_update = attn
+    out = orc.forward(synthetic.make_batch(**kw))['motion_pred']
+    assert torch.equal(ref['motion_pred'], out['motion_pred'])
+    for name, r in ref['rollout_trajs'].items():
+        assert torch.equal(r['traj'], out['rollout_trajs'][name]['traj']), name
+    plain = ProSimOracle(weights.random_state_dict(0)).forward(synthetic.make_batch(**kw))['motion_pred']
+    assert not torch.equal(plain['motion_pred'], out['motion_pred'])          # the variants really change the rollout
+
+
 def test_oracle_bit_equal_to_reference_with_action_noise():
     """MODEL.POLICY.ACT_DECODER.RANDOM_NOISE_STD > 0 (act_decoder.py:113-115): same torch generator state -> same draws
     (the oracle also consumes the degenerate TOP_K = 1 draw of traj_sam.py:313) -> bit-equal noisy rollouts."""
