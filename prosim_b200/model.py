@@ -598,28 +598,8 @@ class ProSimB200(nn.Module):
         return {task: st for task in self.tasks}
 
     def _select_k_emd_from_batch(self, policy_emds, batch):
-        """traj_sam.py:402-439.  One policy token per agent (DECODER.GOAL_PRED disabled, emd [B, N, D]): nothing to select.
-        With K goal-conditioned tokens per agent (emd [B, N, K, D] + goal_prob / goal_point, e.g. handed over by a sampler
-        model): inference picks uniformly among the top-``ROLLOUT.POLICY.TOP_K`` goal probabilities, training the token
-        whose goal point is closest to the ground-truth goal -- index bookkeeping, torch ops like the reference."""
-        if policy_emds['emd'].ndim == 3:
-            return policy_emds
-        goal_prob, goal_point = policy_emds['goal_prob'], policy_emds['goal_point']
-        B, N, K, Dm = policy_emds['emd'].shape
-        if self.mode == 'train':
-            gt_goal = batch.extras['io_pairs_batch']['goal'][:, 0, :]
-            goal_idxs = torch.norm(goal_point - gt_goal[:, :, None, :], dim=-1).min(dim=-1)[1]
-        else:
-            rollout_k = min(self.rollout_top_k, K)
-            top = torch.topk(goal_prob, rollout_k, dim=-1)[1]
-            rand_idxs = torch.randint(0, rollout_k, (B, N,)).to(device=self._device)
-            goal_idxs = torch.gather(top, -1, rand_idxs[..., None]).squeeze(-1)
-        policy_emds = dict(policy_emds)
-        policy_emds.pop('_emd_flat', None)
-        policy_emds['select_idx'] = goal_idxs
-        policy_emds['emd'] = torch.gather(policy_emds['emd'], -2, goal_idxs[..., None, None].repeat(1, 1, 1, Dm)).squeeze(-2)
-        policy_emds['goal'] = torch.gather(goal_point, -2, goal_idxs[..., None, None].repeat(1, 1, 1, 2)).squeeze(-2)
-        return policy_emds
+        """traj_sam.py:402-439."""
+        return select_k_emd_from_batch(policy_emds, batch, self.mode, self.rollout_top_k, self.rollout_top_k_train, self._device)
 
     def rollout_batch(self, batch, scene_embs, policy_emds, policy_agent_ids, agent_trajs, all_t_indices, mode):
         """traj_sam.py:144-175: the closed-loop tick loop, written against the same four methods as the reference
@@ -779,6 +759,30 @@ class ProSimB200(nn.Module):
         res['rollout_trajs'] = _RolloutTrajs(agent_names, rows, st, int(st['last_step']))
         res['_state'] = st
         return {task: res}
+
+
+def select_k_emd_from_batch(policy_emds, batch, mode, rollout_top_k, rollout_top_k_train, device):
+    """traj_sam.py:402-439.  One policy token per agent (DECODER.GOAL_PRED disabled, emd [B, N, D]): nothing to select.
+    With K goal-conditioned tokens per agent (emd [B, N, K, D] + goal_prob [B, N, K] / goal_point [B, N, K, 2]): inference picks
+    uniformly among the top-``ROLLOUT.POLICY.TOP_K`` goal probabilities (one ``torch.randint`` on the host generator, like the
+    reference), training the token whose goal point is closest to the ground-truth goal.  Index bookkeeping in torch."""
+    if policy_emds['emd'].ndim == 3:
+        return policy_emds
+    goal_prob, goal_point = policy_emds['goal_prob'], policy_emds['goal_point']
+    B, N, K, Dm = policy_emds['emd'].shape
+    if mode == 'train':
+        gt_goal = batch.extras['io_pairs_batch']['goal'][:, 0, :]
+        goal_idxs = torch.min(torch.norm(goal_point - gt_goal[:, :, None, :], dim=-1), dim=-1)[1]
+    else:
+        rollout_k = min(rollout_top_k, K)
+        top = torch.topk(goal_prob, rollout_k, dim=-1)[1]
+        rand_idxs = torch.randint(0, rollout_k, (B, N,)).to(device=device)
+        goal_idxs = torch.gather(top, -1, rand_idxs[..., None]).squeeze(-1)
+    policy_emds = {k: v for k, v in policy_emds.items() if not k.startswith('_')}
+    policy_emds['select_idx'] = goal_idxs
+    policy_emds['emd'] = torch.gather(policy_emds['emd'], -2, goal_idxs[..., None, None].repeat(1, 1, 1, Dm)).squeeze(-2)
+    policy_emds['goal'] = torch.gather(goal_point, -2, goal_idxs[..., None, None].repeat(1, 1, 1, 2)).squeeze(-2)
+    return policy_emds
 
 
 class _AgentPositions(Mapping):

@@ -527,6 +527,71 @@ def test_parallel_rollout_batch_and_world_transform():
     assert np.minimum(dh, 2 * math.pi - dh).max() < 1e-5
 
 
+def test_goal_sampler_parallel_rollout_matches_oracle():
+    """parallel_rollout_batch with a sampler model (rollout/gpu_utils.py:203-216): M goal conditions are sampled from the
+    sampler's top_K goal predictions, the policy tokens are generated on the M-replica batch and the replicas rolled out
+    together.  Checked against the oracle run on a hand-replicated CPU batch carrying the SAME sampled goals; also
+    obtain_rollout_trajs_in_world(noise_std > 0) and K goal-conditioned tokens per agent through rollout_batch."""
+    import copy
+    from prosim_b200.containers import BatchCondition, BatchDataDict, BatchPrompt
+    from prosim_b200.rollout import _rep, _rep_imd, obtain_rollout_trajs_in_world, parallel_rollout_batch
+    model = _model(True)
+    kw = dict(n_scenes=1, n_agents=12, n_map=30, steps=20, goal=True)
+    M, K = 3, 4
+    ids = synthetic.make_batch(**kw).extras['prompt']['motion_pred']['agent_ids'][0]
+    g = torch.Generator().manual_seed(9)
+
+    class Sampler:
+        def forward(self, batch, mode):
+            return {'motion_pred': {'pair_names': [f'0-{a}-0' for a in ids], 'goal_point': torch.randn(12, K, 2, generator=g) * 30,
+                                    'goal_prob': torch.rand(12, K, generator=g)}}
+
+    batch = synthetic.make_batch(**kw).to('cuda')
+    torch.manual_seed(21)
+    res = parallel_rollout_batch(batch, M, model, top_K=2, sampler_model=Sampler())['motion_pred']
+    goal = {k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in batch.extras['condition'].all_cond['goal'].items()}
+    assert goal['input'].shape == (M, 12, 3) and not torch.equal(goal['input'][0], goal['input'][1])
+    # the oracle on a CPU batch replicated by hand, with the same goals
+    cpu = synthetic.make_batch(**kw)
+    ex = cpu.extras
+    ex['init_obs'], ex['init_map'] = _rep_imd(ex['init_obs'], M), _rep_imd(ex['init_map'], M)
+    ex['fut_obs'] = BatchDataDict({t: _rep_imd(ex['fut_obs'][t], M) for t in ex['fut_obs'].keys()})
+    ex['prompt'] = BatchPrompt({'motion_pred': {k: (v * M if isinstance(v, list) else _rep(v, M))
+                                                for k, v in ex['prompt']['motion_pred'].items()}})
+    ex['condition'] = BatchCondition({'goal': goal})
+    cpu.scene_ids = list(cpu.scene_ids) * M
+    ref = ProSimOracle(weights.random_state_dict(0, True), True).forward(cpu)['motion_pred']
+    assert res['pair_names'] == ref['pair_names']
+    _, traj, _ = stack_rollout(res)
+    _, traj_ref, _ = stack_rollout(ref)
+    assert np.abs(traj - traj_ref).max() < 1e-4
+    assert np.abs(traj[:12] - traj[12:24]).max() > 1e-2                  # replicas with different goals really differ
+    # world transform with evaluation noise (gpu_utils.py:254-256): same generator state -> same draws
+    batch.centered_world_from_agent_tf = torch.eye(3)[None].repeat(M, 1, 1)
+    quiet, _ = obtain_rollout_trajs_in_world(batch, {'motion_pred': res})
+    torch.manual_seed(4)
+    noisy, _ = obtain_rollout_trajs_in_world(batch, {'motion_pred': res}, noise_std=0.5)
+    d = np.concatenate(noisy)[..., :2] - np.concatenate(quiet)[..., :2]
+    assert 0.3 < d.std() < 0.7 and np.abs(np.concatenate(noisy)[..., 2] - np.concatenate(quiet)[..., 2]).max() < 1e-6
+    # K policy tokens per agent: rollout_batch selects one per agent (traj_sam.py:159, 402-439)
+    b1 = synthetic.make_batch(**kw).to('cuda')
+    with torch.no_grad():
+        scene = model.encode_scene(b1)
+        policy = model.generate_policy(b1, scene, model.encode_prompt(b1))['motion_pred']
+        idsd = {'motion_pred': b1.extras['prompt']['motion_pred']['agent_ids']}
+        emd = policy['emd']
+        multi = {'emd': torch.stack([emd + 0.1 * k for k in range(K)], dim=2), 'agent_type': policy['agent_type'],
+                 'goal_prob': torch.rand(1, 12, K, device='cuda'), 'goal_point': torch.randn(1, 12, K, 2, device='cuda')}
+        top1 = multi['goal_prob'].argmax(-1)
+        out = model.rollout_batch(b1, scene, {'motion_pred': multi}, idsd, model.init_agent_trajs(idsd, b1), [0, 10], 'val')['motion_pred']
+        b2 = synthetic.make_batch(**kw).to('cuda')
+        scene2 = model.encode_scene(b2)
+        chosen = {'emd': torch.gather(multi['emd'], 2, top1[..., None, None].repeat(1, 1, 1, 128)).squeeze(2), 'agent_type': policy['agent_type']}
+        want = model.rollout_batch(b2, scene2, {'motion_pred': chosen}, idsd, model.init_agent_trajs(idsd, b2), [0, 10], 'val')['motion_pred']
+    assert out['goal_prob'].shape == (24, K) and out['goal'].shape == (24, 2)    # carried through like the reference's policy does
+    assert torch.equal(out['motion_pred'], want['motion_pred'])          # ROLLOUT.POLICY.TOP_K = 1: the most probable token
+
+
 def test_graphed_forward_matches_eager_and_accepts_host_batches():
     """CUDA-graph replay (graph_runner.GraphedForward): bit-identical to the eager forward, reusable for a new batch of
     the same shape, fed straight from pinned host memory."""

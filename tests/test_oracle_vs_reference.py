@@ -91,6 +91,51 @@ def test_oracle_bit_equal_to_reference_with_action_noise():
         assert torch.equal(r['traj'], out['rollout_trajs'][name]['traj']), name
 
 
+def test_goal_sampler_helpers_equal_reference():
+    """rollout/gpu_utils.py:125-177 sample_M_goal_cond_to_batch and traj_sam.py:402-439 _select_k_emd_from_batch: same host
+    generator state -> the same draws -> identical tensors (pure index bookkeeping, no device work)."""
+    import copy
+    ref_shim.install_shims()
+    from prosim.rollout.gpu_utils import sample_M_goal_cond_to_batch as ref_sample
+    from prosim_b200.model import select_k_emd_from_batch
+    from prosim_b200.rollout import sample_M_goal_cond_to_batch
+    batch = synthetic.make_batch(n_scenes=1, n_agents=9, n_map=12, steps=20, goal=True)
+    ids = batch.extras['prompt']['motion_pred']['agent_ids'][0]
+    g = torch.Generator().manual_seed(3)
+    K = 6
+    sample = {'motion_pred': {'pair_names': [f'0-{a}-0' for a in ids[:7]],          # two agents without predictions
+                              'goal_point': torch.randn(7, K, 2, generator=g) * 20, 'goal_prob': torch.rand(7, K, generator=g)}}
+    sample['motion_pred']['goal_point'][2] *= 0.01                                     # snapped to (0, 0): inside smooth_dist
+    b1, b2 = copy.deepcopy(batch), copy.deepcopy(batch)
+    torch.manual_seed(11)
+    b1 = ref_sample(b1, copy.deepcopy(sample), top_K=3, M=4, stop_smooth_num=5.0)
+    torch.manual_seed(11)
+    b2 = sample_M_goal_cond_to_batch(b2, copy.deepcopy(sample), 3, 4, stop_smooth_num=5.0)
+    c1, c2 = b1.extras['condition'].all_cond['goal'], b2.extras['condition'].all_cond['goal']
+    assert sorted(c1.keys()) == sorted(c2.keys())
+    for k in ('input', 'mask', 'prompt_idx', 'prompt_mask'):
+        assert torch.equal(c1[k], c2[k]), k
+    assert (c2['input'][:, 2, :2] == 0).all() and c2['input'].shape == (4, 7, 3)
+    # _select_k_emd_from_batch on K goal-conditioned policy tokens per agent
+    m, _ = ref_shim.build_reference_model(())
+    emds = {'emd': torch.randn(2, 5, K, 128, generator=g), 'goal_prob': torch.rand(2, 5, K, generator=g),
+            'goal_point': torch.randn(2, 5, K, 2, generator=g), 'agent_type': torch.ones(2, 5, dtype=torch.long)}
+    m.mode = 'val'
+    torch.manual_seed(5)
+    r = m._select_k_emd_from_batch(dict(emds), None)
+    torch.manual_seed(5)
+    mine = select_k_emd_from_batch(dict(emds), None, 'val', m.rollout_top_k, m.rollout_top_k_train, torch.device('cpu'))
+    for k in ('emd', 'goal', 'select_idx'):
+        assert torch.equal(r[k], mine[k]), k
+    m.rollout_top_k = 3
+    torch.manual_seed(6)
+    r = m._select_k_emd_from_batch(dict(emds), None)
+    torch.manual_seed(6)
+    mine = select_k_emd_from_batch(dict(emds), None, 'val', 3, 1, torch.device('cpu'))
+    assert torch.equal(r['emd'], mine['emd']) and mine['emd'].shape == (2, 5, 128)
+    assert not torch.equal(mine['select_idx'], emds['goal_prob'].argmax(-1))            # top-3 sampling really samples
+
+
 def test_world_transform_equals_reference():
     """oracle.rollout_trajs_in_world == the reference's obtain_rollout_trajs_in_world (rollout/gpu_utils.py:230-281)."""
     import math
