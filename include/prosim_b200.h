@@ -53,7 +53,8 @@ int prosim_abi_version(void);
  * >= 1024 rows: csrc/post_sw.cuh, 32 rows per CTA, up to 9472 rows; csrc/tc_post.cuh, 128 rows per CTA, above), the K'|V'
  * projections (csrc/kv_tc.cuh) and the PointNet encoders (csrc/pointnet_tc.cuh); 0 = fp32 FFMA kernels everywhere (A/B
  * measurement and parity cross-checks).  Other values select kernels by bit (1 node kernels, 2 K'|V', 4 PointNet, 8 allow
- * the 32-row node kernel) for fault isolation.  PROCESS-GLOBAL switch. */
+ * the 32-row node kernel, 16 the fused single-launch edge phase of launches <= 592 rows) for fault isolation.
+ * PROCESS-GLOBAL switch. */
 int prosim_set_tensor_core(int on);
 /* prosim_attn_stack_fwd with fixed sources on both sides runs as up to `parts` (1..4, default 1) independent row chains of
  * >= 1024 rows on internal side streams (forked from / joined to the caller's stream with events; capturable in a CUDA

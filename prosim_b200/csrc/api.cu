@@ -3,7 +3,6 @@
 
 #include "attn.cuh"
 #include "attn2.cuh"
-#include "edge2.cuh"
 #include "edge4.cuh"
 #include "common.cuh"
 #include "graph.cuh"
@@ -25,9 +24,10 @@ namespace {
 
 int g_split = 1;        // row-split chains of prosim_attn_stack_fwd (prosim_set_stack_split); measured 31.4 / 30.9 / 30.6 / 31.4 ms at 1..4 parts
 bool g_use_tc = true;   // node-side GEMMs on tcgen05 (tc_post.cuh); prosim_set_tensor_core(0) selects the FFMA kernels
-int g_tc_mask = 15;     // bit 0: node kernel, bit 1: K'|V', bit 2: PointNet, bit 3: the 32-row "swapped" node kernel (post_sw.cuh) for
-                        // launches it fills the chip with (prosim_set_tensor_core(mask), A/B and fault isolation)
+int g_tc_mask = 31;     // bit 0: node kernels, bit 1: K'|V', bit 2: PointNet, bit 3: the 32-row "swapped" node kernel (post_sw.cuh),
+                        // bit 4: the fused small-launch edge kernel (prosim_set_tensor_core(mask), A/B and fault isolation)
 constexpr int SW_MAX_ROWS = 148 * 32 * 2;   // above two waves of 32-row CTAs the 128-row kernel streams 4x less weight per row
+constexpr int FUSED_EDGE_MAX_ROWS = 592;    // small launches: one fused edge launch instead of three (see launch_edge)
 constexpr int ERR_ARG = -1;
 constexpr int ERR_WORKSPACE = -2;
 
@@ -100,6 +100,8 @@ int setup_attributes() {
   E4_ATTR(96, 1); E4_ATTR(96, 2); E4_ATTR(96, 4); E4_ATTR(96, 8); E4_ATTR(96, 12);
   E4_ATTR(128, 1); E4_ATTR(128, 2); E4_ATTR(128, 4); E4_ATTR(128, 8); E4_ATTR(128, 10);
 #undef E4_ATTR
+  acc(allow_smem(attn_edge4_kernel<96, 2, true>, Edge4Cfg<96>::smem_bytes(2)));
+  acc(allow_smem(attn_edge4_kernel<128, 2, true>, Edge4Cfg<128>::smem_bytes(2)));
   acc(allow_smem(attn_post_kernel<8>, PostSmem<8>::bytes));
   acc(allow_smem(attn_post_kernel<4>, PostSmem<4>::bytes));
   acc(allow_smem(attn_post_kernel<2>, PostSmem<2>::bytes));
@@ -270,7 +272,7 @@ int launch_edge4(const CUtensorMap& tm, const CUtensorMap& tm32, const DstScratc
                  float* pw, float* ft, int ft_tiles, int* counter, cudaStream_t st) {
   const int grid = (n_dst + NW - 1) / NW < 148 ? (n_dst + NW - 1) / NW : 148;   // one persistent CTA per SM
   attn_edge4_kernel<ZD, NW><<<grid, NW * 32, Edge4Cfg<ZD>::smem_bytes(NW), st>>>(tm, tm32, d.qhat, sk, g.deg, g.stride, n_dst, rbar,
-                                                                              pw, ft, ft_tiles, counter);
+                                                                              pw, ft, ft_tiles, counter, Edge4Fused{});
   PROSIM_CHECK_LAUNCH();
   return 0;
 }
@@ -285,6 +287,21 @@ int launch_edge(const DstScratch& d, const float* kv, const prosim_graph_t& g, i
   if (int e = make_z_map(&tm, g.z, z_rows, g.zd)) return e;
   if (int e = make_map2d(&tm32, g.z, z_rows, g.zd, 32)) return e;
   const int ft_tiles = (g.stride + 31) / 32;
+  if (n_dst <= FUSED_EDGE_MAX_ROWS && (g_tc_mask & 16)) {
+    // small launch: q.K' scores, the z pass and the V' aggregation of a row by one warp in ONE launch (one row per warp,
+    // 2 warps per CTA: e.g. 64 CTAs for a single 128-agent scene)
+    LaunchScope ls(PROSIM_K_ATTN_EDGE, st);
+    const Edge4Fused fz{d.q, kv, g.nbr, aggv};
+    const int grid = (n_dst + 1) / 2;
+    if (g.zd == 96)
+      attn_edge4_kernel<96, 2, true><<<grid, 64, Edge4Cfg<96>::smem_bytes(2), st>>>(tm, tm32, d.qhat, sk, g.deg, g.stride, n_dst, rbar, pw,
+                                                                                   ft, ft_tiles, counter, fz);
+    else
+      attn_edge4_kernel<128, 2, true><<<grid, 64, Edge4Cfg<128>::smem_bytes(2), st>>>(tm, tm32, d.qhat, sk, g.deg, g.stride, n_dst, rbar, pw,
+                                                                                     ft, ft_tiles, counter, fz);
+    PROSIM_CHECK_LAUNCH();
+    return 0;
+  }
   {
     LaunchScope ls(PROSIM_K_EDGE_QK, st);
     edge_qk_kernel<<<(n_dst + 7) / 8, 256, 0, st>>>(d.q, kv, g.nbr, g.deg, g.stride, n_dst, sk, counter);
@@ -377,7 +394,7 @@ int prosim_set_stack_split(int parts) {
 }
 int prosim_set_tensor_core(int on) {
   g_use_tc = on != 0;
-  g_tc_mask = on == 1 ? 15 : (on & 15);  // 1 = everything (the default); other values select kernels by bit
+  g_tc_mask = on == 1 ? 31 : (on & 31);  // 1 = everything (the default); other values select kernels by bit
   return 0;
 }
 

@@ -23,13 +23,10 @@ namespace prosim {
 // ---- gather kernels: a warp per destination row, lane = 4 of the 128 columns, EB edges in flight per lane
 constexpr int GATHER_EB = 8;
 
-// Sk[row*stride + e][h] = sum_c q[row][h*16+c] * K'[nbr[e]][h*16+c]
-__global__ void __launch_bounds__(256) edge_qk_kernel(const float* __restrict__ Qg, const float* __restrict__ KV,
-                                                      const int* __restrict__ nbr, const int* __restrict__ deg, int stride,
-                                                      int n_dst, float* __restrict__ Sk, int* __restrict__ row_counter) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) *row_counter = 0;   // dynamic row queue of the attn_edge4 launch that follows
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= n_dst) return;
+// Sk[row*stride + e][h] = sum_c q[row][h*16+c] * K'[nbr[e]][h*16+c]   -- one destination row, one warp
+__device__ __forceinline__ void edge_qk_row(const float* __restrict__ Qg, const float* __restrict__ KV,
+                                            const int* __restrict__ nbr, const int* __restrict__ deg, int stride, int row,
+                                            int lane, float* __restrict__ Sk) {
   const int n_e = min(deg[row], stride);
   const size_t ebase = (size_t)row * stride;
   const float4 q4 = __ldg(reinterpret_cast<const float4*>(Qg + (size_t)row * D) + lane);
@@ -54,22 +51,33 @@ __global__ void __launch_bounds__(256) edge_qk_kernel(const float* __restrict__ 
   }
 }
 
+__global__ void __launch_bounds__(256) edge_qk_kernel(const float* __restrict__ Qg, const float* __restrict__ KV,
+                                                      const int* __restrict__ nbr, const int* __restrict__ deg, int stride,
+                                                      int n_dst, float* __restrict__ Sk, int* __restrict__ row_counter) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *row_counter = 0;   // dynamic row queue of the attn_edge4 launch that follows
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n_dst) return;
+  edge_qk_row(Qg, KV, nbr, deg, stride, row, lane, Sk);
+}
+
 // AggV[row][c] = sum_e a[e][c/16] * V'[nbr[e]][c]   (edges in ascending order)
 // Ft (nullable): per (row, 32-edge tile, head) factor that turns the unnormalised weights of attn_edge4_kernel into
 // attention weights; NULL = Pw already holds them (attn_edge3_kernel).
-__global__ void __launch_bounds__(256) edge_av_kernel(const float* __restrict__ Pw, const float* __restrict__ Ft, int ft_tiles,
-                                                      const float* __restrict__ KV, const int* __restrict__ nbr,
-                                                      const int* __restrict__ deg, int stride, int n_dst,
-                                                      float* __restrict__ AggV) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= n_dst) return;
+// COHERENT: Pw / Ft were written earlier by THIS kernel (fused small-launch edge kernel): read them through L2, not through
+// the non-coherent read-only path
+template <bool COHERENT = false>
+__device__ __forceinline__ void edge_av_row(const float* __restrict__ Pw, const float* __restrict__ Ft, int ft_tiles,
+                                            const float* __restrict__ KV, const int* __restrict__ nbr,
+                                            const int* __restrict__ deg, int stride, int row, int lane,
+                                            float* __restrict__ AggV) {
   const int n_e = min(deg[row], stride);
   const size_t ebase = (size_t)row * stride;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int e0 = 0; e0 < n_e; e0 += 32) {
     const int jl = e0 + lane < n_e ? __ldg(nbr + ebase + e0 + lane) : 0;
     const int nt = min(32, n_e - e0);
-    const float f = Ft != nullptr ? __ldg(Ft + ((size_t)row * ft_tiles + (e0 >> 5)) * 8 + (lane >> 2)) : 1.0f;
+    const float* fp = Ft + ((size_t)row * ft_tiles + (e0 >> 5)) * 8 + (lane >> 2);
+    const float f = Ft != nullptr ? (COHERENT ? __ldcg(fp) : __ldg(fp)) : 1.0f;
     for (int g = 0; g < nt; g += GATHER_EB) {
       float4 v4[GATHER_EB];
       float a[GATHER_EB];
@@ -78,7 +86,8 @@ __global__ void __launch_bounds__(256) edge_av_kernel(const float* __restrict__ 
         const int eu = min(g + u, nt - 1);
         const int j = __shfl_sync(0xffffffffu, jl, eu);
         v4[u] = __ldg(reinterpret_cast<const float4*>(KV + (size_t)j * 256 + 128) + lane);
-        a[u] = g + u < nt ? __ldg(Pw + (ebase + e0 + eu) * 8 + (lane >> 2)) * f : 0.f;
+        const float* pp = Pw + (ebase + e0 + eu) * 8 + (lane >> 2);
+        a[u] = g + u < nt ? (COHERENT ? __ldcg(pp) : __ldg(pp)) * f : 0.f;
       }
 #pragma unroll
       for (int u = 0; u < GATHER_EB; ++u) {
@@ -90,6 +99,15 @@ __global__ void __launch_bounds__(256) edge_av_kernel(const float* __restrict__ 
     }
   }
   *reinterpret_cast<float4*>(AggV + (size_t)row * D + 4 * lane) = acc;
+}
+
+__global__ void __launch_bounds__(256) edge_av_kernel(const float* __restrict__ Pw, const float* __restrict__ Ft, int ft_tiles,
+                                                      const float* __restrict__ KV, const int* __restrict__ nbr,
+                                                      const int* __restrict__ deg, int stride, int n_dst,
+                                                      float* __restrict__ AggV) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= n_dst) return;
+  edge_av_row(Pw, Ft, ft_tiles, KV, nbr, deg, stride, row, lane, AggV);
 }
 
 }  // namespace prosim

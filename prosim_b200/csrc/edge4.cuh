@@ -19,6 +19,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "edge2.cuh"
 
 namespace prosim {
 namespace e4 {
@@ -31,9 +32,10 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
 }
+// bounded wait: a protocol bug traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -43,7 +45,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
-  } while (!done);
+    if (spin > (1u << 22)) __trap();
+  }
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 // L2 policy for data that is read exactly once (the z stream): do not let it push the layer's reusable buffers
@@ -81,12 +84,22 @@ struct Edge4Cfg {
   static constexpr size_t smem_bytes(int nw) { return 1024 + (size_t)nw * WARP_BYTES + (size_t)nw * 8; }
 };
 
-template <int ZD, int NW>
+// FUSED (small launches, one row per warp, no row queue): the warp also computes its row's q.K' scores before the z pass
+// (edge_qk_row) and the V' aggregation after it (edge_av_row) -- one launch instead of three where launch latency, not
+// throughput, is the cost (a single 128-agent scene: 120 x 3 launches of ~15 us each per forward).  Same arithmetic.
+struct Edge4Fused {
+  const float* Qg;     // [n_dst][128] queries
+  const float* KV;     // [n_src][256] K'|V'
+  const int* nbr;      // neighbour lists
+  float* AggV;         // [n_dst][128]
+};
+
+template <int ZD, int NW, bool FUSED = false>
 __global__ void __launch_bounds__(NW * 32, 1)
     attn_edge4_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmZ32,
-                      const float* __restrict__ Qhat, const float* __restrict__ Sk,
-                      const int* __restrict__ deg, int stride, int n_dst, float* __restrict__ Rbar, float* __restrict__ Pw,
-                      float* __restrict__ Ft, int ft_tiles, int* __restrict__ row_counter) {
+                      const float* __restrict__ Qhat, const float* Sk,
+                      const int* __restrict__ deg, int stride, int n_dst, float* __restrict__ Rbar, float* Pw,
+                      float* Ft, int ft_tiles, int* __restrict__ row_counter, Edge4Fused fz) {
   using C = Edge4Cfg<ZD>;
   constexpr int NSEG = C::NSEG;
   extern __shared__ uint8_t smem_raw[];
@@ -115,14 +128,20 @@ __global__ void __launch_bounds__(NW * 32, 1)
   // only 2-5 rows of 1-16 tiles each, so a static split leaves a quarter of the warps idle at the tail
   int row = blockIdx.x * NW + warp;
   int row_next = 0;
-  for (; row < n_dst; row = __shfl_sync(0xffffffffu, row_next, 0)) {
-    if (lane == 0) row_next = gridDim.x * NW + atomicAdd(row_counter, 1);   // consumed at the end of this row
+  for (; row < n_dst; row = FUSED ? n_dst : __shfl_sync(0xffffffffu, row_next, 0)) {
+    if (!FUSED && lane == 0) row_next = gridDim.x * NW + atomicAdd(row_counter, 1);   // consumed at the end of this row
     const int n_e = min(__ldg(deg + row), stride);
     const size_t ebase = (size_t)row * stride;
     float* rb = Rbar + (size_t)row * H * ZD;
+    if (FUSED) {
+      edge_qk_row(fz.Qg, fz.KV, fz.nbr, deg, stride, row, lane, const_cast<float*>(Sk));
+      __threadfence_block();      // the scores are read back below by other lanes of this warp
+      __syncwarp();
+    }
     if (n_e <= 0) {   // no in-edges: the aggregate is zero (the gate / FFN update still runs on the row)
 #pragma unroll
       for (int i = 0; i < H * NSEG; ++i) rb[i * 32 + lane] = 0.f;
+      if (FUSED) edge_av_row<true>(Pw, Ft, ft_tiles, fz.KV, fz.nbr, deg, stride, row, lane, fz.AggV);
       continue;
     }
     const int ntiles = (n_e + 31) >> 5;
@@ -165,8 +184,8 @@ __global__ void __launch_bounds__(NW * 32, 1)
         float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
         if (valid) {
           const float4* sp = reinterpret_cast<const float4*>(Sk + (ebase + t0 + lane) * 8);
-          s0 = __ldg(sp);
-          s1 = __ldg(sp + 1);
+          s0 = FUSED ? __ldcg(sp) : __ldg(sp);
+          s1 = FUSED ? __ldcg(sp + 1) : __ldg(sp + 1);
         }
         acc[0] = make_float2(s0.x, 0.f); acc[1] = make_float2(s0.y, 0.f);
         acc[2] = make_float2(s0.z, 0.f); acc[3] = make_float2(s0.w, 0.f);
@@ -284,6 +303,11 @@ __global__ void __launch_bounds__(NW * 32, 1)
       const float ih = pb[lane & 7];
       float* ft = Ft + (size_t)row * ft_tiles * H;
       for (int i = lane; i < ntiles * H; i += 32) ft[i] = expf(mt[i] - mh) * ih;
+    }
+    if (FUSED) {
+      __threadfence_block();      // Pw / Ft of this row were written by other lanes of this warp
+      __syncwarp();
+      edge_av_row<true>(Pw, Ft, ft_tiles, fz.KV, fz.nbr, deg, stride, row, lane, fz.AggV);
     }
   }
 }

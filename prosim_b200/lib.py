@@ -156,8 +156,8 @@ def profile_read():
 
 def set_tensor_core(on):
     """Tensor-core (tcgen05 / TMEM, 3xTF32) kernels: True = all of them (the default), False = fp32 FFMA kernels, an int
-    mask selects by bit -- 1 node kernel (launches >= 1024 rows), 2 K'|V', 4 PointNet, 8 the 32-row "swapped" node kernel
-    (post_sw.cuh) where it applies (7 = the 128-row node kernel of tc_post.cuh everywhere).  PROCESS-WIDE switch."""
+    mask selects by bit -- 1 node kernels, 2 K'|V', 4 PointNet, 8 the 32-row "swapped" node kernel (post_sw.cuh; 7 = the 128-row
+    kernel of tc_post.cuh for launches >= 1024 rows, FFMA below), 16 the fused single-launch edge phase of small launches.  PROCESS-WIDE switch."""
     call('prosim_set_tensor_core', int(on) if not isinstance(on, bool) else (1 if on else 0))
 
 
