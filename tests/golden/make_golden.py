@@ -20,7 +20,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle import ref_shim  # noqa: E402
 from prosim_b200 import synthetic, weights  # noqa: E402
 
-from tests.helpers import BENCH_CASES, CASES, cond_suffix, to_double as _to_double  # noqa: E402
+from tests.helpers import BENCH_CASES, CASES, DEMO_CASES, cond_suffix, to_double as _to_double  # noqa: E402
 
 
 def _collect(out, ids):
@@ -42,6 +42,9 @@ def main():
     only = sys.argv[1:]                      # optional: regenerate just the named cases
     keep = {n: c[2] for n, c in BENCH_CASES.items()}
     cases = {n: c[:2] for n, c in list(CASES.items()) + list(BENCH_CASES.items()) if not only or n in only}
+    demo = {n: kw for n, kw in DEMO_CASES.items() if not only or n in only}
+    if demo:
+        cases.update({n: (None, False) for n in demo})
     models = {}
     for goal in dict.fromkeys(c[1] for c in cases.values()):
         sd = weights.random_state_dict(0, goal)
@@ -56,7 +59,12 @@ def main():
                        'abs_checksum': float(sum(v.double().abs().sum() for v in sd.values()))}, f)
     for name, (kw, goal) in cases.items():
         m32, m64 = models[goal]
-        b32 = synthetic.make_batch(**kw)
+        if name in demo:      # a real scene of the reference's demo_dataset through the mini-loader
+            from prosim_b200 import demo_loader
+            make = lambda: demo_loader.load_demo_scene(os.path.join(ref_shim.REF_ROOT, 'demo_dataset'), **demo[name])
+        else:
+            make = lambda: synthetic.make_batch(**kw)
+        b32 = make()
         ids = b32.extras['prompt']['motion_pred']['agent_ids']
         with torch.no_grad():
             out32 = m32.forward(b32, 'val')['motion_pred']
@@ -64,7 +72,7 @@ def main():
         torch.set_default_dtype(torch.float64)
         try:
             with torch.no_grad():
-                out64 = m64.forward(_to_double(synthetic.make_batch(**kw)), 'val')['motion_pred']
+                out64 = m64.forward(_to_double(make()), 'val')['motion_pred']
         finally:
             torch.set_default_dtype(prev)
         res = _collect(out32, ids)
@@ -72,6 +80,9 @@ def main():
         res['traj64'], res['vel64'], res['motion_pred64'] = r64['traj'], r64['vel'], r64['motion_pred']
         gap = np.abs(res['traj'][..., :2].astype(np.float64) - res['traj64'][..., :2]).reshape(len(res['traj']), -1, 10, 2)
         print(name, 'fp32-vs-fp64 xy gap per tick:', ['%.1e' % g for g in gap.max(axis=(0, 2, 3))])
+        if name in demo:
+            from prosim_b200 import demo_loader
+            res.update({'batch.' + k: v for k, v in demo_loader.batch_to_arrays(make()).items()})
         if name in keep:                     # large batch: keep the rows of a few scenes of THIS run (file size)
             scenes = [int(n.split('-')[0]) for n in res['agent_names']]
             rows = np.array([i for i, sc in enumerate(scenes) if sc in keep[name]])

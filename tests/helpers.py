@@ -33,6 +33,17 @@ BENCH_CASES = {
 }
 
 
+# BASELINE configs[0], literal: a scene of the reference's demo_dataset (prosim_b200/demo_loader.py), 16 agents, 20 steps.
+# The fixture holds the loaded batch itself (the GPU box has no demo_dataset) next to the reference's rollout of it.
+DEMO_CASES = {'cfg1_demo_scene6_a16_s20': dict(scene='scene_6', ts=10, steps=20, max_agents=16)}
+
+
+def demo_batch(name):
+    from prosim_b200 import demo_loader
+    g = load_golden(name)
+    return demo_loader.batch_from_arrays({k[len('batch.'):]: v for k, v in g.items() if k.startswith('batch.')})
+
+
 def cond_suffix(cond):
     """File-name suffix of the per-model fixtures."""
     return '' if not cond else '_goal' if cond is True else '_' + '_'.join(cond)
