@@ -22,6 +22,8 @@ using namespace prosim;
 
 namespace {
 
+constexpr int g_rt2_min_rows = 128;   // row count from which the 32-row gemm_tile kernels (dstpre2, head2; bit-identical) replace the
+                                      // 2..16-row ones: measured on one 128-agent scene, 12.07 ms per forward at 1024, 11.82 at 128
 int g_split = 1;        // row-split chains of prosim_attn_stack_fwd (prosim_set_stack_split); measured 31.4 / 30.9 / 30.6 / 31.4 ms at 1..4 parts
 bool g_use_tc = true;   // node-side GEMMs on tcgen05 (tc_post.cuh); prosim_set_tensor_core(0) selects the FFMA kernels
 int g_tc_mask = 31;     // bit 0: node kernels, bit 1: K'|V', bit 2: PointNet, bit 3: the 32-row "swapped" node kernel (post_sw.cuh),
@@ -70,7 +72,7 @@ inline int pick_rpt(int n_rows) {
 // v2 (gemm_tile.cuh) kernels for throughput-sized launches: rows per CTA = 16*RT; 0 => use the v1 latency kernels
 inline int pick_rt(int n_rows) {
   if (n_rows >= 64 * 120) return 4;
-  if (n_rows >= 1024) return 2;
+  if (n_rows >= g_rt2_min_rows) return 2;
   return 0;
 }
 

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""profiles/r1_kernel_traffic.json from the raw page of the per-layer `ncu --set full` capture (tools/profile_round.sh):
+"""profiles/r<N>_kernel_traffic.json from the raw page of the per-layer `ncu --set full` capture (tools/profile_round.sh):
 DRAM bytes, duration and tensor-pipe activity of the four kernels of the first policy a2p layer and of the first m2p layer.
 usage: kernel_traffic.py gpurun_out/r1_layer_v8_raw.csv profiles/r1_layer_v8_ncu_summary.txt > profiles/r1_kernel_traffic.json"""
 import csv
@@ -22,6 +22,8 @@ labels = ['policy a2p layer 0 (380k edges, 4096 rows)'] * 4 + ['policy m2p layer
 out = {}
 for d, lab in zip(data, labels):
     name = d[idx['Kernel Name']].split('(')[0].replace('void ', '').replace('prosim::', '').split('<')[0]
+    if name == 'attn_post_sw_kernel':
+        name = 'psw::attn_post_sw_kernel'
     out[f'{name} {"a2p" if "a2p" in lab else "m2p"}'] = {
         'launch': lab,
         'dram_bytes_read': val(d, 'dram__bytes_read.sum'),
