@@ -67,15 +67,48 @@ def bench_config(a):
 
 # ----------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """Samples SM clock / throttle reasons with nvidia-smi every 100 ms while the timed region runs."""
+    """Samples SM clock / throttle reasons while the timed region runs: NVML in a thread every 20 ms (first sample taken
+    synchronously, so that even a sub-second region is covered); nvidia-smi -lms 100 if NVML cannot be loaded."""
     Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, gpu_index):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES', '').split(',')      # NVML / nvidia-smi count physical devices
+        if gpu_index < len(vis) and vis[gpu_index].strip().isdigit():
+            gpu_index = int(vis[gpu_index])
+        self.idx, self.rows, self.proc, self.nvml, self.stop = gpu_index, [], None, None, threading.Event()
+
+    def _nvml_sample(self):
+        n, h = self.nvml
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        act = lambda bit: 'Active' if r & bit else 'Not Active'
+        self.rows.append([str(self.idx), str(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)),
+                          str(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)), '', hex(r),
+                          act(n.nvmlClocksThrottleReasonHwSlowdown), act(n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                          act(n.nvmlClocksThrottleReasonSwThermalSlowdown), act(n.nvmlClocksThrottleReasonSwPowerCap)])
+
+    def _nvml_loop(self):
+        while not self.stop.wait(0.02):
+            try:
+                self._nvml_sample()
+            except Exception:
+                return
 
     def __enter__(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.idx))
+            self._nvml_sample()
+            self.thr = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thr.start()
+            return self
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.idx}', f'--query-gpu={self.Q}',
                                           '--format=csv,noheader,nounits', '-lms', '100'],
@@ -91,6 +124,13 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(',')])
 
     def __exit__(self, *a):
+        self.stop.set()
+        if self.nvml is not None:
+            self.thr.join(timeout=1)
+            try:
+                self._nvml_sample()
+            except Exception:
+                pass
         if self.proc is not None:
             self.proc.terminate()
             try:

@@ -102,8 +102,8 @@ int setup_attributes() {
   E4_ATTR(96, 1); E4_ATTR(96, 2); E4_ATTR(96, 4); E4_ATTR(96, 8); E4_ATTR(96, 12);
   E4_ATTR(128, 1); E4_ATTR(128, 2); E4_ATTR(128, 4); E4_ATTR(128, 8); E4_ATTR(128, 10);
 #undef E4_ATTR
-  acc(allow_smem(attn_edge4_kernel<96, 2, true>, Edge4Cfg<96>::smem_bytes(2)));
-  acc(allow_smem(attn_edge4_kernel<128, 2, true>, Edge4Cfg<128>::smem_bytes(2)));
+  acc(allow_smem(attn_edge4_kernel<96, 2, true>, Edge4Cfg<96, 4>::smem_bytes(2)));
+  acc(allow_smem(attn_edge4_kernel<128, 2, true>, Edge4Cfg<128, 4>::smem_bytes(2)));
   acc(allow_smem(attn_post_kernel<8>, PostSmem<8>::bytes));
   acc(allow_smem(attn_post_kernel<4>, PostSmem<4>::bytes));
   acc(allow_smem(attn_post_kernel<2>, PostSmem<2>::bytes));
@@ -195,6 +195,17 @@ int launch_dstpre(const float* x, int n, const float* w, const DstScratch& d, cu
   if (n <= 0) return 0;
   const int rpt = pick_rpt(n);
   LaunchScope ls(PROSIM_K_ATTN_DSTPRE, st);
+  if ((g_tc_mask & 1) && (g_tc_mask & 8)) {
+    // the first layer of a stack has no previous node kernel to carry its destination-side projections: the 32-row tcgen05
+    // kernel in its "pre-only" mode runs just that tail (16 of its 58 weight chunks) -- the same arithmetic every later
+    // layer of the stack gets, for any launch size (the FFMA kernels below: 127 us per 16 k-row launch, 39 us for 128 rows)
+    psw::Args a{};
+    a.x = x; a.q_n = d.q; a.qhat_n = d.qhat; a.s_n = d.s; a.gx_n = d.gx;
+    a.W = nullptr; a.Wn = w; a.n = n;
+    psw::attn_post_sw_kernel<96><<<(n + psw::NR - 1) / psw::NR, psw::THREADS, psw::SMEM_BYTES, st>>>(a);
+    PROSIM_CHECK_LAUNCH();
+    return 0;
+  }
   const int rt = pick_rt(n);
   if (rt == 4) {
     attn_dstpre2_kernel<8, 8><<<(n + 63) / 64, 256, Pre2Smem<8, 8>::bytes, st>>>(x, n, w, d.q, d.qhat, d.s, d.gx);
@@ -296,10 +307,10 @@ int launch_edge(const DstScratch& d, const float* kv, const prosim_graph_t& g, i
     const Edge4Fused fz{d.q, kv, g.nbr, aggv};
     const int grid = (n_dst + 1) / 2;
     if (g.zd == 96)
-      attn_edge4_kernel<96, 2, true><<<grid, 64, Edge4Cfg<96>::smem_bytes(2), st>>>(tm, tm32, d.qhat, sk, g.deg, g.stride, n_dst, rbar, pw,
+      attn_edge4_kernel<96, 2, true><<<grid, 64, Edge4Cfg<96, 4>::smem_bytes(2), st>>>(tm, tm32, d.qhat, sk, g.deg, g.stride, n_dst, rbar, pw,
                                                                                    ft, ft_tiles, counter, fz);
     else
-      attn_edge4_kernel<128, 2, true><<<grid, 64, Edge4Cfg<128>::smem_bytes(2), st>>>(tm, tm32, d.qhat, sk, g.deg, g.stride, n_dst, rbar, pw,
+      attn_edge4_kernel<128, 2, true><<<grid, 64, Edge4Cfg<128, 4>::smem_bytes(2), st>>>(tm, tm32, d.qhat, sk, g.deg, g.stride, n_dst, rbar, pw,
                                                                                      ft, ft_tiles, counter, fz);
     PROSIM_CHECK_LAUNCH();
     return 0;

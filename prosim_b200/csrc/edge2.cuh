@@ -22,8 +22,10 @@ namespace prosim {
 
 // ---- gather kernels: a warp per destination row, lane = 4 of the 128 columns, EB edges in flight per lane
 constexpr int GATHER_EB = 8;
+constexpr int GATHER_EB_FUSED = 32;   // fused small-launch kernel: 1-2 warps per SM, so a whole tile's gathers are in flight at once
 
 // Sk[row*stride + e][h] = sum_c q[row][h*16+c] * K'[nbr[e]][h*16+c]   -- one destination row, one warp
+template <int EB = GATHER_EB>
 __device__ __forceinline__ void edge_qk_row(const float* __restrict__ Qg, const float* __restrict__ KV,
                                             const int* __restrict__ nbr, const int* __restrict__ deg, int stride, int row,
                                             int lane, float* __restrict__ Sk) {
@@ -33,15 +35,15 @@ __device__ __forceinline__ void edge_qk_row(const float* __restrict__ Qg, const 
   for (int e0 = 0; e0 < n_e; e0 += 32) {
     const int jl = e0 + lane < n_e ? __ldg(nbr + ebase + e0 + lane) : 0;
     const int nt = min(32, n_e - e0);
-    for (int g = 0; g < nt; g += GATHER_EB) {
-      float4 k4[GATHER_EB];
+    for (int g = 0; g < nt; g += EB) {
+      float4 k4[EB];
 #pragma unroll
-      for (int u = 0; u < GATHER_EB; ++u) {
+      for (int u = 0; u < EB; ++u) {
         const int j = __shfl_sync(0xffffffffu, jl, min(g + u, nt - 1));
         k4[u] = __ldg(reinterpret_cast<const float4*>(KV + (size_t)j * 256) + lane);
       }
 #pragma unroll
-      for (int u = 0; u < GATHER_EB; ++u) {
+      for (int u = 0; u < EB; ++u) {
         float d = fmaf(q4.w, k4[u].w, fmaf(q4.z, k4[u].z, fmaf(q4.y, k4[u].y, q4.x * k4[u].x)));
         d += __shfl_xor_sync(0xffffffffu, d, 1);
         d += __shfl_xor_sync(0xffffffffu, d, 2);
@@ -65,7 +67,7 @@ __global__ void __launch_bounds__(256) edge_qk_kernel(const float* __restrict__ 
 // attention weights; NULL = Pw already holds them (attn_edge3_kernel).
 // COHERENT: Pw / Ft were written earlier by THIS kernel (fused small-launch edge kernel): read them through L2, not through
 // the non-coherent read-only path
-template <bool COHERENT = false>
+template <bool COHERENT = false, int EB = GATHER_EB>
 __device__ __forceinline__ void edge_av_row(const float* __restrict__ Pw, const float* __restrict__ Ft, int ft_tiles,
                                             const float* __restrict__ KV, const int* __restrict__ nbr,
                                             const int* __restrict__ deg, int stride, int row, int lane,
@@ -78,11 +80,11 @@ __device__ __forceinline__ void edge_av_row(const float* __restrict__ Pw, const 
     const int nt = min(32, n_e - e0);
     const float* fp = Ft + ((size_t)row * ft_tiles + (e0 >> 5)) * 8 + (lane >> 2);
     const float f = Ft != nullptr ? (COHERENT ? __ldcg(fp) : __ldg(fp)) : 1.0f;
-    for (int g = 0; g < nt; g += GATHER_EB) {
-      float4 v4[GATHER_EB];
-      float a[GATHER_EB];
+    for (int g = 0; g < nt; g += EB) {
+      float4 v4[EB];
+      float a[EB];
 #pragma unroll
-      for (int u = 0; u < GATHER_EB; ++u) {
+      for (int u = 0; u < EB; ++u) {
         const int eu = min(g + u, nt - 1);
         const int j = __shfl_sync(0xffffffffu, jl, eu);
         v4[u] = __ldg(reinterpret_cast<const float4*>(KV + (size_t)j * 256 + 128) + lane);
@@ -90,7 +92,7 @@ __device__ __forceinline__ void edge_av_row(const float* __restrict__ Pw, const 
         a[u] = g + u < nt ? (COHERENT ? __ldcg(pp) : __ldg(pp)) * f : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < GATHER_EB; ++u) {
+      for (int u = 0; u < EB; ++u) {
         acc.x = fmaf(a[u], v4[u].x, acc.x);
         acc.y = fmaf(a[u], v4[u].y, acc.y);
         acc.z = fmaf(a[u], v4[u].z, acc.z);

@@ -83,7 +83,9 @@ struct Args {
   const float *x, *rbar, *aggv, *s, *gx;   // [n][128], [n][8 zd], [n][128] ...
   float* out;                              // [n][128]
   float *q_n, *qhat_n, *s_n, *gx_n;        // next layer's destination-side projections (has_next)
-  const float *W, *Wn;                     // packed layer weights (aw::), next layer's (nullptr = last layer)
+  const float *W, *Wn;                     // packed layer weights (aw::), next layer's (nullptr = last layer);
+                                           // W == nullptr: "pre-only" launch -- just Wn's destination-side projections of x
+                                           // (the first layer of a stack, which has no previous node kernel to ride on)
   int n;
 };
 
@@ -137,6 +139,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
   const float* __restrict__ W = a.W;
   const float* __restrict__ Wn = a.Wn;
   const bool has_next = Wn != nullptr;
+  const bool pre_only = W == nullptr;
   constexpr int VR_HALF_BYTES = (ZD / 2) * D * 4;      // the fp32 Wvr' block [ZD][128] travels as two ring stages
 
   if (warp == 0) tc::tmem_alloc(&sm.tmem_base, 512);
@@ -154,10 +157,12 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
   // per-column vectors -> shared memory (same table as tc_post.cuh)
   for (int i = tid; i < tcp::V_SIZE; i += THREADS) {
     float v = 0.f;
-    if (i < tcp::V_B1) v = W[aw::BO + i];
-    else if (i < tcp::V_B2) v = W[aw::B1 + (i - tcp::V_B1)];
-    else if (i < tcp::V_LNDST_G) v = W[aw::B2 + (i - tcp::V_B2)];
-    else if (has_next) {
+    if (i < tcp::V_LNDST_G) {
+      if (pre_only) v = 0.f;
+      else if (i < tcp::V_B1) v = W[aw::BO + i];
+      else if (i < tcp::V_B2) v = W[aw::B1 + (i - tcp::V_B1)];
+      else v = W[aw::B2 + (i - tcp::V_B2)];
+    } else if (has_next) {
       if (i < tcp::V_BQ) v = Wn[aw::LN_DST_G + (i - tcp::V_LNDST_G)];
       else if (i < tcp::V_BS) v = Wn[aw::BQ + (i - tcp::V_BQ)];
       else if (i < tcp::V_BG) v = Wn[aw::BS + (i - tcp::V_BS)];
@@ -170,11 +175,12 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
   tc::fence_after_sync();
   const uint32_t tmem = sm.tmem_base;
   const int n_chunks = has_next ? 58 : 42;
+  const int chunk0 = pre_only ? 42 : 0;             // ring positions count from the first chunk of the launch
 
   if (warp == 8) {
     // ================================================================== weight producer
     if (lane == 0) {
-      for (int i = 0; i < n_chunks; ++i) {
+      for (int i = chunk0; i < n_chunks; ++i) {
         const float* src;
         uint32_t bytes;
         if (i < 2) {
@@ -196,8 +202,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
           src = Wn + aw::TC_KRG + (i - 54) * 8192;   // Wkr' of two heads per stage
           bytes = 32768;
         }
-        const int s = i % NST;
-        if (i >= NST) tcp::mbar_wait(&sm.empty[s], ((i / NST) - 1) & 1);
+        const int k = i - chunk0, s = k % NST;
+        if (k >= NST) tcp::mbar_wait(&sm.empty[s], ((k / NST) - 1) & 1);
         const uint32_t fb = e4::smem_u32(&sm.full[s]);
         e4::mbar_expect_tx(fb, bytes);
         e4::bulk_copy(e4::smem_u32(sm.ring[s]), src, bytes, fb);
@@ -207,7 +213,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
   } else if (warp == 9) {
     // ================================================================== MMA issuer
     if (lane == 0) {
-      int ci = 2;                                  // chunks 0 and 1 (fp32 Wvr') belong to the epilogue warps
+      int ci = pre_only ? 0 : 2;                   // chunks 0 and 1 (fp32 Wvr') belong to the epilogue warps
       uint32_t ph_op = 0, ph_h = 0;
       long long w_full = 0, w_other = 0;
       auto wait_bar = [&](uint64_t* bar, uint32_t& ph) {
@@ -254,6 +260,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
       };
       const uint32_t actA = e4::smem_u32(sm.actA), actH = e4::smem_u32(sm.actH);
       PSW_MARK(16);
+      if (!pre_only) {
       // 1. gate, 2. out projection
       wait_bar(&sm.opnd_ready, ph_op);
       PSW_MARK(18);
@@ -283,6 +290,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
           gemm128(slot_col(2 + t), actA);                 // up_{t+2} reuses the slot of up_t (read before h_ready was signalled)
           tc::mma_commit(&sm.acc_done[A_UP + t + 2]);
         }
+      }
       }
       PSW_MARK(23);
       if (has_next) {
@@ -438,6 +446,12 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
 #define PSW_EMARK(slot) do { if (tid == 0) PSW_MARK(slot); } while (0)
     PSW_EMARK(0);
     float v[16];
+    if (pre_only) {            // LN_dst'(x) -> operand A, then straight to the projections
+      r_load_glb(a.x, v);
+      r_layernorm(v, tcp::V_LNDST_G, tcp::V_LNDST_B);
+      r_store_opnd(sm.actA, v);
+      publish(&sm.opnd_ready);
+    } else {
     // ---- 0. agg[row][16 h ..] = AggV + sum_d Rbar[row][h][d] Wvr'[d][16 h ..]   (H-map: row = lane, head = warp)
     //         fp32 FFMA, the row's Rbar_h in registers, the weights read as warp-wide broadcasts from the ring (two
     //         stages hold the fp32 [ZD][128] block); ascending d like the FFMA node kernels
@@ -569,6 +583,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
         publish(&sm.opnd_ready);
       }
       PSW_EMARK(10);
+    }
     }
     if (has_next) {
       // ---- 4. q, s, gx (+ bias) -> global as coalesced lines (T-map); q also -> operand H
