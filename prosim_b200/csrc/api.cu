@@ -14,6 +14,7 @@
 #include "tc_gemm.cuh"
 #include "tc_post.cuh"
 #include "post_sw.cuh"
+#include "edge_row.cuh"
 #include "weights_layout.h"
 
 #include <cudaTypedefs.h>
@@ -102,8 +103,8 @@ int setup_attributes() {
   E4_ATTR(96, 1); E4_ATTR(96, 2); E4_ATTR(96, 4); E4_ATTR(96, 8); E4_ATTR(96, 12);
   E4_ATTR(128, 1); E4_ATTR(128, 2); E4_ATTR(128, 4); E4_ATTR(128, 8); E4_ATTR(128, 10);
 #undef E4_ATTR
-  acc(allow_smem(attn_edge4_kernel<96, 2, true>, Edge4Cfg<96, 4>::smem_bytes(2)));
-  acc(allow_smem(attn_edge4_kernel<128, 2, true>, Edge4Cfg<128, 4>::smem_bytes(2)));
+  acc(allow_smem(attn_edge_row_kernel<96>, EdgeRowCfg<96>::smem_bytes()));
+  acc(allow_smem(attn_edge_row_kernel<128>, EdgeRowCfg<128>::smem_bytes()));
   acc(allow_smem(attn_post_kernel<8>, PostSmem<8>::bytes));
   acc(allow_smem(attn_post_kernel<4>, PostSmem<4>::bytes));
   acc(allow_smem(attn_post_kernel<2>, PostSmem<2>::bytes));
@@ -285,7 +286,7 @@ int launch_edge4(const CUtensorMap& tm, const CUtensorMap& tm32, const DstScratc
                  float* pw, float* ft, int ft_tiles, int* counter, cudaStream_t st) {
   const int grid = (n_dst + NW - 1) / NW < 148 ? (n_dst + NW - 1) / NW : 148;   // one persistent CTA per SM
   attn_edge4_kernel<ZD, NW><<<grid, NW * 32, Edge4Cfg<ZD>::smem_bytes(NW), st>>>(tm, tm32, d.qhat, sk, g.deg, g.stride, n_dst, rbar,
-                                                                              pw, ft, ft_tiles, counter, Edge4Fused{});
+                                                                              pw, ft, ft_tiles, counter);
   PROSIM_CHECK_LAUNCH();
   return 0;
 }
@@ -301,17 +302,14 @@ int launch_edge(const DstScratch& d, const float* kv, const prosim_graph_t& g, i
   if (int e = make_map2d(&tm32, g.z, z_rows, g.zd, 32)) return e;
   const int ft_tiles = (g.stride + 31) / 32;
   if (n_dst <= FUSED_EDGE_MAX_ROWS && (g_tc_mask & 16)) {
-    // small launch: q.K' scores, the z pass and the V' aggregation of a row by one warp in ONE launch (one row per warp,
-    // 2 warps per CTA: e.g. 64 CTAs for a single 128-agent scene)
+    // small launch: q.K' scores, the z pass and the V' aggregation in ONE launch, one CTA of four warps per row (edge_row.cuh)
     LaunchScope ls(PROSIM_K_ATTN_EDGE, st);
-    const Edge4Fused fz{d.q, kv, g.nbr, aggv};
-    const int grid = (n_dst + 1) / 2;
     if (g.zd == 96)
-      attn_edge4_kernel<96, 2, true><<<grid, 64, Edge4Cfg<96, 4>::smem_bytes(2), st>>>(tm, tm32, d.qhat, sk, g.deg, g.stride, n_dst, rbar, pw,
-                                                                                   ft, ft_tiles, counter, fz);
+      attn_edge_row_kernel<96><<<n_dst, 128, EdgeRowCfg<96>::smem_bytes(), st>>>(tm, tm32, d.qhat, d.q, kv, g.nbr, g.deg, g.stride, n_dst,
+                                                                              sk, rbar, pw, ft, ft_tiles, aggv);
     else
-      attn_edge4_kernel<128, 2, true><<<grid, 64, Edge4Cfg<128, 4>::smem_bytes(2), st>>>(tm, tm32, d.qhat, sk, g.deg, g.stride, n_dst, rbar, pw,
-                                                                                     ft, ft_tiles, counter, fz);
+      attn_edge_row_kernel<128><<<n_dst, 128, EdgeRowCfg<128>::smem_bytes(), st>>>(tm, tm32, d.qhat, d.q, kv, g.nbr, g.deg, g.stride, n_dst,
+                                                                                sk, rbar, pw, ft, ft_tiles, aggv);
     PROSIM_CHECK_LAUNCH();
     return 0;
   }

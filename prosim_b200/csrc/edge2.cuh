@@ -22,17 +22,16 @@ namespace prosim {
 
 // ---- gather kernels: a warp per destination row, lane = 4 of the 128 columns, EB edges in flight per lane
 constexpr int GATHER_EB = 8;
-constexpr int GATHER_EB_FUSED = 32;   // fused small-launch kernel: 1-2 warps per SM, so a whole tile's gathers are in flight at once
 
 // Sk[row*stride + e][h] = sum_c q[row][h*16+c] * K'[nbr[e]][h*16+c]   -- one destination row, one warp
 template <int EB = GATHER_EB>
 __device__ __forceinline__ void edge_qk_row(const float* __restrict__ Qg, const float* __restrict__ KV,
                                             const int* __restrict__ nbr, const int* __restrict__ deg, int stride, int row,
-                                            int lane, float* __restrict__ Sk) {
+                                            int lane, float* __restrict__ Sk, int tile_first = 0, int tile_step = 1) {
   const int n_e = min(deg[row], stride);
   const size_t ebase = (size_t)row * stride;
   const float4 q4 = __ldg(reinterpret_cast<const float4*>(Qg + (size_t)row * D) + lane);
-  for (int e0 = 0; e0 < n_e; e0 += 32) {
+  for (int e0 = 32 * tile_first; e0 < n_e; e0 += 32 * tile_step) {   // (tile_first, tile_step): the caller's share of the row
     const int jl = e0 + lane < n_e ? __ldg(nbr + ebase + e0 + lane) : 0;
     const int nt = min(32, n_e - e0);
     for (int g = 0; g < nt; g += EB) {
@@ -65,9 +64,7 @@ __global__ void __launch_bounds__(256) edge_qk_kernel(const float* __restrict__ 
 // AggV[row][c] = sum_e a[e][c/16] * V'[nbr[e]][c]   (edges in ascending order)
 // Ft (nullable): per (row, 32-edge tile, head) factor that turns the unnormalised weights of attn_edge4_kernel into
 // attention weights; NULL = Pw already holds them (attn_edge3_kernel).
-// COHERENT: Pw / Ft were written earlier by THIS kernel (fused small-launch edge kernel): read them through L2, not through
-// the non-coherent read-only path
-template <bool COHERENT = false, int EB = GATHER_EB>
+template <int EB = GATHER_EB>
 __device__ __forceinline__ void edge_av_row(const float* __restrict__ Pw, const float* __restrict__ Ft, int ft_tiles,
                                             const float* __restrict__ KV, const int* __restrict__ nbr,
                                             const int* __restrict__ deg, int stride, int row, int lane,
@@ -79,7 +76,7 @@ __device__ __forceinline__ void edge_av_row(const float* __restrict__ Pw, const 
     const int jl = e0 + lane < n_e ? __ldg(nbr + ebase + e0 + lane) : 0;
     const int nt = min(32, n_e - e0);
     const float* fp = Ft + ((size_t)row * ft_tiles + (e0 >> 5)) * 8 + (lane >> 2);
-    const float f = Ft != nullptr ? (COHERENT ? __ldcg(fp) : __ldg(fp)) : 1.0f;
+    const float f = Ft != nullptr ? __ldg(fp) : 1.0f;
     for (int g = 0; g < nt; g += EB) {
       float4 v4[EB];
       float a[EB];
@@ -89,7 +86,7 @@ __device__ __forceinline__ void edge_av_row(const float* __restrict__ Pw, const 
         const int j = __shfl_sync(0xffffffffu, jl, eu);
         v4[u] = __ldg(reinterpret_cast<const float4*>(KV + (size_t)j * 256 + 128) + lane);
         const float* pp = Pw + (ebase + e0 + eu) * 8 + (lane >> 2);
-        a[u] = g + u < nt ? (COHERENT ? __ldcg(pp) : __ldg(pp)) * f : 0.f;
+        a[u] = g + u < nt ? __ldg(pp) * f : 0.f;
       }
 #pragma unroll
       for (int u = 0; u < EB; ++u) {

@@ -72,10 +72,7 @@ __device__ __forceinline__ void bulk_copy(uint32_t dst, const void* src, uint32_
 
 }  // namespace e4
 
-// NSTAGE z buffers per warp: 1 in the persistent kernel (12 warps x 18 KB fill the SM; other warps hide a warp's fetch),
-// 4 in the fused small-launch kernel (one or two warps per SM: nothing else hides the fetch, so up to four tiles -- a whole
-// agent row -- are in flight from the start of the row, behind the q.K' gathers)
-template <int ZD, int NSTAGE = 1>
+template <int ZD>
 struct Edge4Cfg {
   static constexpr int NSEG = ZD / 32;              // 32-float (128 B) column segments of a z row
   static constexpr int ZBYTES = NSEG * 4096;        // [NSEG][32 edges][128 B]
@@ -83,42 +80,31 @@ struct Edge4Cfg {
   static constexpr int PBYTES = 32 * H * 4;         // tile weights [32 edges][8 heads]
   static constexpr int MT_TILES = 24;               // running max per tile: stride <= 768
   static constexpr int MBYTES = MT_TILES * H * 4;
-  static constexpr int WARP_BYTES = NSTAGE * ZBYTES + QBYTES + PBYTES + MBYTES;
-  static constexpr size_t smem_bytes(int nw) { return 1024 + (size_t)nw * WARP_BYTES + (size_t)nw * NSTAGE * 8; }
+  static constexpr int WARP_BYTES = ZBYTES + QBYTES + PBYTES + MBYTES;
+  static constexpr size_t smem_bytes(int nw) { return 1024 + (size_t)nw * WARP_BYTES + (size_t)nw * 8; }
 };
 
-// FUSED (small launches, one row per warp, no row queue): the warp also computes its row's q.K' scores before the z pass
-// (edge_qk_row) and the V' aggregation after it (edge_av_row) -- one launch instead of three where launch latency, not
-// throughput, is the cost (a single 128-agent scene: 120 x 3 launches of ~15 us each per forward).  Same arithmetic.
-struct Edge4Fused {
-  const float* Qg;     // [n_dst][128] queries
-  const float* KV;     // [n_src][256] K'|V'
-  const int* nbr;      // neighbour lists
-  float* AggV;         // [n_dst][128]
-};
-
-template <int ZD, int NW, bool FUSED = false, int NSTAGE = (FUSED ? 4 : 1)>
+template <int ZD, int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
     attn_edge4_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmZ32,
-                      const float* __restrict__ Qhat, const float* Sk,
-                      const int* __restrict__ deg, int stride, int n_dst, float* __restrict__ Rbar, float* Pw,
-                      float* Ft, int ft_tiles, int* __restrict__ row_counter, Edge4Fused fz) {
-  using C = Edge4Cfg<ZD, NSTAGE>;
+                      const float* __restrict__ Qhat, const float* __restrict__ Sk,
+                      const int* __restrict__ deg, int stride, int n_dst, float* __restrict__ Rbar, float* __restrict__ Pw,
+                      float* __restrict__ Ft, int ft_tiles, int* __restrict__ row_counter) {
+  using C = Edge4Cfg<ZD>;
   constexpr int NSEG = C::NSEG;
-  constexpr int ZWARP = NSTAGE * C::ZBYTES;
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* gbase = smem_raw + ((1024u - (e4::smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzled boxes need 1 KB alignment
-  uint8_t* zb0 = gbase + warp * ZWARP;
-  float* qb = reinterpret_cast<float*>(gbase + NW * ZWARP + warp * C::QBYTES);
-  float* pb = reinterpret_cast<float*>(gbase + NW * (ZWARP + C::QBYTES) + warp * C::PBYTES);
-  float* mt = reinterpret_cast<float*>(gbase + NW * (ZWARP + C::QBYTES + C::PBYTES) + warp * C::MBYTES);
-  const uint32_t bar0 = e4::smem_u32(gbase + NW * C::WARP_BYTES + warp * NSTAGE * 8);   // one mbarrier per z buffer
-  const uint32_t zb0_s = e4::smem_u32(zb0), qb_s = e4::smem_u32(qb);
-  if (lane < NSTAGE) e4::mbar_init(bar0 + lane * 8, 1);
+  uint8_t* zb = gbase + warp * C::ZBYTES;
+  float* qb = reinterpret_cast<float*>(gbase + NW * C::ZBYTES + warp * C::QBYTES);
+  float* pb = reinterpret_cast<float*>(gbase + NW * (C::ZBYTES + C::QBYTES) + warp * C::PBYTES);
+  float* mt = reinterpret_cast<float*>(gbase + NW * (C::ZBYTES + C::QBYTES + C::PBYTES) + warp * C::MBYTES);
+  const uint32_t bar = e4::smem_u32(gbase + NW * C::WARP_BYTES + warp * 8);
+  const uint32_t zb_s = e4::smem_u32(zb), qb_s = e4::smem_u32(qb);
+  if (lane == 0) e4::mbar_init(bar, 1);
   __syncwarp();
 
-  uint32_t phase_bits = 0;   // bit b = parity of the next completion of buffer b's mbarrier
+  uint32_t phase = 0;
   const uint64_t z_policy = e4::policy_evict_first();
   // swizzled byte offsets inside a tile: zoff[j] = 16-byte chunk j of this lane's row (score pass, lane = edge);
   // coff[u] = this lane's feature column in edge u of a group of 8 (aggregation pass, lane = column)
@@ -132,20 +118,35 @@ __global__ void __launch_bounds__(NW * 32, 1)
   // only 2-5 rows of 1-16 tiles each, so a static split leaves a quarter of the warps idle at the tail
   int row = blockIdx.x * NW + warp;
   int row_next = 0;
-  for (; row < n_dst; row = FUSED ? n_dst : __shfl_sync(0xffffffffu, row_next, 0)) {
-    if (!FUSED && lane == 0) row_next = gridDim.x * NW + atomicAdd(row_counter, 1);   // consumed at the end of this row
+  for (; row < n_dst; row = __shfl_sync(0xffffffffu, row_next, 0)) {
+    if (lane == 0) row_next = gridDim.x * NW + atomicAdd(row_counter, 1);   // consumed at the end of this row
     const int n_e = min(__ldg(deg + row), stride);
     const size_t ebase = (size_t)row * stride;
     float* rb = Rbar + (size_t)row * H * ZD;
+    if (n_e <= 0) {   // no in-edges: the aggregate is zero (the gate / FFN update still runs on the row)
+#pragma unroll
+      for (int i = 0; i < H * NSEG; ++i) rb[i * 32 + lane] = 0.f;
+      continue;
+    }
     const int ntiles = (n_e + 31) >> 5;
-    // ---- fetch of tile t into buffer t % NSTAGE (+ the row's Qhat with its first tile), all on that buffer's mbarrier
-    // a full tile is NSEG boxes of [32 edges x 32 floats] (tmZ32); a partial one is fetched in 8-edge boxes so that at
-    // most 7 rows beyond the list are read.  Callers make sure every lane is done with the buffer (__syncwarp).
-    auto fetch_tile = [&](int t) {
+    float m[H], lsum[H];           // running max (warp uniform), this lane's share of the running sum
+    float2 r01[NSEG], r23[NSEG], r45[NSEG], r67[NSEG];   // Rbar[h][seg*32 + lane] as head pairs
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      m[h] = -INFINITY;
+      lsum[h] = 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < NSEG; ++c) r01[c] = r23[c] = r45[c] = r67[c] = make_float2(0.f, 0.f);
+
+    for (int t = 0; t < ntiles; ++t) {
       const int t0 = t << 5, nt = min(32, n_e - t0);
+      // ---- fetch: z boxes of this tile (+ the row's Qhat with its first tile), all on one mbarrier phase
+      // a full tile is NSEG boxes of [32 edges x 32 floats] (tmZ32); a partial one is fetched in 8-edge boxes so that at
+      // most 7 rows beyond the list are read
       const bool full_tile = nt == 32;
       const int nbox = full_tile ? NSEG : ((nt + 7) >> 3) * NSEG;
-      const uint32_t bar = bar0 + (t % NSTAGE) * 8, zb_s = zb0_s + (t % NSTAGE) * C::ZBYTES;
+      __syncwarp();                                   // every lane is done with the previous tile's buffers
       if (lane == 0) e4::mbar_expect_tx(bar, (full_tile ? NSEG * 4096 : nbox * 1024) + (t == 0 ? C::QBYTES : 0));
       __syncwarp();
       if (lane < nbox) {
@@ -160,36 +161,6 @@ __global__ void __launch_bounds__(NW * 32, 1)
         e4::fence_proxy_async();
         e4::bulk_copy(qb_s, Qhat + (size_t)row * H * D, C::QBYTES, bar);
       }
-    };
-    __syncwarp();                                     // every lane is done with the previous row's buffers
-#pragma unroll
-    for (int t = 0; t < NSTAGE; ++t)
-      if (t < ntiles) fetch_tile(t);
-    if (FUSED) {
-      edge_qk_row<GATHER_EB_FUSED>(fz.Qg, fz.KV, fz.nbr, deg, stride, row, lane, const_cast<float*>(Sk));
-      __threadfence_block();      // the scores are read back below by other lanes of this warp
-      __syncwarp();
-    }
-    if (n_e <= 0) {   // no in-edges: the aggregate is zero (the gate / FFN update still runs on the row)
-#pragma unroll
-      for (int i = 0; i < H * NSEG; ++i) rb[i * 32 + lane] = 0.f;
-      if (FUSED) edge_av_row<true, GATHER_EB_FUSED>(Pw, Ft, ft_tiles, fz.KV, fz.nbr, deg, stride, row, lane, fz.AggV);
-      continue;
-    }
-    float m[H], lsum[H];           // running max (warp uniform), this lane's share of the running sum
-    float2 r01[NSEG], r23[NSEG], r45[NSEG], r67[NSEG];   // Rbar[h][seg*32 + lane] as head pairs
-#pragma unroll
-    for (int h = 0; h < H; ++h) {
-      m[h] = -INFINITY;
-      lsum[h] = 0.f;
-    }
-#pragma unroll
-    for (int c = 0; c < NSEG; ++c) r01[c] = r23[c] = r45[c] = r67[c] = make_float2(0.f, 0.f);
-
-    for (int t = 0; t < ntiles; ++t) {
-      const int t0 = t << 5, nt = min(32, n_e - t0);
-      const int stage = NSTAGE == 1 ? 0 : t % NSTAGE;
-      const uint8_t* zb = zb0 + stage * C::ZBYTES;
       // ---- the q.K' part of the scores (edge_qk_kernel), lane = edge: its latency hides behind the tile's
       const bool valid = lane < nt;
       float2 acc[H];
@@ -197,16 +168,16 @@ __global__ void __launch_bounds__(NW * 32, 1)
         float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
         if (valid) {
           const float4* sp = reinterpret_cast<const float4*>(Sk + (ebase + t0 + lane) * 8);
-          s0 = FUSED ? __ldcg(sp) : __ldg(sp);
-          s1 = FUSED ? __ldcg(sp + 1) : __ldg(sp + 1);
+          s0 = __ldg(sp);
+          s1 = __ldg(sp + 1);
         }
         acc[0] = make_float2(s0.x, 0.f); acc[1] = make_float2(s0.y, 0.f);
         acc[2] = make_float2(s0.z, 0.f); acc[3] = make_float2(s0.w, 0.f);
         acc[4] = make_float2(s1.x, 0.f); acc[5] = make_float2(s1.y, 0.f);
         acc[6] = make_float2(s1.z, 0.f); acc[7] = make_float2(s1.w, 0.f);
       }
-      e4::mbar_wait(bar0 + stage * 8, (phase_bits >> stage) & 1u);
-      phase_bits ^= 1u << stage;
+      e4::mbar_wait(bar, phase);
+      phase ^= 1;
       if (ZD == 96 && t == 0) {   // features 96..127 of the embedding duplicate 64..95: fold Qhat once per row
 #pragma unroll
         for (int h = 0; h < H; ++h) qb[h * D + 64 + lane] += qb[h * D + 96 + lane];
@@ -289,10 +260,6 @@ __global__ void __launch_bounds__(NW * 32, 1)
         default: PROSIM_AGG_GROUP(0)
       }
 #undef PROSIM_AGG_GROUP
-      if (t + NSTAGE < ntiles) {
-        __syncwarp();                                 // every lane is done with this tile's buffer
-        fetch_tile(t + NSTAGE);
-      }
     }
 
     // ---- row epilogue: 1 / (sum + 1e-16), Rbar, and the per-tile factors exp(m_tile - m_final) / (sum + 1e-16)
@@ -320,11 +287,6 @@ __global__ void __launch_bounds__(NW * 32, 1)
       const float ih = pb[lane & 7];
       float* ft = Ft + (size_t)row * ft_tiles * H;
       for (int i = lane; i < ntiles * H; i += 32) ft[i] = expf(mt[i] - mh) * ih;
-    }
-    if (FUSED) {
-      __threadfence_block();      // Pw / Ft of this row were written by other lanes of this warp
-      __syncwarp();
-      edge_av_row<true, GATHER_EB_FUSED>(Pw, Ft, ft_tiles, fz.KV, fz.nbr, deg, stride, row, lane, fz.AggV);
     }
   }
 }
