@@ -142,12 +142,48 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
   const bool pre_only = W == nullptr;
   constexpr int VR_HALF_BYTES = (ZD / 2) * D * 4;      // the fp32 Wvr' block [ZD][128] travels as two ring stages
 
+  if (tid == 0 && blockIdx.x == 0 && has_next) tcp::g_tcp_dbg[30] = clock64();
   if (warp == 0) tc::tmem_alloc(&sm.tmem_base, 512);
-  if (tid == 32) {
+  const int n_chunks = has_next ? 58 : 42;
+  const int chunk0 = pre_only ? 42 : 0;             // ring positions count from the first chunk of the launch
+  // weight chunk i of the launch's script -> ring stage (i - chunk0) % NST (producer thread only)
+  auto issue_chunk = [&](int i) {
+    const float* src;
+    uint32_t bytes;
+    if (i < 2) {
+      src = W + (ZD == 96 ? aw::WVRG96T : aw::WVRGT) + i * (VR_HALF_BYTES / 4);   // fp32 [ZD][128]: the FFMA agg
+      bytes = VR_HALF_BYTES;
+    } else if (i < 10) {
+      src = W + aw::TC_GA + (i - 2) * 8192;      // Wga (4), Wo (4): contiguous
+      bytes = 32768;
+    } else if (i < 42) {
+      src = W + aw::TC_FF2 + (i - 10) * 8192;    // up_0, up_1, down_0, up_2, down_1, up_3, down_2, down_3 (4 k-chunks each)
+      bytes = 32768;
+    } else if (i < 46) {
+      src = Wn + aw::TC_Q + (i - 42) * 8192;     // next layer's Wq first (q feeds the Qhat GEMMs) ...
+      bytes = 32768;
+    } else if (i < 54) {
+      src = Wn + aw::TC_S + (i - 46) * 8192;     // ... then Ws, Wgx (contiguous)
+      bytes = 32768;
+    } else {
+      src = Wn + aw::TC_KRG + (i - 54) * 8192;   // Wkr' of two heads per stage
+      bytes = 32768;
+    }
+    const int k = i - chunk0, s = k % NST;
+    if (k >= NST) tcp::mbar_wait(&sm.empty[s], ((k / NST) - 1) & 1);
+    const uint32_t fb = e4::smem_u32(&sm.full[s]);
+    e4::mbar_expect_tx(fb, bytes);
+    e4::bulk_copy(e4::smem_u32(sm.ring[s]), src, bytes, fb);
+  };
+  if (tid == EPI_THREADS) {   // the producer thread arms its own ring and starts the first NST copies under the rest of the set-up
     for (int i = 0; i < NST; ++i) {
       e4::mbar_init(e4::smem_u32(&sm.full[i]), 1);
       e4::mbar_init(e4::smem_u32(&sm.empty[i]), 1);
     }
+    e4::fence_proxy_async();
+    for (int i = chunk0; i < chunk0 + NST; ++i) issue_chunk(i);
+  }
+  if (tid == 32) {
     e4::mbar_init(e4::smem_u32(&sm.opnd_ready), EPI_WARPS);
     e4::mbar_init(e4::smem_u32(&sm.h_ready), EPI_WARPS);
     e4::mbar_init(e4::smem_u32(&sm.sgx_read), EPI_WARPS);
@@ -174,40 +210,11 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = sm.tmem_base;
-  const int n_chunks = has_next ? 58 : 42;
-  const int chunk0 = pre_only ? 42 : 0;             // ring positions count from the first chunk of the launch
 
   if (warp == 8) {
     // ================================================================== weight producer
     if (lane == 0) {
-      for (int i = chunk0; i < n_chunks; ++i) {
-        const float* src;
-        uint32_t bytes;
-        if (i < 2) {
-          src = W + (ZD == 96 ? aw::WVRG96T : aw::WVRGT) + i * (VR_HALF_BYTES / 4);   // fp32 [ZD][128]: the FFMA agg
-          bytes = VR_HALF_BYTES;
-        } else if (i < 10) {
-          src = W + aw::TC_GA + (i - 2) * 8192;      // Wga (4), Wo (4): contiguous
-          bytes = 32768;
-        } else if (i < 42) {
-          src = W + aw::TC_FF2 + (i - 10) * 8192;    // up_0, up_1, down_0, up_2, down_1, up_3, down_2, down_3 (4 k-chunks each)
-          bytes = 32768;
-        } else if (i < 46) {
-          src = Wn + aw::TC_Q + (i - 42) * 8192;     // next layer's Wq first (q feeds the Qhat GEMMs) ...
-          bytes = 32768;
-        } else if (i < 54) {
-          src = Wn + aw::TC_S + (i - 46) * 8192;     // ... then Ws, Wgx (contiguous)
-          bytes = 32768;
-        } else {
-          src = Wn + aw::TC_KRG + (i - 54) * 8192;   // Wkr' of two heads per stage
-          bytes = 32768;
-        }
-        const int k = i - chunk0, s = k % NST;
-        if (k >= NST) tcp::mbar_wait(&sm.empty[s], ((k / NST) - 1) & 1);
-        const uint32_t fb = e4::smem_u32(&sm.full[s]);
-        e4::mbar_expect_tx(fb, bytes);
-        e4::bulk_copy(e4::smem_u32(sm.ring[s]), src, bytes, fb);
-      }
+      for (int i = chunk0 + NST; i < n_chunks; ++i) issue_chunk(i);
     }
     __syncwarp();
   } else if (warp == 9) {
@@ -456,12 +463,27 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
     //         fp32 FFMA, the row's Rbar_h in registers, the weights read as warp-wide broadcasts from the ring (two
     //         stages hold the fp32 [ZD][128] block); ascending d like the FFMA node kernels
     {
+      // The row's Rbar_h (ZD floats) reaches its thread in passes of PW floats through a warp-private staging tile: the
+      // 32 rows x PW floats of a pass are read from global memory as whole 128-byte lines and re-read row-wise from shared
+      // memory.  (Reading them straight into the owning thread -- 16 bytes per lane at a 3 KB stride -- cost ~7 k cycles of
+      // LSU address divergence per CTA: 28 instructions x 8 warps x 32 distinct lines.)  The tile lives in the activation
+      // operands, which nobody touches before the agg result is written.
+      constexpr int PW = ZD == 96 ? 48 : 32, NPASS = ZD / PW, P4 = PW / 4, PITCH = PW + 4;
+      static_assert(8 * 32 * PITCH * 4 <= 2 * OPND_BYTES, "staging tiles must fit in actA + actH");
       const bool ok = row0 + lane < a.n;
-      float4 rb[ZD / 4];
+      float* stg = reinterpret_cast<float*>(sm.actA) + warp * (32 * PITCH);
+      float4 g[P4], rb[P4];
       float2 av[8];
-      const float4* rp = reinterpret_cast<const float4*>(a.rbar + (size_t)(row0 + lane) * (H * ZD) + warp * ZD);
+      auto load_pass = [&](int pass) {
 #pragma unroll
-      for (int i = 0; i < ZD / 4; ++i) rb[i] = ok ? __ldg(rp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int it = 0; it < P4; ++it) {
+          const int idx = it * 32 + lane, r = idx / P4, c4 = idx % P4;
+          g[it] = row0 + r < a.n
+                      ? __ldg(reinterpret_cast<const float4*>(a.rbar + (size_t)(row0 + r) * (H * ZD) + warp * ZD + pass * PW) + c4)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      load_pass(0);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -470,12 +492,27 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
         av[2 * i + 1] = make_float2(t4.z, t4.w);
       }
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        tcp::mbar_wait(&sm.full[half], 0);
-        const float* wv = reinterpret_cast<const float*>(sm.ring[half]) + 16 * warp;
+      for (int pass = 0; pass < NPASS; ++pass) {
 #pragma unroll
-        for (int dq = 0; dq < ZD / 8; ++dq) {
-          const float4 r4 = rb[half * (ZD / 8) + dq];
+        for (int it = 0; it < P4; ++it) {
+          const int idx = it * 32 + lane, r = idx / P4, c4 = idx % P4;
+          *reinterpret_cast<float4*>(stg + r * PITCH + 4 * c4) = g[it];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < P4; ++i) rb[i] = *reinterpret_cast<const float4*>(stg + lane * PITCH + 4 * i);
+        __syncwarp();
+        if (pass + 1 < NPASS) load_pass(pass + 1);          // in flight under this pass's FMAs
+        constexpr int PPH = NPASS / 2;                      // passes per weight half (= ring stage)
+        const int half = pass / PPH;
+        if (pass % PPH == 0) {
+          tcp::mbar_wait(&sm.full[half], 0);
+          if (half == 0) PSW_EMARK(2); else PSW_EMARK(15);
+        }
+        const float* wv = reinterpret_cast<const float*>(sm.ring[half]) + (pass % PPH) * PW * D + 16 * warp;
+#pragma unroll
+        for (int dq = 0; dq < P4; ++dq) {
+          const float4 r4 = rb[dq];
           const float rv[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -490,6 +527,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
           }
         }
       }
+      PSW_EMARK(14);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         *reinterpret_cast<float4*>(scr + lane * SCR_LD + 16 * warp + 4 * i) = make_float4(av[2 * i].x, av[2 * i].y, av[2 * i + 1].x, av[2 * i + 1].y);

@@ -38,4 +38,5 @@ print('epilogue:', ' | '.join(f'{n} {t[i] - t0}' for i, n in enumerate(ne)))
 nm = ['start', 'agg issued', 'a(agg)', 'gate issued', 'a(u)', 'out issued', 'a(xn)', 'ffn issued', 'a(xd)', 'sgq issued', 'a(q)',
       'qhat issued']
 print('mma     :', ' | '.join(f'{n} {t[16 + i] - t0}' for i, n in enumerate(nm)))
+print('agg detail: kernel entry', t[30] - t0, '| weights half 0 landed', t[2] - t0, '| half 1 waited', t[15] - t0, '| ffma done', t[14] - t0)
 print('mma thread waited (cycles): weights', t[28], 'epilogue', t[29], 'timeout id', t[31])
