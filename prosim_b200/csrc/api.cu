@@ -30,6 +30,8 @@ bool g_use_tc = true;   // node-side GEMMs on tcgen05 (tc_post.cuh); prosim_set_
 int g_tc_mask = 31;     // bit 0: node kernels, bit 1: K'|V', bit 2: PointNet, bit 3: the 32-row "swapped" node kernel (post_sw.cuh),
                         // bit 4: the fused small-launch edge kernel (prosim_set_tensor_core(mask), A/B and fault isolation)
 constexpr int SW_MAX_ROWS = 148 * 32 * 2;   // above two waves of 32-row CTAs the 128-row kernel streams 4x less weight per row
+// 16 rows per CTA while that still fits one wave: twice the CTAs, half the per-CTA epilogue work (bit-identical to 32 rows)
+inline bool sw_rows16(int n) { return (n + 15) / 16 <= 148; }
 constexpr int FUSED_EDGE_MAX_ROWS = 592;    // small launches: one fused edge launch instead of three (see launch_edge)
 constexpr int ERR_ARG = -1;
 constexpr int ERR_WORKSPACE = -2;
@@ -126,8 +128,10 @@ int setup_attributes() {
   acc(allow_smem(attn_dstpre2_kernel<8, 8>, Pre2Smem<8, 8>::bytes));
   acc(allow_smem(attn_post2_kernel<4, 8>, Post2Smem<4, 8>::bytes));
   acc(allow_smem(tcp::attn_post_tc_kernel, tcp::SMEM_BYTES));
-  acc(allow_smem(psw::attn_post_sw_kernel<96>, psw::SMEM_BYTES));
-  acc(allow_smem(psw::attn_post_sw_kernel<128>, psw::SMEM_BYTES));
+  acc(allow_smem(psw::attn_post_sw_kernel<96, 32>, psw::SMEM_BYTES));
+  acc(allow_smem(psw::attn_post_sw_kernel<128, 32>, psw::SMEM_BYTES));
+  acc(allow_smem(psw::attn_post_sw_kernel<96, 16>, psw::SMEM_BYTES));
+  acc(allow_smem(psw::attn_post_sw_kernel<128, 16>, psw::SMEM_BYTES));
   state = e == cudaSuccess ? 1 : (int)e + 1000;
   return e == cudaSuccess ? 0 : (int)e;
 }
@@ -203,7 +207,8 @@ int launch_dstpre(const float* x, int n, const float* w, const DstScratch& d, cu
     psw::Args a{};
     a.x = x; a.q_n = d.q; a.qhat_n = d.qhat; a.s_n = d.s; a.gx_n = d.gx;
     a.W = nullptr; a.Wn = w; a.n = n;
-    psw::attn_post_sw_kernel<96><<<(n + psw::NR - 1) / psw::NR, psw::THREADS, psw::SMEM_BYTES, st>>>(a);
+    if (sw_rows16(n)) psw::attn_post_sw_kernel<96, 16><<<(n + 15) / 16, psw::THREADS, psw::SMEM_BYTES, st>>>(a);
+    else psw::attn_post_sw_kernel<96, 32><<<(n + 31) / 32, psw::THREADS, psw::SMEM_BYTES, st>>>(a);
     PROSIM_CHECK_LAUNCH();
     return 0;
   }
@@ -358,9 +363,15 @@ int launch_post(const float* x, int n, int zd, const float* rbar, const float* a
     a.x = x; a.rbar = rbar; a.aggv = aggv; a.s = cur.s; a.gx = cur.gx; a.out = out;
     a.q_n = nxt.q; a.qhat_n = nxt.qhat; a.s_n = nxt.s; a.gx_n = nxt.gx;
     a.W = w; a.Wn = w_next; a.n = n;
-    const int grid = (n + psw::NR - 1) / psw::NR;
-    if (zd == 96) psw::attn_post_sw_kernel<96><<<grid, psw::THREADS, psw::SMEM_BYTES, st>>>(a);
-    else psw::attn_post_sw_kernel<128><<<grid, psw::THREADS, psw::SMEM_BYTES, st>>>(a);
+    if (sw_rows16(n)) {
+      const int grid = (n + 15) / 16;
+      if (zd == 96) psw::attn_post_sw_kernel<96, 16><<<grid, psw::THREADS, psw::SMEM_BYTES, st>>>(a);
+      else psw::attn_post_sw_kernel<128, 16><<<grid, psw::THREADS, psw::SMEM_BYTES, st>>>(a);
+    } else {
+      const int grid = (n + 31) / 32;
+      if (zd == 96) psw::attn_post_sw_kernel<96, 32><<<grid, psw::THREADS, psw::SMEM_BYTES, st>>>(a);
+      else psw::attn_post_sw_kernel<128, 32><<<grid, psw::THREADS, psw::SMEM_BYTES, st>>>(a);
+    }
     PROSIM_CHECK_LAUNCH();
     return 0;
   }

@@ -54,12 +54,10 @@
 namespace prosim {
 namespace psw {
 
-constexpr int NR = 32;                     // destination rows per CTA
+constexpr int NR_MAX = 32;                 // destination rows per CTA: 32, or 16 for launches that would leave SMs idle
 constexpr int NST = 4;                     // weight ring stages
 constexpr int STAGE_BYTES = 32768;
-constexpr int SLAB_BYTES = 8192;           // one 32-wide k block of an activation operand: 64 rows (32 hi + 32 lo) x 128 B
-constexpr int LO_OFF = 4096;               // lo rows follow the hi rows inside a slab
-constexpr int OPND_BYTES = 4 * SLAB_BYTES;
+constexpr int OPND_BYTES = 4 * 2 * NR_MAX * 128;   // four 32-wide k slabs of [NR hi rows | NR lo rows] x 128 B
 constexpr int SCR_LD = 132;                // scratch row pitch (floats)
 constexpr int EPI_THREADS = 256, EPI_WARPS = 8;
 constexpr int THREADS = EPI_THREADS + 64;
@@ -71,7 +69,7 @@ struct Smem {
   uint8_t actA[OPND_BYTES];                // activation operand: agg / u / LN(x1) / LN_dst(out)
   uint8_t actH[OPND_BYTES];                // FFN hidden operand, q operand
   uint8_t ring[NST][STAGE_BYTES];
-  float scratch[NR * SCR_LD];
+  float scratch[NR_MAX * SCR_LD];
   float vec[tcp::V_SIZE];
   uint64_t full[NST], empty[NST];
   uint64_t opnd_ready, sgx_read, h_ready, h_free, acc_done[NACC];
@@ -99,26 +97,39 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
   return d;
 }
-// 16 accumulator values = hi.hi half (columns taddr ..) + cross-term half (columns taddr + 32 ..), one wait for both loads
-__device__ __forceinline__ void tmem_ld16_pair(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16], q[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-      : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
-        "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
-      : "r"(taddr + 32)
-      : "memory");
+// VPT accumulator values = hi.hi half (columns taddr ..) + cross-term half (columns taddr + NR ..), one wait for both loads
+template <int VPT, int NR>
+__device__ __forceinline__ void tmem_ld_pair(uint32_t taddr, float (&v)[VPT]) {
+  uint32_t r[VPT], q[VPT];
+  if constexpr (VPT == 16) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]),
+          "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+        : "r"(taddr + NR)
+        : "memory");
+  } else {
+    static_assert(VPT == 8, "8 or 16 rows per thread");
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7])
+                 : "r"(taddr + NR)
+                 : "memory");
+  }
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(q[i]);
+  for (int i = 0; i < VPT; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(q[i]);
 }
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) { tcp::mbar_arrive(e4::smem_u32(bar)); }
@@ -130,8 +141,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) { tcp::mbar_arrive(e4
     if (blockIdx.x == 0 && has_next) tcp::g_tcp_dbg[slot] = clock64(); \
   } while (0)
 
-template <int ZD>
+template <int ZD, int NR>
 __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_constant__ Args a) {
+  static_assert(NR == 32 || NR == 16, "rows per CTA");
+  constexpr int SLAB_BYTES = 2 * NR * 128;   // one 32-wide k block of an activation operand: NR hi rows then NR lo rows, 128 B each
+  constexpr int LO_OFF = NR * 128;
+  constexpr int VPT = NR / 2;                // values per epilogue thread in every index map
+  constexpr int LPR = EPI_THREADS / NR;      // R-map: lanes per row (8 / 16)
+  constexpr int GPT = VPT / 4;               // R-map: 4-float feature groups per thread, group sg + LPR i
   extern __shared__ uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (e4::smem_u32(smem_raw) & 1023u)) & 1023u));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -251,7 +268,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
         for (int ks = 0; ks < KC_ / 8; ++ks) {
           const uint64_t wh = wh0 + (uint64_t)(ks * 16), wl = wl0 + (uint64_t)(ks * 16);
           const uint64_t xd = x0 + (uint64_t)(ks * 2);                          // + 32 bytes inside the swizzled row
-          tc::mma_tf32(tmem + d_col, wh, xd, idesc64, accumulate || ks > 0);    // [hi.hi | hi.lo]: rows 0..31 hi, 32..63 lo
+          tc::mma_tf32(tmem + d_col, wh, xd, idesc64, accumulate || ks > 0);    // [hi.hi | hi.lo]: rows 0..NR-1 hi, NR..2NR-1 lo
           tc::mma_tf32(tmem + d_col + NR, wl, xd, idesc32, true);               // + lo.hi onto the cross-term half
         }
         if (part == parts - 1) {
@@ -331,9 +348,9 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
   } else {
     // ================================================================== epilogue warps
     const int q4 = warp & 3, ch = warp >> 2;
-    const int f = q4 * 32 + lane;                          // T-map: feature, rows 16 ch .. 16 ch + 15
+    const int f = q4 * 32 + lane;                          // T-map: feature, rows VPT ch .. VPT ch + VPT - 1
     const uint32_t lb = tmem + ((uint32_t)(q4 * 32) << 16);
-    const int rr = 4 * warp + (lane >> 3), sg = lane & 7;  // R-map: row, feature groups sg + 8 i
+    const int rr = (NR / 8) * warp + lane / LPR, sg = lane % LPR;   // R-map: row, feature groups sg + LPR i
     const bool rr_ok = row0 + rr < a.n;
     const float* vec = sm.vec;
     float* scr = sm.scratch;
@@ -349,12 +366,12 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(bar);
     };
-    // T-map: 16 rows of this thread's feature -> hi / lo rows of the swizzled activation operand at `opnd`
-    auto t_store_opnd = [&](uint8_t* opnd, const float (&v)[16]) {
-      uint8_t* p = opnd + q4 * SLAB_BYTES + (2 * ch) * 1024 + (lane & 3) * 4;
+    // T-map: VPT rows of this thread's feature -> hi / lo rows of the swizzled activation operand at `opnd`
+    auto t_store_opnd = [&](uint8_t* opnd, const float (&v)[VPT]) {
+      uint8_t* p = opnd + q4 * SLAB_BYTES + ((VPT / 8) * ch) * 1024 + (lane & 3) * 4;
       const int c = lane >> 2;                             // 16-byte chunk of the row before the swizzle
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < VPT; ++i) {
         const float hi = tcp::tf32_rna_finite(v[i]);
         const float lo = tcp::tf32_rna_finite(v[i] - hi);
         uint8_t* pe = p + (i >> 3) * 1024 + (i & 7) * 128 + ((c ^ (i & 7)) << 4);
@@ -362,124 +379,141 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
         *reinterpret_cast<float*>(pe + LO_OFF) = lo;
       }
     };
-    // R-map: this thread's 4 groups of 4 features of row rr (group sg + 8 i = chunk sg of slab i)
-    auto r_store_opnd = [&](uint8_t* opnd, const float (&v)[16]) {
-      uint8_t* p = opnd + (rr >> 3) * 1024 + (rr & 7) * 128 + ((sg ^ (rr & 7)) << 4);
+    // R-map: this thread's GPT groups of 4 features of row rr (group g = sg + LPR i = chunk g % 8 of slab g / 8)
+    auto r_store_opnd = [&](uint8_t* opnd, const float (&v)[VPT]) {
+      uint8_t* p = opnd + (rr >> 3) * 1024 + (rr & 7) * 128;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < GPT; ++i) {
+        const int g = sg + LPR * i;
+        uint8_t* pe = p + (g >> 3) * SLAB_BYTES + (((g & 7) ^ (rr & 7)) << 4);
         float4 hi, lo;
         hi.x = tcp::tf32_rna_finite(v[4 * i]);     lo.x = tcp::tf32_rna_finite(v[4 * i] - hi.x);
         hi.y = tcp::tf32_rna_finite(v[4 * i + 1]); lo.y = tcp::tf32_rna_finite(v[4 * i + 1] - hi.y);
         hi.z = tcp::tf32_rna_finite(v[4 * i + 2]); lo.z = tcp::tf32_rna_finite(v[4 * i + 2] - hi.z);
         hi.w = tcp::tf32_rna_finite(v[4 * i + 3]); lo.w = tcp::tf32_rna_finite(v[4 * i + 3] - hi.w);
-        *reinterpret_cast<float4*>(p + i * SLAB_BYTES) = hi;
-        *reinterpret_cast<float4*>(p + i * SLAB_BYTES + LO_OFF) = lo;
+        *reinterpret_cast<float4*>(pe) = hi;
+        *reinterpret_cast<float4*>(pe + LO_OFF) = lo;
       }
     };
-    auto r_load_scr = [&](float (&v)[16]) {
+    auto r_load_scr = [&](float (&v)[VPT]) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 t = *reinterpret_cast<const float4*>(scr + rr * SCR_LD + 4 * (sg + 8 * i));
+      for (int i = 0; i < GPT; ++i) {
+        const float4 t = *reinterpret_cast<const float4*>(scr + rr * SCR_LD + 4 * (sg + LPR * i));
         v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
       }
     };
-    auto r_load_vec = [&](const float* p, float (&v)[16]) {
+    auto r_load_vec = [&](const float* p, float (&v)[VPT]) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 t = *reinterpret_cast<const float4*>(p + 4 * (sg + 8 * i));
+      for (int i = 0; i < GPT; ++i) {
+        const float4 t = *reinterpret_cast<const float4*>(p + 4 * (sg + LPR * i));
         v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
       }
     };
-    auto r_load_glb = [&](const float* base, float (&v)[16]) {   // row rr of a [n][128] global matrix
+    auto r_load_glb = [&](const float* base, float (&v)[VPT]) {   // row rr of a [n][128] global matrix
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < GPT; ++i) {
         float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rr_ok) t = __ldg(reinterpret_cast<const float4*>(base + (size_t)(row0 + rr) * D) + sg + 8 * i);
+        if (rr_ok) t = __ldg(reinterpret_cast<const float4*>(base + (size_t)(row0 + rr) * D) + sg + LPR * i);
         v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
       }
     };
-    auto r_store_glb = [&](float* base, const float (&v)[16]) {
+    auto r_store_glb = [&](float* base, const float (&v)[VPT]) {
       if (rr_ok) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          *(reinterpret_cast<float4*>(base + (size_t)(row0 + rr) * D) + sg + 8 * i) =
+        for (int i = 0; i < GPT; ++i)
+          *(reinterpret_cast<float4*>(base + (size_t)(row0 + rr) * D) + sg + LPR * i) =
               make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
       }
     };
-    auto row_sum8 = [&](float p) -> float {                      // over the 8 lanes that share a row
+    // Sum over the 128 features of a row from per-group partials t[i] (group sg + LPR i), as ONE fixed tree for both row
+    // counts: level 1 pairs groups g and g + 16, level 2 pairs g and g + 8 (g < 8), then xor-shuffles 1, 2, 4 -- in registers
+    // where a thread holds both partners, by shuffle where it does not.  A row's statistics therefore do not depend on NR.
+    auto row_tree = [&](const float (&t)[GPT]) -> float {
+      float p;
+      if constexpr (NR == 32) {
+        p = (t[0] + t[2]) + (t[1] + t[3]);
+      } else {
+        p = t[0] + t[1];
+        p += __shfl_xor_sync(0xffffffffu, p, 8);
+      }
       p += __shfl_xor_sync(0xffffffffu, p, 1);
       p += __shfl_xor_sync(0xffffffffu, p, 2);
       p += __shfl_xor_sync(0xffffffffu, p, 4);
       return p;
     };
     // two-pass LayerNorm of the row (R-map), affine from vec + g_off / b_off
-    auto r_layernorm = [&](float (&v)[16], int g_off, int b_off) {
-      float s = 0.f;
+    auto r_layernorm = [&](float (&v)[VPT], int g_off, int b_off) {
+      float t[GPT];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) s += v[i];
-      const float mean = row_sum8(s) * (1.0f / 128.0f);
-      float qv = 0.f;
+      for (int i = 0; i < GPT; ++i) t[i] = ((v[4 * i] + v[4 * i + 1]) + v[4 * i + 2]) + v[4 * i + 3];
+      const float mean = row_tree(t) * (1.0f / 128.0f);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float d = v[i] - mean;
-        qv = fmaf(d, d, qv);
+      for (int i = 0; i < GPT; ++i) {
+        const float d0 = v[4 * i] - mean, d1 = v[4 * i + 1] - mean, d2 = v[4 * i + 2] - mean, d3 = v[4 * i + 3] - mean;
+        t[i] = fmaf(d3, d3, fmaf(d2, d2, fmaf(d1, d1, d0 * d0)));
       }
-      const float rstd = 1.0f / sqrtf(row_sum8(qv) * (1.0f / 128.0f) + LN_EPS);
-      float g[16], b[16];
+      const float rstd = 1.0f / sqrtf(row_tree(t) * (1.0f / 128.0f) + LN_EPS);
+      float g[VPT], b[VPT];
       r_load_vec(vec + g_off, g);
       r_load_vec(vec + b_off, b);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = (v[i] - mean) * rstd * g[i] + b[i];
+      for (int i = 0; i < VPT; ++i) v[i] = (v[i] - mean) * rstd * g[i] + b[i];
     };
-    // T-map global access: element [row0 + 16 ch + i][f]
-    auto t_load_glb = [&](const float* base, float (&v)[16]) {
+    // T-map global access: element [row0 + VPT ch + i][f]
+    auto t_load_glb = [&](const float* base, float (&v)[VPT]) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int r = row0 + 16 * ch + i;
+      for (int i = 0; i < VPT; ++i) {
+        const int r = row0 + VPT * ch + i;
         v[i] = r < a.n ? __ldg(base + (size_t)r * D + f) : 0.f;
       }
     };
-    auto t_store_glb = [&](float* base, size_t ld, int col, const float (&v)[16]) {
+    auto t_store_glb = [&](float* base, size_t ld, int col, const float (&v)[VPT]) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int r = row0 + 16 * ch + i;
+      for (int i = 0; i < VPT; ++i) {
+        const int r = row0 + VPT * ch + i;
         if (r < a.n) base[(size_t)r * ld + col + f] = v[i];
       }
     };
-    auto t_store_scr = [&](const float (&v)[16]) {
+    auto t_store_scr = [&](const float (&v)[VPT]) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) scr[(16 * ch + i) * SCR_LD + f] = v[i];
+      for (int i = 0; i < VPT; ++i) scr[(VPT * ch + i) * SCR_LD + f] = v[i];
     };
 #define PSW_EMARK(slot) do { if (tid == 0) PSW_MARK(slot); } while (0)
     PSW_EMARK(0);
-    float v[16];
+    float v[VPT];
     if (pre_only) {            // LN_dst'(x) -> operand A, then straight to the projections
       r_load_glb(a.x, v);
       r_layernorm(v, tcp::V_LNDST_G, tcp::V_LNDST_B);
       r_store_opnd(sm.actA, v);
       publish(&sm.opnd_ready);
     } else {
-    // ---- 0. agg[row][16 h ..] = AggV + sum_d Rbar[row][h][d] Wvr'[d][16 h ..]   (H-map: row = lane, head = warp)
-    //         fp32 FFMA, the row's Rbar_h in registers, the weights read as warp-wide broadcasts from the ring (two
-    //         stages hold the fp32 [ZD][128] block); ascending d like the FFMA node kernels
+    // ---- 0. agg[row][16 h ..] = (AggV + sum_{d < ZD/2} Rbar[row][h][d] Wvr'[d][16 h ..]) + sum_{d >= ZD/2} ...     (H-map)
+    //         fp32 FFMA: thread = (row, head = warp), for NR = 16 also (half of d) = lane / 16; Rbar_h in registers, the
+    //         weights as broadcasts from the ring (two stages hold the fp32 [ZD][128] block).  Two ascending-d chains, one per
+    //         weight half, added at the end: the same arithmetic whether one thread runs both (NR = 32) or two lanes one each.
     {
-      // The row's Rbar_h (ZD floats) reaches its thread in passes of PW floats through a warp-private staging tile: the
-      // 32 rows x PW floats of a pass are read from global memory as whole 128-byte lines and re-read row-wise from shared
-      // memory.  (Reading them straight into the owning thread -- 16 bytes per lane at a 3 KB stride -- cost ~7 k cycles of
-      // LSU address divergence per CTA: 28 instructions x 8 warps x 32 distinct lines.)  The tile lives in the activation
-      // operands, which nobody touches before the agg result is written.
+      // Rbar reaches its thread in passes of PW floats through a warp-private staging tile of 32 "slots" (NR = 32: slot =
+      // row; NR = 16: slot = 16 half + row): a pass is read from global memory as whole 128-byte lines and re-read slot-wise
+      // from shared memory.  (Reading it straight into the owning thread -- 16 bytes per lane at a 3 KB stride -- cost ~7 k
+      // cycles of LSU address divergence per CTA: 28 instructions x 8 warps x 32 distinct lines.)  The tile lives in the
+      // activation operands, which nobody touches before the agg result is written.
       constexpr int PW = ZD == 96 ? 48 : 32, NPASS = ZD / PW, P4 = PW / 4, PITCH = PW + 4;
+      constexpr int PPH = NPASS / 2;                        // passes per weight half (= ring stage)
+      constexpr int NLOOP = NR == 32 ? NPASS : PPH;         // NR = 16: both halves advance together
       static_assert(8 * 32 * PITCH * 4 <= 2 * OPND_BYTES, "staging tiles must fit in actA + actH");
-      const bool ok = row0 + lane < a.n;
+      const int arow = NR == 32 ? lane : (lane & 15), ahalf = NR == 32 ? 0 : (lane >> 4);
+      const bool ok = row0 + arow < a.n;
       float* stg = reinterpret_cast<float*>(sm.actA) + warp * (32 * PITCH);
       float4 g[P4], rb[P4];
-      float2 av[8];
+      float2 av[8], av2[8];
       auto load_pass = [&](int pass) {
 #pragma unroll
         for (int it = 0; it < P4; ++it) {
-          const int idx = it * 32 + lane, r = idx / P4, c4 = idx % P4;
+          const int idx = it * 32 + lane, slot = idx / P4, c4 = idx % P4;
+          const int r = NR == 32 ? slot : (slot & 15);
+          const int dpass = NR == 32 ? pass : (slot >> 4) * PPH + pass;
           g[it] = row0 + r < a.n
-                      ? __ldg(reinterpret_cast<const float4*>(a.rbar + (size_t)(row0 + r) * (H * ZD) + warp * ZD + pass * PW) + c4)
+                      ? __ldg(reinterpret_cast<const float4*>(a.rbar + (size_t)(row0 + r) * (H * ZD) + warp * ZD + dpass * PW) + c4)
                       : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       };
@@ -487,50 +521,72 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok) t4 = __ldg(reinterpret_cast<const float4*>(a.aggv + (size_t)(row0 + lane) * D + 16 * warp) + i);
+        if (ok && ahalf == 0) t4 = __ldg(reinterpret_cast<const float4*>(a.aggv + (size_t)(row0 + arow) * D + 16 * warp) + i);
         av[2 * i] = make_float2(t4.x, t4.y);
         av[2 * i + 1] = make_float2(t4.z, t4.w);
+        av2[2 * i] = av2[2 * i + 1] = make_float2(0.f, 0.f);
       }
 #pragma unroll
-      for (int pass = 0; pass < NPASS; ++pass) {
+      for (int pass = 0; pass < NLOOP; ++pass) {
 #pragma unroll
         for (int it = 0; it < P4; ++it) {
-          const int idx = it * 32 + lane, r = idx / P4, c4 = idx % P4;
-          *reinterpret_cast<float4*>(stg + r * PITCH + 4 * c4) = g[it];
+          const int idx = it * 32 + lane, slot = idx / P4, c4 = idx % P4;
+          *reinterpret_cast<float4*>(stg + slot * PITCH + 4 * c4) = g[it];
         }
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < P4; ++i) rb[i] = *reinterpret_cast<const float4*>(stg + lane * PITCH + 4 * i);
         __syncwarp();
-        if (pass + 1 < NPASS) load_pass(pass + 1);          // in flight under this pass's FMAs
-        constexpr int PPH = NPASS / 2;                      // passes per weight half (= ring stage)
-        const int half = pass / PPH;
-        if (pass % PPH == 0) {
-          tcp::mbar_wait(&sm.full[half], 0);
+        if (pass + 1 < NLOOP) load_pass(pass + 1);          // in flight under this pass's FMAs
+        const int half = NR == 32 ? pass / PPH : ahalf;
+        if (NR == 32 ? (pass % PPH == 0) : (pass == 0)) {
+          if (NR == 32) {
+            tcp::mbar_wait(&sm.full[half], 0);
+          } else {
+            tcp::mbar_wait(&sm.full[0], 0);
+            tcp::mbar_wait(&sm.full[1], 0);
+          }
           if (half == 0) PSW_EMARK(2); else PSW_EMARK(15);
         }
         const float* wv = reinterpret_cast<const float*>(sm.ring[half]) + (pass % PPH) * PW * D + 16 * warp;
+        auto chain = [&](float2 (&acc)[8]) {
 #pragma unroll
-        for (int dq = 0; dq < P4; ++dq) {
-          const float4 r4 = rb[dq];
-          const float rv[4] = {r4.x, r4.y, r4.z, r4.w};
+          for (int dq = 0; dq < P4; ++dq) {
+            const float4 r4 = rb[dq];
+            const float rv[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float* wr = wv + (dq * 4 + j) * D;
+            for (int j = 0; j < 4; ++j) {
+              const float* wr = wv + (dq * 4 + j) * D;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 w4 = *reinterpret_cast<const float4*>(wr + 4 * i);
-              const float2 rr2 = make_float2(rv[j], rv[j]);      // packed FFMA2: two columns per instruction (same rounding)
-              av[2 * i] = __ffma2_rn(rr2, make_float2(w4.x, w4.y), av[2 * i]);
-              av[2 * i + 1] = __ffma2_rn(rr2, make_float2(w4.z, w4.w), av[2 * i + 1]);
+              for (int i = 0; i < 4; ++i) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wr + 4 * i);
+                const float2 rr2 = make_float2(rv[j], rv[j]);      // packed FFMA2: two columns per instruction (same rounding)
+                acc[2 * i] = __ffma2_rn(rr2, make_float2(w4.x, w4.y), acc[2 * i]);
+                acc[2 * i + 1] = __ffma2_rn(rr2, make_float2(w4.z, w4.w), acc[2 * i + 1]);
+              }
             }
           }
-        }
+        };
+        if (NR == 32 && half == 1) chain(av2); else chain(av);
       }
       PSW_EMARK(14);
+      if constexpr (NR == 16) {   // the second-half chain lives in lane + 16
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        *reinterpret_cast<float4*>(scr + lane * SCR_LD + 16 * warp + 4 * i) = make_float4(av[2 * i].x, av[2 * i].y, av[2 * i + 1].x, av[2 * i + 1].y);
+        for (int i = 0; i < 8; ++i) {
+          av2[i].x = __shfl_xor_sync(0xffffffffu, av[i].x, 16);
+          av2[i].y = __shfl_xor_sync(0xffffffffu, av[i].y, 16);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        av[i].x += av2[i].x;
+        av[i].y += av2[i].y;
+      }
+      if (NR == 32 || lane < 16) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<float4*>(scr + arow * SCR_LD + 16 * warp + 4 * i) = make_float4(av[2 * i].x, av[2 * i].y, av[2 * i + 1].x, av[2 * i + 1].y);
+      }
       epi_barrier();
       if (tid == 0) {          // every epilogue thread has read the two weight stages
         mbar_arrive(&sm.empty[0]);
@@ -544,15 +600,15 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
     }
     // ---- 1. gate: g = sigmoid(acc + Gx) ; u = agg + g (S - agg) -> operand A        (T-map)
     {
-      float gxv[16], sv[16];
+      float gxv[VPT], sv[VPT];
       t_load_glb(a.gx, gxv);
       t_load_glb(a.s, sv);
       wait_acc(A_GATE);
       PSW_EMARK(4);
-      tmem_ld16_pair(lb + slot_col(0) + 16 * ch, v);
+      tmem_ld_pair<VPT, NR>(lb + slot_col(0) + VPT * ch, v);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float ag = scr[(16 * ch + i) * SCR_LD + f];
+      for (int i = 0; i < VPT; ++i) {
+        const float ag = scr[(VPT * ch + i) * SCR_LD + f];
         const float g = 1.0f / (1.0f + expf(-(v[i] + gxv[i])));
         v[i] = ag + g * (sv[i] - ag);
       }
@@ -561,21 +617,21 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
       PSW_EMARK(5);
     }
     // ---- 2. o = acc + bo ; x1 = x + LN_post(o) (kept in registers, R-map) ; LN_ffpre(x1) -> operand A
-    float x1[16];
+    float x1[VPT];
     {
       r_load_glb(a.x, x1);
       const float bo = vec[tcp::V_BO + f];
       wait_acc(A_OUT);
       PSW_EMARK(6);
-      tmem_ld16_pair(lb + slot_col(1) + 16 * ch, v);
+      tmem_ld_pair<VPT, NR>(lb + slot_col(1) + VPT * ch, v);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] += bo;
+      for (int i = 0; i < VPT; ++i) v[i] += bo;
       t_store_scr(v);
       epi_barrier();
       r_load_scr(v);
       r_layernorm(v, tcp::V_LNPOST_G, tcp::V_LNPOST_B);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < VPT; ++i) {
         x1[i] += v[i];
         v[i] = x1[i];
       }
@@ -589,9 +645,9 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
     for (int tt = 0; tt < 4; ++tt) {
       const float b1 = vec[tcp::V_B1 + 128 * tt + f];
       wait_acc(A_UP + tt);
-      tmem_ld16_pair(lb + slot_col(2 + (tt & 1)) + 16 * ch, v);
+      tmem_ld_pair<VPT, NR>(lb + slot_col(2 + (tt & 1)) + VPT * ch, v);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + b1, 0.f);
+      for (int i = 0; i < VPT; ++i) v[i] = fmaxf(v[i] + b1, 0.f);
       if (tt > 0) {
         tcp::mbar_wait(&sm.h_free, ph_hfree);   // down_{t-1} has consumed the hidden operand
         ph_hfree ^= 1;
@@ -605,15 +661,15 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
       PSW_EMARK(8);
       wait_acc(A_DOWN);
       PSW_EMARK(9);
-      tmem_ld16_pair(lb + slot_col(4) + 16 * ch, v);
+      tmem_ld_pair<VPT, NR>(lb + slot_col(4) + VPT * ch, v);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] += b2;
+      for (int i = 0; i < VPT; ++i) v[i] += b2;
       t_store_scr(v);
       epi_barrier();
       r_load_scr(v);
       r_layernorm(v, tcp::V_LNFFPOST_G, tcp::V_LNFFPOST_B);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] += x1[i];
+      for (int i = 0; i < VPT; ++i) v[i] += x1[i];
       r_store_glb(a.out, v);
       if (has_next) {
         r_layernorm(v, tcp::V_LNDST_G, tcp::V_LNDST_B);
@@ -629,9 +685,9 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
         const float bq = vec[tcp::V_BQ + f];
         wait_acc(A_Q);
         PSW_EMARK(11);
-        tmem_ld16_pair(lb + slot_col(2) + 16 * ch, v);
+        tmem_ld_pair<VPT, NR>(lb + slot_col(2) + VPT * ch, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += bq;
+        for (int i = 0; i < VPT; ++i) v[i] += bq;
         t_store_opnd(sm.actH, v);             // every MMA that read the hidden operand completed before acc_done[DOWN]
         publish(&sm.opnd_ready);              // q operand written, slot 2 read
         PSW_EMARK(12);
@@ -640,17 +696,17 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
       {
         const float bs = vec[tcp::V_BS + f];
         wait_acc(A_S);
-        tmem_ld16_pair(lb + slot_col(0) + 16 * ch, v);
+        tmem_ld_pair<VPT, NR>(lb + slot_col(0) + VPT * ch, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += bs;
+        for (int i = 0; i < VPT; ++i) v[i] += bs;
         t_store_glb(a.s_n, D, 0, v);
       }
       {
         const float bg = vec[tcp::V_BG + f];
         wait_acc(A_GX);
-        tmem_ld16_pair(lb + slot_col(1) + 16 * ch, v);
+        tmem_ld_pair<VPT, NR>(lb + slot_col(1) + VPT * ch, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += bg;
+        for (int i = 0; i < VPT; ++i) v[i] += bg;
         publish(&sm.sgx_read);                // slots 0 and 1 read: the last two Qhat GEMMs may overwrite them
         t_store_glb(a.gx_n, D, 0, v);
       }
@@ -658,7 +714,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
 #pragma unroll 1
       for (int h = 0; h < H; ++h) {
         wait_acc(A_QH + h);
-        tmem_ld16_pair(lb + slot_col(qh_slot(h)) + 16 * ch, v);
+        tmem_ld_pair<VPT, NR>(lb + slot_col(qh_slot(h)) + VPT * ch, v);
         t_store_glb(a.qhat_n, (size_t)H * D, h * D, v);
       }
       PSW_EMARK(13);

@@ -609,3 +609,16 @@ def test_graphed_forward_matches_eager_and_accepts_host_batches():
         for name, r in eager['rollout_trajs'].items():
             assert torch.equal(r['traj'], out['rollout_trajs'][name]['traj']), (first, name)
     assert len(runner._cache) == 1
+
+
+def test_single_scene_equals_large_batch_bit_for_bit():
+    """The latency path and the throughput path are the same arithmetic: a scene rolled out alone (16-row node-kernel CTAs,
+    one-launch edge kernel with four warps per row, small-launch head) equals the same scene inside a 30-scene batch (3000 rows:
+    32-row node-kernel CTAs, the three-kernel persistent edge path, 32-row head kernel) bit for bit."""
+    kw = dict(n_agents=100, n_map=80, steps=30)
+    out_b, _ = _run_gpu(dict(kw, n_scenes=30), False)
+    for s in (0, 17, 29):
+        out_1, _ = _run_gpu(dict(kw, n_scenes=1, first_scene=s), False)
+        for name, r in out_1['rollout_trajs'].items():
+            other = out_b['rollout_trajs'][f'{s}-{name.split("-", 1)[1]}']
+            assert torch.equal(r['traj'], other['traj']) and torch.equal(r['vel'], other['vel']), (s, name)
