@@ -207,8 +207,10 @@ int launch_dstpre(const float* x, int n, const float* w, const DstScratch& d, cu
     psw::Args a{};
     a.x = x; a.q_n = d.q; a.qhat_n = d.qhat; a.s_n = d.s; a.gx_n = d.gx;
     a.W = nullptr; a.Wn = w; a.n = n;
-    if (sw_rows16(n)) psw::attn_post_sw_kernel<96, 16><<<(n + 15) / 16, psw::THREADS, psw::SMEM_BYTES, st>>>(a);
-    else psw::attn_post_sw_kernel<96, 32><<<(n + 31) / 32, psw::THREADS, psw::SMEM_BYTES, st>>>(a);
+    cudaError_t le;
+    if (sw_rows16(n)) le = launch_pdl(psw::attn_post_sw_kernel<96, 16>, dim3((n + 15) / 16), dim3(psw::THREADS), psw::SMEM_BYTES, st, a);
+    else le = launch_pdl(psw::attn_post_sw_kernel<96, 32>, dim3((n + 31) / 32), dim3(psw::THREADS), psw::SMEM_BYTES, st, a);
+    if (le != cudaSuccess) return (int)le;
     PROSIM_CHECK_LAUNCH();
     return 0;
   }
@@ -309,12 +311,14 @@ int launch_edge(const DstScratch& d, const float* kv, const prosim_graph_t& g, i
   if (n_dst <= FUSED_EDGE_MAX_ROWS && (g_tc_mask & 16)) {
     // small launch: q.K' scores, the z pass and the V' aggregation in ONE launch, one CTA of four warps per row (edge_row.cuh)
     LaunchScope ls(PROSIM_K_ATTN_EDGE, st);
+    cudaError_t le;
     if (g.zd == 96)
-      attn_edge_row_kernel<96><<<n_dst, 128, EdgeRowCfg<96>::smem_bytes(), st>>>(tm, tm32, d.qhat, d.q, kv, g.nbr, g.deg, g.stride, n_dst,
-                                                                              sk, rbar, pw, ft, ft_tiles, aggv);
+      le = launch_pdl(attn_edge_row_kernel<96>, dim3(n_dst), dim3(128), EdgeRowCfg<96>::smem_bytes(), st, tm, tm32, d.qhat, d.q, kv, g.nbr,
+                      g.deg, g.stride, n_dst, sk, rbar, pw, ft, ft_tiles, aggv);
     else
-      attn_edge_row_kernel<128><<<n_dst, 128, EdgeRowCfg<128>::smem_bytes(), st>>>(tm, tm32, d.qhat, d.q, kv, g.nbr, g.deg, g.stride, n_dst,
-                                                                                sk, rbar, pw, ft, ft_tiles, aggv);
+      le = launch_pdl(attn_edge_row_kernel<128>, dim3(n_dst), dim3(128), EdgeRowCfg<128>::smem_bytes(), st, tm, tm32, d.qhat, d.q, kv,
+                      g.nbr, g.deg, g.stride, n_dst, sk, rbar, pw, ft, ft_tiles, aggv);
+    if (le != cudaSuccess) return (int)le;
     PROSIM_CHECK_LAUNCH();
     return 0;
   }
@@ -363,15 +367,17 @@ int launch_post(const float* x, int n, int zd, const float* rbar, const float* a
     a.x = x; a.rbar = rbar; a.aggv = aggv; a.s = cur.s; a.gx = cur.gx; a.out = out;
     a.q_n = nxt.q; a.qhat_n = nxt.qhat; a.s_n = nxt.s; a.gx_n = nxt.gx;
     a.W = w; a.Wn = w_next; a.n = n;
+    cudaError_t le;
     if (sw_rows16(n)) {
-      const int grid = (n + 15) / 16;
-      if (zd == 96) psw::attn_post_sw_kernel<96, 16><<<grid, psw::THREADS, psw::SMEM_BYTES, st>>>(a);
-      else psw::attn_post_sw_kernel<128, 16><<<grid, psw::THREADS, psw::SMEM_BYTES, st>>>(a);
+      const dim3 grid((n + 15) / 16);
+      if (zd == 96) le = launch_pdl(psw::attn_post_sw_kernel<96, 16>, grid, dim3(psw::THREADS), psw::SMEM_BYTES, st, a);
+      else le = launch_pdl(psw::attn_post_sw_kernel<128, 16>, grid, dim3(psw::THREADS), psw::SMEM_BYTES, st, a);
     } else {
-      const int grid = (n + 31) / 32;
-      if (zd == 96) psw::attn_post_sw_kernel<96, 32><<<grid, psw::THREADS, psw::SMEM_BYTES, st>>>(a);
-      else psw::attn_post_sw_kernel<128, 32><<<grid, psw::THREADS, psw::SMEM_BYTES, st>>>(a);
+      const dim3 grid((n + 31) / 32);
+      if (zd == 96) le = launch_pdl(psw::attn_post_sw_kernel<96, 32>, grid, dim3(psw::THREADS), psw::SMEM_BYTES, st, a);
+      else le = launch_pdl(psw::attn_post_sw_kernel<128, 32>, grid, dim3(psw::THREADS), psw::SMEM_BYTES, st, a);
     }
+    if (le != cudaSuccess) return (int)le;
     PROSIM_CHECK_LAUNCH();
     return 0;
   }

@@ -22,6 +22,30 @@ constexpr float LN_EPS = 1e-5f;
     if (e__ != cudaSuccess) return (int)e__;        \
   } while (0)
 
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl() may be scheduled as soon as every CTA of its
+// predecessor in the stream has executed pdl_launch_dependents() (or exited); it must execute pdl_wait() -- which returns when
+// the predecessor grid has completed and its memory operations are visible -- before it reads or writes anything the
+// predecessor (or anything before it) touches.  Used for the two kernels that alternate in the single-scene layer loop
+// (edge_row.cuh, post_sw.cuh): the next kernel's launch latency and set-up (barrier init, TMEM allocation, the first weight
+// copies) run under the tail of the current one.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -48,8 +48,10 @@ __global__ void __launch_bounds__(128)
   float* mt = reinterpret_cast<float*>(gbase + NSTAGE * C::ZBYTES + C::QBYTES + C::PBYTES);
   const uint32_t bar0 = e4::smem_u32(gbase + NSTAGE * C::ZBYTES + C::QBYTES + C::PBYTES + C::MBYTES);
   const uint32_t zb0_s = e4::smem_u32(zb0), qb_s = e4::smem_u32(qb);
+  pdl_launch_dependents();
   if (threadIdx.x < NSTAGE) e4::mbar_init(bar0 + threadIdx.x * 8, 1);
   __syncthreads();
+  pdl_wait();   // every input of this kernel is produced by its predecessors (common.cuh: programmatic dependent launch)
 
   const int n_e = min(__ldg(deg + row), stride);
   const int ntiles = (n_e + 31) >> 5;

@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
   constexpr int VR_HALF_BYTES = (ZD / 2) * D * 4;      // the fp32 Wvr' block [ZD][128] travels as two ring stages
 
   if (tid == 0 && blockIdx.x == 0 && has_next) tcp::g_tcp_dbg[30] = clock64();
+  pdl_launch_dependents();   // the next kernel in the stream may be scheduled; it blocks in its own pdl_wait() until we are done
   if (warp == 0) tc::tmem_alloc(&sm.tmem_base, 512);
   const int n_chunks = has_next ? 58 : 42;
   const int chunk0 = pre_only ? 42 : 0;             // ring positions count from the first chunk of the launch
@@ -227,6 +228,9 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = sm.tmem_base;
+  // Everything above touched only the weights (constant during a forward) and this CTA's shared / tensor memory; from here on
+  // the kernel reads what the previous kernel wrote and writes what it may still be reading.
+  pdl_wait();
 
   if (warp == 8) {
     // ================================================================== weight producer
