@@ -412,7 +412,7 @@ def run_b200(a):
             if pm['launches']:
                 fl = algorithmic_flops_post(A) / (pm['ms'] / pm['launches'] * 1e-3) / 1e12
                 fp = 148 * 128 * 2 * peaks1.get('sm_max_mhz', 1965.0) * 1e6 / 1e12
-                single['roofline_dense_kernel'] = {'kernel': 'attn_post_kernel (fp32 FFMA, launches < 1024 rows)', 'bound': 'tensor',
+                single['roofline_dense_kernel'] = {'kernel': 'psw::attn_post_sw_kernel (tcgen05 3xTF32, 16 rows per CTA: 8 CTAs for one scene)', 'bound': 'tensor',
                                                    'achieved': fl, 'peak': peaks1.get('bf16_tflops_sustained') or 1400.0,
                                                    'unit': 'TFLOP/s', 'frac': fl / (peaks1.get('bf16_tflops_sustained') or 1400.0),
                                                    'fp32_ffma_frac': fl / fp, 'share_of_step': pm['ms'] / pm['forward_ms']}

@@ -49,12 +49,15 @@ typedef struct {
 } prosim_stack_side_t;
 
 int prosim_abi_version(void);
-/* Tensor-core kernels: 1 (default) = tcgen05 / TMEM 3xTF32 for the node-side GEMMs of the AttentionLayer (launches of
- * >= 1024 rows: csrc/post_sw.cuh, 32 rows per CTA, up to 9472 rows; csrc/tc_post.cuh, 128 rows per CTA, above), the K'|V'
- * projections (csrc/kv_tc.cuh) and the PointNet encoders (csrc/pointnet_tc.cuh); 0 = fp32 FFMA kernels everywhere (A/B
- * measurement and parity cross-checks).  Other values select kernels by bit (1 node kernels, 2 K'|V', 4 PointNet, 8 allow
- * the 32-row node kernel, 16 the fused single-launch edge phase of launches <= 592 rows) for fault isolation.
- * PROCESS-GLOBAL switch. */
+/* Kernel selection: 1 (default) = tcgen05 / TMEM 3xTF32 kernels for the node-side GEMMs of the AttentionLayer
+ * (csrc/post_sw.cuh: 16 or 32 destination rows per CTA for launches of up to 9472 rows, incl. its "pre-only" mode for the
+ * first layer of a stack; csrc/tc_post.cuh, 128 rows per CTA, above), the K'|V' projections (csrc/kv_tc.cuh) and the
+ * PointNet encoders (csrc/pointnet_tc.cuh), and the one-launch edge kernel (csrc/edge_row.cuh) for launches of <= 592 rows;
+ * 0 = fp32 FFMA kernels and the three-kernel edge path everywhere (A/B measurement and parity cross-checks).  Other values
+ * select by bit (1 node kernels, 2 K'|V', 4 PointNet, 8 allow the 16/32-row node kernel, 16 the one-launch edge kernel) for
+ * fault isolation.  PROCESS-GLOBAL switch: not part of the re-entrant data path, must not be flipped while another thread
+ * enqueues work.  The environment variable PROSIM_NO_PDL=1 (read once, at the first launch) turns programmatic dependent
+ * launch off for the kernels that use it. */
 int prosim_set_tensor_core(int on);
 /* prosim_attn_stack_fwd with fixed sources on both sides runs as up to `parts` (1..4, default 1) independent row chains of
  * >= 1024 rows on internal side streams (forked from / joined to the caller's stream with events; capturable in a CUDA
@@ -68,6 +71,10 @@ int prosim_set_stack_split(int parts);
 /* Measurement support: SM-clock timestamps of the phases of CTA 0 of the last tcgen05 node-kernel launch
  * ([0..15] epilogue thread, [16..31] MMA thread; csrc/tc_post.cuh TCP_MARK). */
 int prosim_tc_debug_read(long long* out32);
+/* Test support: fills the shared memory (226 KB) and all 512 tensor-memory columns of every SM with `pattern` (e.g. NaN).
+ * Neither is cleared between kernels or processes; a forward whose result changes after a scrub consumes on-chip state it
+ * never wrote (tools/poison_check.py). */
+int prosim_debug_scrub(float pattern, void* stream);
 
 /* Launch accounting and optional per-kernel CUDA-event timing (measurement support for bench.py; not part of
  * the data path).  kernel_class < 0 in prosim_launch_count = all classes; prosim_profile_enable(-1) disables. */

@@ -27,7 +27,7 @@ constexpr int g_rt2_min_rows = 128;   // row count from which the 32-row gemm_ti
                                       // 2..16-row ones: measured on one 128-agent scene, 12.07 ms per forward at 1024, 11.82 at 128
 int g_split = 1;        // row-split chains of prosim_attn_stack_fwd (prosim_set_stack_split); measured 31.4 / 30.9 / 30.6 / 31.4 ms at 1..4 parts
 bool g_use_tc = true;   // node-side GEMMs on tcgen05 (tc_post.cuh); prosim_set_tensor_core(0) selects the FFMA kernels
-int g_tc_mask = 31;     // bit 0: node kernels, bit 1: K'|V', bit 2: PointNet, bit 3: the 32-row "swapped" node kernel (post_sw.cuh),
+int g_tc_mask = std::getenv("PROSIM_TC_MASK") ? std::atoi(std::getenv("PROSIM_TC_MASK")) & 31 : 31;   // env: fault isolation from a fresh process     // bit 0: node kernels, bit 1: K'|V', bit 2: PointNet, bit 3: the 32-row "swapped" node kernel (post_sw.cuh),
                         // bit 4: the fused small-launch edge kernel (prosim_set_tensor_core(mask), A/B and fault isolation)
 constexpr int SW_MAX_ROWS = 148 * 32 * 2;   // above two waves of 32-row CTAs the 128-row kernel streams 4x less weight per row
 // 16 rows per CTA while that still fits one wave: twice the CTAs, half the per-CTA epilogue work (bit-identical to 32 rows)
@@ -408,9 +408,44 @@ int launch_post(const float* x, int n, int zd, const float* rbar, const float* a
 
 }  // namespace
 
+// test support (prosim_debug_scrub): one CTA per SM (227 KB of dynamic shared memory), 128 threads = 128 TMEM lanes
+__global__ void __launch_bounds__(128, 1) scrub_kernel(float pattern, int smem_floats) {
+  extern __shared__ float scrub_smem[];
+  __shared__ uint32_t tmem_slot;
+  for (int i = threadIdx.x; i < smem_floats; i += 128) scrub_smem[i] = pattern;
+  if (threadIdx.x < 32) tc::tmem_alloc(&tmem_slot, 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t taddr = tmem_slot + ((uint32_t)((threadIdx.x >> 5) * 32) << 16);
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = pattern;
+  for (int c = 0; c < 512; c += 32) tcp::tmem_st32(taddr + c, v);
+  asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+  tc::fence_before_sync();
+  __syncthreads();
+  if (threadIdx.x < 32) tc::tmem_dealloc(tmem_slot, 512);
+  // keep the CTA alive long enough for the other SMs to receive theirs (one CTA per SM by shared-memory size)
+  const long long t0 = clock64();
+  while (clock64() - t0 < 200000) {}
+  if (scrub_smem[smem_floats - 1 - threadIdx.x] != pattern && pattern == pattern) tmem_slot = 0;   // keep the stores
+}
+
 extern "C" {
 
 int prosim_abi_version(void) { return 8; }
+int prosim_debug_scrub(float pattern, void* stream) {
+  constexpr int BYTES = 226 * 1024;
+  cudaError_t e = cudaFuncSetAttribute(scrub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES);
+  if (e != cudaSuccess) return (int)e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  for (int rep = 0; rep < 2; ++rep) scrub_kernel<<<sms, 128, BYTES, static_cast<cudaStream_t>(stream)>>>(pattern, BYTES / 4);
+  PROSIM_CHECK_LAUNCH();
+  return 0;
+}
 int prosim_tc_debug_read(long long* out32) {
   if (!out32) return ERR_ARG;
   return (int)cudaMemcpyFromSymbol(out32, tcp::g_tcp_dbg, 32 * sizeof(long long));

@@ -5,6 +5,7 @@
 // the reference's fp32 PyTorch path is gated at 1e-5 per tick.  Reductions run in a fixed order
 // (no float atomics), so results are bit-reproducible run to run and independent of batch size.
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -29,8 +30,20 @@ constexpr float LN_EPS = 1e-5f;
 // (edge_row.cuh, post_sw.cuh): the next kernel's launch latency and set-up (barrier init, TMEM allocation, the first weight
 // copies) run under the tail of the current one.  Without the launch attribute both instructions are no-ops.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// A pointer to data the predecessor produced, "acquired" after pdl_wait(): the value passes through a volatile asm, so no load
+// through it -- not even a read-only (ld.global.nc / __restrict__) one, which the compiler may otherwise move freely because
+// the kernel promises the data is constant during its lifetime -- can be scheduled before the wait.
+template <typename T>
+__device__ __forceinline__ T* pdl_acquire(T* p) {
+  asm volatile("" : "+l"(p)::"memory");
+  return p;
+}
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+inline bool pdl_enabled() {   // PROSIM_NO_PDL=1: plain stream-ordered launches (A/B and fault isolation)
+  static const bool on = std::getenv("PROSIM_NO_PDL") == nullptr;
+  return on;
+}
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -42,7 +55,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 

@@ -24,13 +24,16 @@ namespace prosim {
 constexpr int GATHER_EB = 8;
 
 // Sk[row*stride + e][h] = sum_c q[row][h*16+c] * K'[nbr[e]][h*16+c]   -- one destination row, one warp
-template <int EB = GATHER_EB>
+// COHERENT: the queries were written by a kernel this one may overlap with under programmatic dependent launch (edge_row.cuh):
+// read them through L2, not through the non-coherent path
+template <int EB = GATHER_EB, bool COHERENT = false>
 __device__ __forceinline__ void edge_qk_row(const float* __restrict__ Qg, const float* __restrict__ KV,
                                             const int* __restrict__ nbr, const int* __restrict__ deg, int stride, int row,
                                             int lane, float* __restrict__ Sk, int tile_first = 0, int tile_step = 1) {
   const int n_e = min(deg[row], stride);
   const size_t ebase = (size_t)row * stride;
-  const float4 q4 = __ldg(reinterpret_cast<const float4*>(Qg + (size_t)row * D) + lane);
+  const float4* qp = reinterpret_cast<const float4*>(Qg + (size_t)row * D) + lane;
+  const float4 q4 = COHERENT ? __ldcg(qp) : __ldg(qp);
   for (int e0 = 32 * tile_first; e0 < n_e; e0 += 32 * tile_step) {   // (tile_first, tile_step): the caller's share of the row
     const int jl = e0 + lane < n_e ? __ldg(nbr + ebase + e0 + lane) : 0;
     const int nt = min(32, n_e - e0);

@@ -32,9 +32,8 @@ constexpr int EDGE_ROW_EB = 32;   // gathers in flight per lane
 template <int ZD>
 __global__ void __launch_bounds__(128)
     attn_edge_row_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmZ32,
-                         const float* __restrict__ Qhat, const float* __restrict__ Qg, const float* __restrict__ KV,
-                         const int* __restrict__ nbr, const int* __restrict__ deg, int stride, int n_dst, float* Sk,
-                         float* __restrict__ Rbar, float* Pw, float* Ft, int ft_tiles, float* __restrict__ AggV) {
+                         const float* Qhat_, const float* Qg_, const float* KV_, const int* nbr_, const int* deg_, int stride,
+                         int n_dst, float* Sk_, float* Rbar_, float* Pw_, float* Ft_, int ft_tiles, float* AggV_) {
   using C = EdgeRowCfg<ZD>;
   constexpr int NSEG = C::NSEG, NSTAGE = C::NSTAGE;
   extern __shared__ uint8_t smem_raw[];
@@ -52,6 +51,18 @@ __global__ void __launch_bounds__(128)
   if (threadIdx.x < NSTAGE) e4::mbar_init(bar0 + threadIdx.x * 8, 1);
   __syncthreads();
   pdl_wait();   // every input of this kernel is produced by its predecessors (common.cuh: programmatic dependent launch)
+  // Qg (like Sk / Pw / Ft below) is read with ld.global.cg only: under programmatic dependent launch this CTA may be resident
+  // while the ping-pong q buffer is still being rewritten, which the non-coherent path's read-only contract excludes (post_sw.cuh)
+  const float* __restrict__ Qhat = pdl_acquire(Qhat_);
+  const float* Qg = pdl_acquire(Qg_);
+  const float* __restrict__ KV = pdl_acquire(KV_);
+  const int* __restrict__ nbr = pdl_acquire(nbr_);
+  const int* __restrict__ deg = pdl_acquire(deg_);
+  float* Sk = pdl_acquire(Sk_);
+  float* Pw = pdl_acquire(Pw_);
+  float* Ft = pdl_acquire(Ft_);
+  float* __restrict__ Rbar = pdl_acquire(Rbar_);
+  float* __restrict__ AggV = pdl_acquire(AggV_);
 
   const int n_e = min(__ldg(deg + row), stride);
   const int ntiles = (n_e + 31) >> 5;
@@ -84,7 +95,7 @@ __global__ void __launch_bounds__(128)
       if (t < ntiles) fetch_tile(t);
   }
   // ---- q.K' scores of the row: tile t by warp t % 4 (edge_qk_kernel's arithmetic, edge by edge)
-  edge_qk_row<EDGE_ROW_EB>(Qg, KV, nbr, deg, stride, row, lane, Sk, warp, 4);
+  edge_qk_row<EDGE_ROW_EB, true>(Qg, KV, nbr, deg, stride, row, lane, Sk, warp, 4);
   __syncthreads();                                        // Sk is read back below by other warps (through L2)
 
   float* rb = Rbar + (size_t)row * H * ZD;

@@ -142,7 +142,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) { tcp::mbar_arrive(e4
   } while (0)
 
 template <int ZD, int NR>
-__global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_constant__ Args a) {
+__global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_constant__ Args a_in) {
   static_assert(NR == 32 || NR == 16, "rows per CTA");
   constexpr int SLAB_BYTES = 2 * NR * 128;   // one 32-wide k block of an activation operand: NR hi rows then NR lo rows, 128 B each
   constexpr int LO_OFF = NR * 128;
@@ -153,8 +153,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw + ((1024u - (e4::smem_u32(smem_raw) & 1023u)) & 1023u));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * NR;
-  const float* __restrict__ W = a.W;
-  const float* __restrict__ Wn = a.Wn;
+  const float* __restrict__ W = a_in.W;
+  const float* __restrict__ Wn = a_in.Wn;
   const bool has_next = Wn != nullptr;
   const bool pre_only = W == nullptr;
   constexpr int VR_HALF_BYTES = (ZD / 2) * D * 4;      // the fp32 Wvr' block [ZD][128] travels as two ring stages
@@ -231,6 +231,13 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
   // Everything above touched only the weights (constant during a forward) and this CTA's shared / tensor memory; from here on
   // the kernel reads what the previous kernel wrote and writes what it may still be reading.
   pdl_wait();
+  // Row buffers are read with ld.global.cg (L2) from here on, never through the non-coherent path (__ldg / ld.global.nc), whose
+  // contract ("read-only for the lifetime of the kernel") a CTA that became resident several grids early cannot honour: the
+  // ping-pong q / s / gx / x buffers ARE rewritten between its launch and its pdl_wait().  A precaution, not a measured bug.
+  Args a = a_in;   // the row buffers are only reachable through pointers acquired after the wait
+  a.x = pdl_acquire(a.x); a.rbar = pdl_acquire(a.rbar); a.aggv = pdl_acquire(a.aggv); a.s = pdl_acquire(a.s); a.gx = pdl_acquire(a.gx);
+  a.out = pdl_acquire(a.out); a.q_n = pdl_acquire(a.q_n); a.qhat_n = pdl_acquire(a.qhat_n); a.s_n = pdl_acquire(a.s_n);
+  a.gx_n = pdl_acquire(a.gx_n);
 
   if (warp == 8) {
     // ================================================================== weight producer
@@ -417,7 +424,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
 #pragma unroll
       for (int i = 0; i < GPT; ++i) {
         float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rr_ok) t = __ldg(reinterpret_cast<const float4*>(base + (size_t)(row0 + rr) * D) + sg + LPR * i);
+        if (rr_ok) t = __ldcg(reinterpret_cast<const float4*>(base + (size_t)(row0 + rr) * D) + sg + LPR * i);
         v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
       }
     };
@@ -468,7 +475,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
 #pragma unroll
       for (int i = 0; i < VPT; ++i) {
         const int r = row0 + VPT * ch + i;
-        v[i] = r < a.n ? __ldg(base + (size_t)r * D + f) : 0.f;
+        v[i] = r < a.n ? __ldcg(base + (size_t)r * D + f) : 0.f;
       }
     };
     auto t_store_glb = [&](float* base, size_t ld, int col, const float (&v)[VPT]) {
@@ -517,7 +524,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
           const int r = NR == 32 ? slot : (slot & 15);
           const int dpass = NR == 32 ? pass : (slot >> 4) * PPH + pass;
           g[it] = row0 + r < a.n
-                      ? __ldg(reinterpret_cast<const float4*>(a.rbar + (size_t)(row0 + r) * (H * ZD) + warp * ZD + dpass * PW) + c4)
+                      ? __ldcg(reinterpret_cast<const float4*>(a.rbar + (size_t)(row0 + r) * (H * ZD) + warp * ZD + dpass * PW) + c4)
                       : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       };
@@ -525,7 +532,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_post_sw_kernel(const __grid_c
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok && ahalf == 0) t4 = __ldg(reinterpret_cast<const float4*>(a.aggv + (size_t)(row0 + arow) * D + 16 * warp) + i);
+        if (ok && ahalf == 0) t4 = __ldcg(reinterpret_cast<const float4*>(a.aggv + (size_t)(row0 + arow) * D + 16 * warp) + i);
         av[2 * i] = make_float2(t4.x, t4.y);
         av[2 * i + 1] = make_float2(t4.z, t4.w);
         av2[2 * i] = av2[2 * i + 1] = make_float2(0.f, 0.f);

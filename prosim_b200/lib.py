@@ -16,7 +16,7 @@ SYMBOLS = (
     'prosim_build_knn_edges', 'prosim_edge_pe', 'prosim_attn_kv', 'prosim_attn_layer_fwd', 'prosim_attn_stack_fwd',
     'prosim_policy_head_fwd', 'prosim_reconst_fwd', 'prosim_mlp2_fwd', 'prosim_init_traj', 'prosim_step_env',
     'prosim_gather_pose', 'prosim_step_agent_traj', 'prosim_launch_count', 'prosim_profile_enable', 'prosim_profile_read',
-    'prosim_rollout_to_world', 'prosim_tc_gemm_test', 'prosim_set_tensor_core', 'prosim_tc_debug_read', 'prosim_set_stack_split', 'prosim_tag_embed_fwd', 'prosim_cond_pool_fwd', 'prosim_workspace_bytes', 'prosim_policy_tick', 'prosim_obs_fuse_floats', 'prosim_obs_fuse_fwd',
+    'prosim_rollout_to_world', 'prosim_tc_gemm_test', 'prosim_set_tensor_core', 'prosim_tc_debug_read', 'prosim_debug_scrub', 'prosim_set_stack_split', 'prosim_tag_embed_fwd', 'prosim_cond_pool_fwd', 'prosim_workspace_bytes', 'prosim_policy_tick', 'prosim_obs_fuse_floats', 'prosim_obs_fuse_fwd',
 )
 
 KERNEL_CLASSES = {'pointnet': 0, 'radius': 1, 'knn': 2, 'edge_pe': 3, 'attn_kv': 4, 'attn_dstpre': 5, 'attn_edge': 6,
@@ -71,6 +71,7 @@ _SIGS = {
     'prosim_tc_gemm_test': [_P, _P, _P, c_int, c_int, _P],
     'prosim_set_tensor_core': [c_int],
     'prosim_tc_debug_read': [_P],
+    'prosim_debug_scrub': [c_float, _P],
     'prosim_set_stack_split': [c_int],
     'prosim_policy_tick': [POINTER(Tick), _P, c_size_t, _P],
     'prosim_obs_fuse_fwd': [_P, _P, _P, _P, c_int, _P, _P],

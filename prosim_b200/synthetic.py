@@ -33,6 +33,41 @@ def _rot(x, y, theta):
     return x * c - y * s, x * s + y * c
 
 
+def _map_geometry(centre, mhead, kappa):
+    """Polyline geometry from the random draws (pure function of its arguments)."""
+    f32 = torch.float32
+    s = (torch.arange(MAP_VEC + 1, dtype=f32) - MAP_VEC / 2.0) * 0.5
+    ang = mhead[:, None] + kappa[:, None] * s[None, :]
+    step = 0.5
+    dx = torch.cos(ang) * step
+    dy = torch.sin(ang) * step
+    px = centre[:, 0:1] + torch.cumsum(dx, dim=1) - dx
+    py = centre[:, 1:2] + torch.cumsum(dy, dim=1) - dy
+    start = torch.stack([px[:, :-1], py[:, :-1]], dim=-1)
+    end = torch.stack([px[:, 1:], py[:, 1:]], dim=-1)
+    p0, p1 = start[:, 0], end[:, -1]
+    m_heading = torch.atan2(p1[:, 1] - p0[:, 1], p1[:, 0] - p0[:, 0])
+    m_pos = (p0 + p1) / 2
+    sx, sy = _rot(start[..., 0] - m_pos[:, None, 0], start[..., 1] - m_pos[:, None, 1], -m_heading[:, None])
+    ex, ey = _rot(end[..., 0] - m_pos[:, None, 0], end[..., 1] - m_pos[:, None, 1], -m_heading[:, None])
+    return m_pos, m_heading, sx, sy, ex, ey
+
+
+def _map_geometry_checked(centre, mhead, kappa):
+    """_map_geometry evaluated until two consecutive evaluations agree bit for bit.  Its fp32 torch CPU ops (cos / sin / cumsum /
+    atan2) were observed to return results a few ulp apart on the FIRST call of ~8 % of fresh processes on the B200 box's host
+    (never on later calls, never in the authoring container): with Fourier features of sub-metre wavelength downstream, those
+    ulps are a 5e-5 difference in the first tick's output -- enough to fail the 1e-5 gate against goldens that were generated
+    from the regular values (tests/diag_first_forward.py tracked a 1-in-12 "flaky first test" down to this)."""
+    prev = _map_geometry(centre, mhead, kappa)
+    for _ in range(4):
+        cur = _map_geometry(centre, mhead, kappa)
+        if all(torch.equal(a, b) for a, b in zip(prev, cur)):
+            return cur
+        prev = cur
+    return prev
+
+
 def _one_scene(g, n_agents, n_map):
     f32 = torch.float32
     U = lambda *shape: torch.rand(*shape, generator=g, dtype=f32)
@@ -69,20 +104,7 @@ def _one_scene(g, n_agents, n_map):
     centre = U(n_map, 2) * 300.0 - 150.0
     mhead = U(n_map) * (2 * math.pi) - math.pi
     kappa = (U(n_map) - 0.5) * 0.08
-    s = (torch.arange(MAP_VEC + 1, dtype=f32) - MAP_VEC / 2.0) * 0.5
-    ang = mhead[:, None] + kappa[:, None] * s[None, :]
-    step = 0.5
-    dx = torch.cos(ang) * step
-    dy = torch.sin(ang) * step
-    px = centre[:, 0:1] + torch.cumsum(dx, dim=1) - dx
-    py = centre[:, 1:2] + torch.cumsum(dy, dim=1) - dy
-    start = torch.stack([px[:, :-1], py[:, :-1]], dim=-1)
-    end = torch.stack([px[:, 1:], py[:, 1:]], dim=-1)
-    p0, p1 = start[:, 0], end[:, -1]
-    m_heading = torch.atan2(p1[:, 1] - p0[:, 1], p1[:, 0] - p0[:, 0])
-    m_pos = (p0 + p1) / 2
-    sx, sy = _rot(start[..., 0] - m_pos[:, None, 0], start[..., 1] - m_pos[:, None, 1], -m_heading[:, None])
-    ex, ey = _rot(end[..., 0] - m_pos[:, None, 0], end[..., 1] - m_pos[:, None, 1], -m_heading[:, None])
+    m_pos, m_heading, sx, sy, ex, ey = _map_geometry_checked(centre, mhead, kappa)
     msel, lsel = U(n_map), U(n_map)
     mtype = torch.where(msel < 0.5, 1.0, torch.where(msel < 0.75, 2.0, 3.0))
     tls = torch.where(lsel < 0.7, -1.0, torch.where(lsel < 0.8, 0.0, torch.where(lsel < 0.9, 1.0, 2.0)))

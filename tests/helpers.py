@@ -90,3 +90,41 @@ def to_double(batch):
         if ex['condition'][c]['input'].is_floating_point():       # action tags stay int64
             ex['condition'][c]['input'] = ex['condition'][c]['input'].double()
     return batch
+
+
+def batch_sha1(batch):
+    """Checksum of every tensor of a (CPU) synthetic batch, in a fixed traversal order."""
+    import hashlib
+    h = hashlib.sha1()
+
+    def walk(o):
+        if torch.is_tensor(o):
+            h.update(o.detach().contiguous().cpu().numpy().tobytes())
+        elif isinstance(o, dict):
+            for k in sorted(o, key=str):
+                walk(o[k])
+        elif hasattr(o, '_data'):
+            walk(o._data)
+        elif hasattr(o, 'input') and hasattr(o, 'mask'):
+            walk(o.input), walk(o.mask), walk(getattr(o, 'position', None)), walk(getattr(o, 'heading', None))
+        elif isinstance(o, (list, tuple)):
+            for x in o:
+                walk(x)
+    walk(batch.extras)
+    return h.hexdigest()
+
+
+def make_case_batch(name):
+    """The synthetic input batch of a golden case, verified against the checksum recorded when the golden was generated
+    (tests/golden/input_checksums.json): a parity failure must never be a test-input difference in disguise
+    (prosim_b200/synthetic.py::_map_geometry_checked has the story)."""
+    import json
+    from prosim_b200 import synthetic
+    kw = (CASES.get(name) or BENCH_CASES[name])[0]
+    want = json.load(open(os.path.join(GOLDEN, 'input_checksums.json')))[name]
+    for _ in range(3):
+        batch = synthetic.make_batch(**kw)
+        if batch_sha1(batch) == want:
+            return batch
+    raise AssertionError(f'{name}: synthetic.make_batch does not reproduce the inputs the golden was generated from '
+                         f'(sha1 {batch_sha1(batch)} != {want})')

@@ -11,7 +11,7 @@ import torch
 
 from oracle.prosim_oracle import ProSimOracle
 from prosim_b200 import synthetic, weights
-from tests.helpers import BENCH_CASES, CASES, edge_set, load_golden, per_tick_max, stack_rollout
+from tests.helpers import BENCH_CASES, CASES, edge_set, load_golden, make_case_batch, per_tick_max, stack_rollout
 
 pytestmark = pytest.mark.gpu
 
@@ -27,10 +27,11 @@ def _model(goal):
     return _models[goal]
 
 
-def _run_gpu(kw, goal, keep_edges=False):
+def _run_gpu(kw, goal, keep_edges=False, name=None):
+    """name: a golden case -- its inputs are checked against the checksum recorded with the golden (helpers.make_case_batch)."""
     model = _model(goal)
     model.keep_tick_edges = keep_edges
-    batch = synthetic.make_batch(**kw).to('cuda')
+    batch = (make_case_batch(name) if name else synthetic.make_batch(**kw)).to('cuda')
     with torch.no_grad():
         out = model.forward(batch, 'val')['motion_pred']
     torch.cuda.synchronize()
@@ -42,7 +43,7 @@ def _run_gpu(kw, goal, keep_edges=False):
 def test_closed_loop_matches_reference_golden(name):
     kw, goal = CASES[name]
     gold = load_golden(name)
-    out, _ = _run_gpu(kw, goal)
+    out, _ = _run_gpu(kw, goal, name=name)
     names, traj, vel = stack_rollout(out)
     # bit-exact bookkeeping: agent order, pair names, shapes, probabilities
     assert names == gold['agent_names'].tolist()
@@ -108,7 +109,7 @@ def test_benchmarked_shape_matches_reference_golden(name):
     kw, goal, scenes = BENCH_CASES[name]
     gold = load_golden(name)
     n_sw, n_post = lib.launch_count(lib.KERNEL_CLASSES['attn_post_sw']), lib.launch_count(lib.KERNEL_CLASSES['attn_post'])
-    out, _ = _run_gpu(kw, goal)
+    out, _ = _run_gpu(kw, goal, name=name)
     n_sw = lib.launch_count(lib.KERNEL_CLASSES['attn_post_sw']) - n_sw
     n_post = lib.launch_count(lib.KERNEL_CLASSES['attn_post']) - n_post
     assert n_sw >= 12 * 8 + 12 and n_post == 12 * 8 + 12 + 12          # ticks + generator (+ encoder) on the 32-row kernel
@@ -151,7 +152,7 @@ def test_benchmarked_shape_teacher_forced_ticks(name):
     kw, goal, scenes = BENCH_CASES[name]
     gold = load_golden(name)
     model = _model(goal)
-    batch = synthetic.make_batch(**kw).to('cuda')
+    batch = make_case_batch(name).to('cuda')
     rows, P = torch.as_tensor(gold['rows']).cuda(), int(gold['n_rows'])
     R = len(rows)
     with torch.no_grad():
@@ -360,9 +361,9 @@ def test_batch_invariance_across_kernel_variants():
 
 
 def test_batch_invariance_tensor_core_kernel():
-    """tcgen05 node kernel (launches of >= 1024 rows): a scene's result does not depend on what else is in the batch
-    (bit exact between a 12-scene and a 20-scene batch), and it agrees with the FFMA path of the single-scene launch to
-    fp32 rounding (3xTF32 products, 2^-21 relative each)."""
+    """tcgen05 node kernel: a scene's result does not depend on what else is in the batch (bit exact between a 12-scene and a
+    20-scene batch, and -- since the 16-row and 32-row CTAs, the one-launch and the three-kernel edge paths share their
+    arithmetic -- with the scene run alone; test_single_scene_equals_large_batch_bit_for_bit asserts the latter exactly)."""
     kw = dict(n_agents=100, n_map=80, steps=20)
     out_a, _ = _run_gpu(dict(kw, n_scenes=12), False)
     out_b, _ = _run_gpu(dict(kw, n_scenes=20), False)
@@ -382,7 +383,7 @@ def test_batch_invariance_tensor_core_kernel():
 def test_tensor_core_path_with_capped_generator_graph():
     """>= 1024 policy rows with 450 map polylines per scene: the generator's scene->prompt graph hits its 512-neighbour
     cap (16 z tiles per row in the edge kernel) on the tensor-core path; checked against the same scenes run one by one
-    (FFMA path, itself pinned to the reference goldens)."""
+    (one-launch edge kernel with four warps per row, itself pinned to the reference goldens)."""
     kw = dict(n_agents=100, n_map=450, steps=20)
     out_a, _ = _run_gpu(dict(kw, n_scenes=11), False)
     worst = 0.0
