@@ -56,8 +56,8 @@ int prosim_abi_version(void);
  * 0 = fp32 FFMA kernels and the three-kernel edge path everywhere (A/B measurement and parity cross-checks).  Other values
  * select by bit (1 node kernels, 2 K'|V', 4 PointNet, 8 allow the 16/32-row node kernel, 16 the one-launch edge kernel) for
  * fault isolation.  PROCESS-GLOBAL switch: not part of the re-entrant data path, must not be flipped while another thread
- * enqueues work.  The environment variable PROSIM_NO_PDL=1 (read once, at the first launch) turns programmatic dependent
- * launch off for the kernels that use it. */
+ * enqueues work.  Environment: PROSIM_TC_MASK = initial mask (fault isolation from a fresh process); PROSIM_NO_PDL=1 (read
+ * once, at the first launch) turns programmatic dependent launch off for the kernels that use it. */
 int prosim_set_tensor_core(int on);
 /* prosim_attn_stack_fwd with fixed sources on both sides runs as up to `parts` (1..4, default 1) independent row chains of
  * >= 1024 rows on internal side streams (forked from / joined to the caller's stream with events; capturable in a CUDA

@@ -27,8 +27,10 @@ constexpr int g_rt2_min_rows = 128;   // row count from which the 32-row gemm_ti
                                       // 2..16-row ones: measured on one 128-agent scene, 12.07 ms per forward at 1024, 11.82 at 128
 int g_split = 1;        // row-split chains of prosim_attn_stack_fwd (prosim_set_stack_split); measured 31.4 / 30.9 / 30.6 / 31.4 ms at 1..4 parts
 bool g_use_tc = true;   // node-side GEMMs on tcgen05 (tc_post.cuh); prosim_set_tensor_core(0) selects the FFMA kernels
-int g_tc_mask = std::getenv("PROSIM_TC_MASK") ? std::atoi(std::getenv("PROSIM_TC_MASK")) & 31 : 31;   // env: fault isolation from a fresh process     // bit 0: node kernels, bit 1: K'|V', bit 2: PointNet, bit 3: the 32-row "swapped" node kernel (post_sw.cuh),
-                        // bit 4: the fused small-launch edge kernel (prosim_set_tensor_core(mask), A/B and fault isolation)
+// Kernel selection mask (prosim_set_tensor_core; initial value from the environment variable PROSIM_TC_MASK for fault isolation
+// from a fresh process): bit 0 node kernels on tcgen05, bit 1 K'|V', bit 2 PointNet, bit 3 the 16 / 32-row "swapped" node kernel
+// (post_sw.cuh) incl. its pre-only mode, bit 4 the one-launch edge kernel of small launches (edge_row.cuh)
+int g_tc_mask = std::getenv("PROSIM_TC_MASK") ? std::atoi(std::getenv("PROSIM_TC_MASK")) & 31 : 31;
 constexpr int SW_MAX_ROWS = 148 * 32 * 2;   // above two waves of 32-row CTAs the 128-row kernel streams 4x less weight per row
 // 16 rows per CTA while that still fits one wave: twice the CTAs, half the per-CTA epilogue work (bit-identical to 32 rows)
 inline bool sw_rows16(int n) { return (n + 15) / 16 <= 148; }
@@ -434,7 +436,7 @@ __global__ void __launch_bounds__(128, 1) scrub_kernel(float pattern, int smem_f
 
 extern "C" {
 
-int prosim_abi_version(void) { return 8; }
+int prosim_abi_version(void) { return 9; }
 int prosim_debug_scrub(float pattern, void* stream) {
   constexpr int BYTES = 226 * 1024;
   cudaError_t e = cudaFuncSetAttribute(scrub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES);

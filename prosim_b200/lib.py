@@ -8,7 +8,7 @@ from ctypes import POINTER, Structure, c_float, c_int, c_int32, c_size_t, c_void
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libprosim_b200.so')
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 SYMBOLS = (
     'prosim_abi_version', 'prosim_attn_layer_floats', 'prosim_pointnet_floats', 'prosim_head_floats',
