@@ -107,3 +107,21 @@ def test_synthetic_batch_layout():
     assert sorted(ex['init_obs']['agent_ids'][0]) == sorted(ex['prompt']['motion_pred']['agent_ids'][0])
     again = synthetic.make_batch(agents_per_scene=[5, 3], map_per_scene=[7, 9], steps=30, goal=True, permute_obs=True)
     assert torch.equal(torch.nan_to_num(again.extras['init_obs']['input']), torch.nan_to_num(ex['init_obs']['input']))
+
+
+def test_synthetic_inputs_reproduce_the_checksums_recorded_with_the_goldens():
+    """The golden-compared GPU tests build their inputs through helpers.make_case_batch, which insists on the checksum recorded
+    when the golden was generated (tests/golden/input_checksums.json).  Here: the generator reproduces every one of them on this
+    host, twice in a row, and the guarded map geometry equals a plain evaluation."""
+    import torch
+    from prosim_b200 import synthetic
+    from tests.helpers import BENCH_CASES, CASES, batch_sha1, make_case_batch
+    for name in list(CASES) + list(BENCH_CASES):
+        a = make_case_batch(name)
+        assert batch_sha1(a) == batch_sha1(make_case_batch(name)), name
+    g = torch.Generator().manual_seed(7)
+    centre = torch.rand(40, 2, generator=g) * 300.0 - 150.0
+    mhead = torch.rand(40, generator=g) * 6.0 - 3.0
+    kappa = (torch.rand(40, generator=g) - 0.5) * 0.08
+    for x, y in zip(synthetic._map_geometry(centre, mhead, kappa), synthetic._map_geometry_checked(centre, mhead, kappa)):
+        assert torch.equal(x, y)
