@@ -8,10 +8,6 @@ import torch
 from prosim_b200 import synthetic, weights
 from prosim_b200.model import ProSimB200
 from tests.helpers import CASES, load_golden
-if os.environ.get('PROBE_ORACLE'):
-    from oracle import ref_shim  # noqa: F401  (what tests/conftest.py and the test module import)
-    ref_shim.reference_available()
-    from oracle.prosim_oracle import ProSimOracle  # noqa: F401
 name = 'cfg1_a16_m256_s20'
 b = synthetic.make_batch(**CASES[name][0])
 h = hashlib.sha1()
@@ -26,8 +22,7 @@ walk(b.extras)
 sd = weights.random_state_dict(0)
 hw = hashlib.sha1()
 for k in sorted(sd): hw.update(sd[k].numpy().tobytes())
-from prosim_b200.config import get_config
-model = ProSimB200(get_config(opts=None), sd, device='cuda') if os.environ.get('PROBE_ORACLE') else ProSimB200(state_dict=sd, device='cuda')
+model = ProSimB200(state_dict=sd, device='cuda')
 with torch.no_grad():
     out = model.forward(b.to('cuda'), 'val')['motion_pred']
 mp = out['motion_pred'].cpu().numpy()
