@@ -20,3 +20,17 @@ def pytest_collection_modifyitems(config, items):
         for item in items:
             if 'ref_tree' in item.keywords:
                 item.add_marker(skip)
+
+
+@pytest.fixture(scope='session', autouse=True)
+def _warm_cpu_math():
+    """The first calls of torch's fp32 CPU transcendental kernels in a process were seen to return values a few ulp off on the GPU
+    box's host (profiles/r2_first_forward_probe.txt).  The synthetic generator guards itself; this warm-up
+    keeps the same effect away from whatever CPU-side reference computation happens to run first in a session."""
+    import torch
+    x = torch.linspace(-3.0, 3.0, 4096, dtype=torch.float32)
+    for _ in range(2):
+        for f in (torch.cos, torch.sin, torch.exp, torch.atan, torch.sqrt):
+            f(x.abs() if f is torch.sqrt else x)
+        torch.atan2(x, x.flip(0)), torch.cumsum(x.view(64, 64), dim=1), torch.norm(x.view(-1, 2), dim=-1)
+    yield
